@@ -1,0 +1,154 @@
+/* tmf.h -- C ABI of libtmf_sm100a.so: the B200 (sm_100a) kernels behind TransMF_AD's training hot path.
+ *
+ * The reference (Kateridge/TransMF_AD) has no native layer: its "FFI" for this path is the set of
+ * torch.nn / ATen calls made by models/networks.py and models/mymodel.py.  Each entry point below names the
+ * reference call site(s) it replaces.  Conventions:
+ *   - plain pointers and sizes only; every device buffer (incl. workspaces) is owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no internal synchronisation;
+ *   - return 0 on success, non-zero on error; tmf_last_error() returns a thread-local message;
+ *   - no CPU fallback and no other architecture: tmf_check_device() fails unless the device is cc 10.x;
+ *   - "groups": the two sNet towers (MRI, PET) have identical shapes but separate tensors, so the conv-stack
+ *     entry points take `ng` (1 or 2) and, for every tensor, a HOST array of `ng` device pointers; both
+ *     towers run in one launch (grid.z = group).
+ *   - activations are NDHWC ("channels-last-3d"): index ((((n*D + d)*H + h)*W + w)*C + c).
+ *   - bf16 buffers are passed as void*; fp32 as float*; per-channel statistics accumulate in double.
+ */
+#ifndef TMF_H_
+#define TMF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMF_MAX_GROUPS 2
+
+/* pooling modes fused behind BatchNorm + LeakyReLU (reference models/networks.py:25,34,43 MaxPool3d(2,2);
+ * :52 AvgPool3d(2,2); floor mode) */
+#define TMF_POOL_NONE 0
+#define TMF_POOL_MAX 1
+#define TMF_POOL_AVG 2
+
+/* conv implementation selector */
+#define TMF_CONV_AUTO 0
+#define TMF_CONV_DIRECT 1   /* CUDA-core implicit GEMM (bring-up / cross-check path) */
+#define TMF_CONV_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM */
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* library                                                                                                    */
+const char* tmf_last_error(void);
+int tmf_version(void);
+/* 0 iff the current CUDA device is a cc 10.x part (B200); otherwise an error (no fallback). */
+int tmf_check_device(void);
+/* number of kernel launches issued through this library by the calling process so far */
+int64_t tmf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* sNet conv stack -- replaces nn.Conv3d / nn.BatchNorm3d / nn.LeakyReLU / nn.MaxPool3d / nn.AvgPool3d of        */
+/* reference models/networks.py:21-53 (forward) and their autograd backward.                                   */
+
+/* fp32 master weight (Cout,Cin,k,k,k) -> bf16 wf[tap][Cout][Cin] (forward operand) and, if wd != NULL,
+ * bf16 wd[tap][Cin][Cout] with flipped taps (dgrad operand).  k = 3 (27 taps) or 1. */
+int tmf_pack_conv_weights(int ng, const float* const* w, void* const* wf, void* const* wd,
+                          int cout, int cin, int ksize, void* stream);
+
+/* conv1.0 (Cin = 1, 3x3x3, pad 1), fp32 input and weights, bf16 output y[B,D,H,W,Cout], per-channel
+ * sum / sum-of-squares of the stored (rounded) y into stats[2*Cout] (double; zeroed by the call).
+ * reference models/networks.py:22 */
+int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const float* const* bias,
+                  void* const* y, double* const* stats, int B, int D, int H, int W, int cout, void* stream);
+
+/* dW[Cout][27] (+ optionally dbias) of conv1.0 from dy (bf16) and x (fp32); dw is overwritten. */
+int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw,
+                    int B, int D, int H, int W, int cout, void* stream);
+
+/* 3x3x3 (pad 1) or 1x1x1 convolution, bf16 NDHWC input a[B,D,H,W,Cin], packed bf16 weights wf[tap][Cout][Cin],
+ * optional fp32 bias, bf16 output y[B,D,H,W,Cout], optional stats (as above; NULL array = none).
+ * Also used for dgrad (a = dy, wf = flipped/transposed pack, bias = stats = NULL).
+ * reference models/networks.py:28,31,37,40,46,49 */
+int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const float* const* bias,
+                   void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
+                   int ksize, int impl, void* stream);
+
+/* dW (fp32, reference layout (Cout,Cin,k,k,k), overwritten) = sum_v dy[v,co] * a[v+tap,ci]. */
+int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float* const* dw,
+                     int B, int D, int H, int W, int cin, int cout, int ksize, int impl, void* stream);
+
+/* BatchNorm statistics -> coefficients.  coef[4*C] = {scale = gamma*invstd, shift = beta - mean*scale, mean,
+ * invstd}.  training != 0: batch statistics from stats (biased variance), running_mean/var updated with
+ * momentum (unbiased variance) and num_batches_tracked += 1; training == 0: running statistics.
+ * reference models/networks.py:23,29,32,38,41,47,50 */
+int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamma, const float* const* beta,
+                    float* const* running_mean, float* const* running_var, int64_t* const* num_batches_tracked,
+                    float* const* coef, int C, int64_t count, float momentum, float eps, int training,
+                    void* stream);
+
+/* out = pool(leaky_relu(y*scale + shift)); out is bf16, or fp32 when out_fp32 != 0.  Floor-mode 2x2x2 pools. */
+int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, void* const* out, int out_fp32,
+                        int B, int D, int H, int W, int C, int pool, float slope, void* stream);
+
+/* backward, pass 1: sums[2*C] (double, zeroed by the call) = {sum dz, sum dz*xhat} with
+ * dz = unpool(dout) * leaky_relu'(z) (max-pool routes to the first maximum in (d,h,w) scan order). */
+int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, const void* const* y,
+                               const float* const* coef, double* const* sums, int B, int D, int H, int W, int C,
+                               int pool, float slope, void* stream);
+
+/* backward, between the passes: dgamma, dbeta (fp32, overwritten), dbias (conv bias grad; may be NULL),
+ * bcoef[2*C] = {mean(dz), mean(dz*xhat)} (zeros in eval mode). */
+int tmf_bn_bwd_finalize(int ng, const double* const* sums, const float* const* coef, float* const* dgamma,
+                        float* const* dbeta, float* const* dbias, float* const* bcoef, int C, int64_t count,
+                        int training, void* stream);
+
+/* backward, pass 2: dy (bf16 [B,D,H,W,C]) = scale * (dz - mean(dz) - xhat * mean(dz*xhat)). */
+int tmf_bn_act_pool_bwd_apply(int ng, const void* const* dout, int dout_fp32, const void* const* y,
+                              const float* const* coef, const float* const* bcoef, void* const* dy,
+                              int B, int D, int H, int W, int C, int pool, float slope, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* fusion transformer / heads (fp32 tensors, row-major)                                                        */
+
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias) + residual; act: 0 none, 1 exact-erf GELU; bias/residual may be NULL.
+ * If pre != NULL the pre-activation is also stored there.   reference nn.Linear at models/networks.py:128,132,
+ * 149,150,153; models/mymodel.py:190-194 */
+int tmf_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* pre,
+                   int M, int K, int N, int act, void* stream);
+/* dx[M,K] (+)= dy[M,N] . w[N,K] */
+int tmf_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, int accumulate, void* stream);
+/* dw[N,K] = dy^T . x ; dbias[N] = column sums of dy (dbias may be NULL); both overwritten */
+int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta (+ residual); saves mean / rstd per row.  reference models/networks.py:117,219 */
+int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                      float* mean, float* rstd, int rows, int dim, float eps, void* stream);
+/* dx (+)= LN backward; dgamma / dbeta are ACCUMULATED into (caller zeroes). */
+int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* stream);
+
+/* dx = dy * gelu'(pre)  (exact erf form, reference models/networks.py:129) */
+int tmf_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream);
+
+/* multi-head cross attention on short sequences.  q[B,Nq,h*dh], kv[B,Nk,2*h*dh] (k then v),
+ * out[B,Nq,h*dh], lse[B,h,Nq] (log-sum-exp of the scaled scores).  reference models/networks.py:166-174 */
+int tmf_attn_fwd(const float* q, const float* kv, float* out, float* lse, int B, int Nq, int Nk, int heads,
+                 int dh, float scale, void* stream);
+int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float* out, const float* lse,
+                 float* dq, float* dkv, int B, int Nq, int Nk, int heads, int dh, float scale, void* stream);
+
+/* token pooling over n: mean[B,C], max[B,C] (+ argmax, first maximum) of x[B,N,C]; either output may be NULL.
+ * reference models/networks.py:264-269 (GAP / GMP), models/mymodel.py:193 (AdaptiveAvgPool3d(1)) */
+int tmf_token_pool_fwd(const float* x, float* mean, float* max, int32_t* argmax, int B, int N, int C, void* stream);
+/* dx[B,N,C] (+)= dmean/N + onehot(argmax) * dmax; dmean or dmax may be NULL */
+int tmf_token_pool_bwd(const float* dmean, const float* dmax, const int32_t* argmax, float* dx, int B, int N, int C,
+                       int accumulate, void* stream);
+
+/* y = alpha * (alpha_dev ? *alpha_dev : 1) * x.  Gradient-reversal backward uses alpha = -1 with the caller's
+ * 1-element device tensor lambda (no host sync), or alpha = -lambda.  reference
+ * models/gradient_reversal/functional.py:11-16 */
+int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMF_H_ */

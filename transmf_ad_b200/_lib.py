@@ -1,0 +1,113 @@
+"""ctypes binding of libtmf_sm100a.so (declared in include/tmf.h).
+
+There is deliberately NO fallback: if the shared library is missing, or the device is not a cc 10.x part, every
+op raises.  Host code passes raw device pointers (``tensor.data_ptr()``) and the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtmf_sm100a.so")
+
+POOL_NONE, POOL_MAX, POOL_AVG = 0, 1, 2
+CONV_AUTO, CONV_DIRECT, CONV_UMMA = 0, 1, 2
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_pp = C.POINTER(C.c_void_p)          # host array of device pointers
+
+# name -> argtypes  (must mirror include/tmf.h; tests/test_abi.py checks every symbol is exported)
+SIGNATURES = {
+    "tmf_pack_conv_weights": [_i, _pp, _pp, _pp, _i, _i, _i, _vp],
+    "tmf_conv1_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv1_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv3d_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv3d_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_bn_finalize": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i64, _f, _f, _i, _vp],
+    "tmf_bn_act_pool_fwd": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_bn_act_pool_bwd_reduce": [_i, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_bn_bwd_finalize": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i64, _i, _vp],
+    "tmf_bn_act_pool_bwd_apply": [_i, _pp, _i, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "tmf_linear_dgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "tmf_linear_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tmf_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "tmf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tmf_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
+    "tmf_attn_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_token_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tmf_token_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
+}
+PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
+         "tmf_launch_count": (_i64, [])}
+
+_lib = None
+_device_checked = False
+
+
+def load():
+    """dlopen the library (no GPU needed); raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m transmf_ad_b200.build` (there is no fallback path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        for name, (res, argtypes) in PLAIN.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = res
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().tmf_last_error().decode()
+
+
+def launch_count():
+    return int(load().tmf_launch_count())
+
+
+def _require_device():
+    global _device_checked
+    if not _device_checked:
+        if not torch.cuda.is_available():
+            raise RuntimeError("transmf_ad_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if load().tmf_check_device() != 0:
+            raise RuntimeError(last_error())
+        _device_checked = True
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device pointer of a tensor (or NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ptrs(ts):
+    """host array of device pointers, one per group; ``None`` -> NULL array."""
+    if ts is None:
+        return C.cast(None, _pp)
+    arr = (C.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
+    return C.cast(arr, _pp)
+
+
+def call(name, *args):
+    """Invoke an entry point on the current stream; raises RuntimeError(tmf_last_error()) on failure."""
+    _require_device()
+    rc = getattr(load(), name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")

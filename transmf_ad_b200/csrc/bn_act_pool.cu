@@ -1,0 +1,393 @@
+// bn_act_pool.cu -- the memory-bound passes between the convolutions of sNet:
+//   BatchNorm3d (train / eval) -> LeakyReLU(0.01) -> {none | MaxPool3d(2,2) | AvgPool3d(2,2)}, forward and backward,
+//   on NDHWC bf16 tensors, 16-byte vectorised (8 channels per thread), per-channel reductions in double.
+// Reference semantics: models/networks.py:23-25, 29-34, 38-43, 47-52 (nn.BatchNorm3d eps 1e-5 momentum 0.1, biased
+// variance for normalisation / unbiased into running_var; nn.LeakyReLU() slope 0.01; floor-mode pools; max-pool
+// gradient to the first maximum in (d,h,w) scan order).
+#include "common.cuh"
+
+namespace tmf {
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const float> gamma,
+                                   GroupPtr<const float> beta, GroupPtr<float> rmean, GroupPtr<float> rvar,
+                                   GroupPtr<int64_t> nbt, GroupPtr<float> coef, int C, double count, float momentum,
+                                   float eps, int training) {
+  const int g = blockIdx.z;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt.p[g] != nullptr) nbt.p[g][0] += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = stats.p[g][c] / count;
+    double v = stats.p[g][C + c] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (rmean.p[g] != nullptr) {
+      const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+      rmean.p[g][c] = (1.f - momentum) * rmean.p[g][c] + momentum * mean;
+      rvar.p[g][c] = (1.f - momentum) * rvar.p[g][c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rmean.p[g][c];
+    var = rvar.p[g][c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float scale = gamma.p[g][c] * invstd;
+  coef.p[g][c] = scale;
+  coef.p[g][C + c] = beta.p[g][c] - mean * scale;
+  coef.p[g][2 * C + c] = mean;
+  coef.p[g][3 * C + c] = invstd;
+}
+
+__global__ void bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
+                                       GroupPtr<float> dbeta, GroupPtr<float> dbias, GroupPtr<float> bcoef, int C,
+                                       double count, int training) {
+  const int g = blockIdx.z;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums.p[g][c], s2 = sums.p[g][C + c];
+  dgamma.p[g][c] = (float)s2;
+  dbeta.p[g][c] = (float)s1;
+  if (training) {
+    bcoef.p[g][c] = (float)(s1 / count);
+    bcoef.p[g][C + c] = (float)(s2 / count);
+    // train-mode BatchNorm cancels the conv bias exactly: sum_v dy = 0
+    if (dbias.p[g] != nullptr) dbias.p[g][c] = 0.f;
+  } else {
+    bcoef.p[g][c] = 0.f;
+    bcoef.p[g][C + c] = 0.f;
+    if (dbias.p[g] != nullptr) dbias.p[g][c] = coef.p[g][c] * (float)s1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct ActPoolArgs {
+  GroupPtr<const __nv_bfloat16> y;    // pre-BN conv output [B,D,H,W,C]
+  GroupPtr<const float> coef;         // scale, shift, mean, invstd
+  GroupPtr<const float> bcoef;        // mean(dz), mean(dz*xhat)          (bwd apply)
+  GroupPtr<void> out;                 // fwd output (bf16 or fp32)
+  GroupPtr<const void> dout;          // bwd: gradient w.r.t. fwd output (bf16 or fp32)
+  GroupPtr<__nv_bfloat16> dy;         // bwd apply output
+  GroupPtr<double> sums;              // bwd reduce output
+  int B, D, H, W, C, pool, fp32io;
+  int Do, Ho, Wo;                     // forward output dims (floor)
+  int Dc, Hc, Wc;                     // ceil dims (windows that touch any input voxel)
+  float slope;
+};
+
+__device__ __forceinline__ void load8f(const void* base, int64_t elem_off, int fp32, float* f) {
+  if (fp32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off), f);
+  }
+}
+__device__ __forceinline__ void store8f(void* base, int64_t elem_off, int fp32, const float* f) {
+  if (fp32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(f[0], f[1], f[2], f[3]);
+    p[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
+  const int g = blockIdx.z;
+  const int CQ = p.C >> 3;
+  const int64_t total = (int64_t)p.B * p.Do * p.Ho * p.Wo * CQ;
+  const __nv_bfloat16* yg = p.y.p[g];
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % CQ);
+    int64_t r = idx / CQ;
+    const int wo = (int)(r % p.Wo); r /= p.Wo;
+    const int ho = (int)(r % p.Ho); r /= p.Ho;
+    const int dd = (int)(r % p.Do);
+    const int n = (int)(r / p.Do);
+    const int c0 = cq * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = p.coef.p[g][c0 + j]; sh[j] = p.coef.p[g][p.C + c0 + j]; }
+    float o[8];
+    if (p.pool == TMF_POOL_NONE) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(yg + ((((int64_t)n * p.D + dd) * p.H + ho) * p.W + wo) * p.C + c0), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        o[j] = z > 0.f ? z : z * p.slope;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (p.pool == TMF_POOL_MAX) ? -INFINITY : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int di = 2 * dd + (q >> 2), hi = 2 * ho + ((q >> 1) & 1), wi = 2 * wo + (q & 1);
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(yg + ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float a = z > 0.f ? z : z * p.slope;
+          o[j] = (p.pool == TMF_POOL_MAX) ? fmaxf(o[j], a) : o[j] + a;
+        }
+      }
+      if (p.pool == TMF_POOL_AVG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] *= 0.125f;
+      }
+    }
+    store8f(p.out.p[g], ((((int64_t)n * p.Do + dd) * p.Ho + ho) * p.Wo + wo) * p.C + c0, p.fp32io, o);
+  }
+}
+
+// Backward over 2x2x2 windows (or single voxels when pool == NONE).  REDUCE: accumulate sum dz, sum dz*xhat.
+// APPLY: write dy = scale * (dz - m1 - xhat*m2) for every existing input voxel (incl. those dropped by floor pooling).
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
+  const int g = blockIdx.z;
+  extern __shared__ float red[];  // [2][C] (REDUCE only)
+  const int CQ = p.C >> 3;
+  if (!APPLY) {
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int Dw = APPLY ? p.Dc : p.Do, Hw = APPLY ? p.Hc : p.Ho, Ww = APPLY ? p.Wc : p.Wo;
+  const int64_t total = (int64_t)p.B * Dw * Hw * Ww * CQ;
+  const __nv_bfloat16* yg = p.y.p[g];
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  int last_cq = -1;
+  const int npos = (p.pool == TMF_POOL_NONE) ? 1 : 8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % CQ);
+    int64_t r = idx / CQ;
+    const int ww = (int)(r % Ww); r /= Ww;
+    const int hw = (int)(r % Hw); r /= Hw;
+    const int dw = (int)(r % Dw);
+    const int n = (int)(r / Dw);
+    const int c0 = cq * 8;
+    if (!APPLY && cq != last_cq) {
+      if (last_cq >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&red[last_cq * 8 + j], s1[j]);
+          atomicAdd(&red[p.C + last_cq * 8 + j], s2[j]);
+          s1[j] = 0.f; s2[j] = 0.f;
+        }
+      }
+      last_cq = cq;
+    }
+    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = p.coef.p[g][c0 + j];
+      sh[j] = p.coef.p[g][p.C + c0 + j];
+      mu[j] = p.coef.p[g][2 * p.C + c0 + j];
+      is[j] = p.coef.p[g][3 * p.C + c0 + j];
+      if (APPLY) { m1[j] = p.bcoef.p[g][c0 + j]; m2[j] = p.bcoef.p[g][p.C + c0 + j]; }
+    }
+    const bool win_ok = (p.pool == TMF_POOL_NONE) || (dw < p.Do && hw < p.Ho && ww < p.Wo);
+    float go[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) go[j] = 0.f;
+    if (win_ok) {
+      const int64_t ooff = (p.pool == TMF_POOL_NONE)
+                               ? ((((int64_t)n * p.D + dw) * p.H + hw) * p.W + ww) * p.C + c0
+                               : ((((int64_t)n * p.Do + dw) * p.Ho + hw) * p.Wo + ww) * p.C + c0;
+      load8f(p.dout.p[g], ooff, p.fp32io, go);
+    }
+    // pass 1 (max only): locate the first maximum of the activation per channel
+    int amax[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax[j] = 0;
+    if (p.pool == TMF_POOL_MAX && win_ok) {
+      float best[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int di = 2 * dw + (q >> 2), hi = 2 * hw + ((q >> 1) & 1), wi = 2 * ww + (q & 1);
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(yg + ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float a = z > 0.f ? z : z * p.slope;
+          if (a > best[j]) { best[j] = a; amax[j] = q; }
+        }
+      }
+    }
+    // pass 2: per position dz -> reduce or apply
+    for (int q = 0; q < npos; ++q) {
+      int di, hi, wi;
+      if (p.pool == TMF_POOL_NONE) { di = dw; hi = hw; wi = ww; }
+      else { di = 2 * dw + (q >> 2); hi = 2 * hw + ((q >> 1) & 1); wi = 2 * ww + (q & 1); }
+      if (di >= p.D || hi >= p.H || wi >= p.W) continue;
+      const int64_t ioff = ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(yg + ioff), f);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float xhat = (f[j] - mu[j]) * is[j];
+        float gsel;
+        if (p.pool == TMF_POOL_MAX) gsel = (win_ok && amax[j] == q) ? go[j] : 0.f;
+        else if (p.pool == TMF_POOL_AVG) gsel = go[j] * 0.125f;
+        else gsel = go[j];
+        const float dz = z > 0.f ? gsel : gsel * p.slope;
+        if (APPLY) {
+          o[j] = sc[j] * (dz - m1[j] - xhat * m2[j]);
+        } else {
+          s1[j] += dz;
+          s2[j] = fmaf(dz, xhat, s2[j]);
+        }
+      }
+      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p[g] + ioff) = pack8(o);
+    }
+  }
+  if (!APPLY) {
+    if (last_cq >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[last_cq * 8 + j], s1[j]);
+        atomicAdd(&red[p.C + last_cq * 8 + j], s2[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
+  }
+}
+
+static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool, float slope, int fp32io) {
+  TMF_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "bn_act_pool: C must be a multiple of 8 in [8,1024] (got %d)", C);
+  TMF_REQUIRE(pool == TMF_POOL_NONE || pool == TMF_POOL_MAX || pool == TMF_POOL_AVG, "bn_act_pool: bad pool mode %d",
+              pool);
+  p.B = B; p.D = D; p.H = H; p.W = W; p.C = C; p.pool = pool; p.slope = slope; p.fp32io = fp32io;
+  if (pool == TMF_POOL_NONE) {
+    p.Do = p.Dc = D; p.Ho = p.Hc = H; p.Wo = p.Wc = W;
+  } else {
+    p.Do = D / 2; p.Ho = H / 2; p.Wo = W / 2;
+    p.Dc = (D + 1) / 2; p.Hc = (H + 1) / 2; p.Wc = (W + 1) / 2;
+    TMF_REQUIRE(p.Do > 0 && p.Ho > 0 && p.Wo > 0, "bn_act_pool: volume %dx%dx%d too small to pool", D, H, W);
+  }
+  return 0;
+}
+
+static int pick_grid(int64_t total_threads, int CQ) {
+  int64_t blocks = (total_threads + 255) / 256;
+  const int64_t cap = 148 * 16;
+  if (blocks > cap) blocks = cap;
+  // keep (gridDim.x * 256) a multiple of CQ so that a thread's channel chunk is loop-invariant
+  int64_t a = 256, b = CQ;
+  while (b) { int64_t t = a % b; a = b; b = t; }
+  const int64_t mult = CQ / a;
+  blocks = ((blocks + mult - 1) / mult) * mult;
+  return (int)blocks;
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+extern "C" {
+
+int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamma, const float* const* beta,
+                    float* const* running_mean, float* const* running_var, int64_t* const* num_batches_tracked,
+                    float* const* coef, int C, int64_t count, float momentum, float eps, int training, void* stream) {
+  TMF_CHECK_NG(ng);
+  GroupPtr<const double> gs;
+  GroupPtr<const float> gg, gb;
+  GroupPtr<float> grm, grv, gc;
+  GroupPtr<int64_t> gn;
+  if (!load_group(gs, stats, ng, training != 0, "stats") || !load_group(gg, gamma, ng, true, "gamma") ||
+      !load_group(gb, beta, ng, true, "beta") || !load_group(grm, running_mean, ng, training == 0, "running_mean") ||
+      !load_group(grv, running_var, ng, training == 0, "running_var") ||
+      !load_group(gn, num_batches_tracked, ng, false, "num_batches_tracked") || !load_group(gc, coef, ng, true, "coef"))
+    return 1;
+  TMF_REQUIRE(count > 0, "bn_finalize: count must be positive");
+  dim3 grid(ceil_div(C, 128), 1, ng);
+  bn_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
+                                                             eps, training);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, void* const* out, int out_fp32, int B,
+                        int D, int H, int W, int C, int pool, float slope, void* stream) {
+  TMF_CHECK_NG(ng);
+  ActPoolArgs p{};
+  if (fill_args(p, B, D, H, W, C, pool, slope, out_fp32)) return 1;
+  if (!load_group(p.y, (const __nv_bfloat16* const*)y, ng, true, "y") || !load_group(p.coef, coef, ng, true, "coef") ||
+      !load_group(p.out, (void* const*)out, ng, true, "out"))
+    return 1;
+  const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
+  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  bn_act_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, const void* const* y,
+                               const float* const* coef, double* const* sums, int B, int D, int H, int W, int C,
+                               int pool, float slope, void* stream) {
+  TMF_CHECK_NG(ng);
+  ActPoolArgs p{};
+  if (fill_args(p, B, D, H, W, C, pool, slope, dout_fp32)) return 1;
+  if (!load_group(p.y, (const __nv_bfloat16* const*)y, ng, true, "y") || !load_group(p.coef, coef, ng, true, "coef") ||
+      !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
+    return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(sums[g], 0, sizeof(double) * 2 * C, st));
+  const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
+  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  bn_act_pool_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), st>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_bwd_finalize(int ng, const double* const* sums, const float* const* coef, float* const* dgamma,
+                        float* const* dbeta, float* const* dbias, float* const* bcoef, int C, int64_t count,
+                        int training, void* stream) {
+  TMF_CHECK_NG(ng);
+  GroupPtr<const double> gs;
+  GroupPtr<const float> gc;
+  GroupPtr<float> gdg, gdb, gdbias, gbc;
+  if (!load_group(gs, sums, ng, true, "sums") || !load_group(gc, coef, ng, true, "coef") ||
+      !load_group(gdg, dgamma, ng, true, "dgamma") || !load_group(gdb, dbeta, ng, true, "dbeta") ||
+      !load_group(gdbias, dbias, ng, false, "dbias") || !load_group(gbc, bcoef, ng, true, "bcoef"))
+    return 1;
+  dim3 grid(ceil_div(C, 128), 1, ng);
+  bn_bwd_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
+                                                                 training);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_act_pool_bwd_apply(int ng, const void* const* dout, int dout_fp32, const void* const* y,
+                              const float* const* coef, const float* const* bcoef, void* const* dy, int B, int D,
+                              int H, int W, int C, int pool, float slope, void* stream) {
+  TMF_CHECK_NG(ng);
+  ActPoolArgs p{};
+  if (fill_args(p, B, D, H, W, C, pool, slope, dout_fp32)) return 1;
+  if (!load_group(p.y, (const __nv_bfloat16* const*)y, ng, true, "y") || !load_group(p.coef, coef, ng, true, "coef") ||
+      !load_group(p.bcoef, bcoef, ng, true, "bcoef") ||
+      !load_group(p.dout, (const void* const*)dout, ng, true, "dout") ||
+      !load_group(p.dy, (__nv_bfloat16* const*)dy, ng, true, "dy"))
+    return 1;
+  const int64_t total = (int64_t)B * p.Dc * p.Hc * p.Wc * (C / 8);
+  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  bn_act_pool_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// common.cuh -- shared helpers for libtmf_sm100a (error plumbing, grouped pointers, bf16 packing).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tmf.h"
+
+namespace tmf {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// One pointer per group (sNet tower); passed to kernels by value, indexed with blockIdx.z.
+template <typename T>
+struct GroupPtr {
+  T* p[TMF_MAX_GROUPS];
+};
+
+template <typename T>
+static inline bool load_group(GroupPtr<T>& g, T* const* host, int ng, bool required, const char* name) {
+  for (int i = 0; i < TMF_MAX_GROUPS; ++i) g.p[i] = nullptr;
+  if (host == nullptr) {
+    if (required) { set_error("%s: NULL pointer array", name); return false; }
+    return true;
+  }
+  for (int i = 0; i < ng; ++i) {
+    g.p[i] = host[i];
+    if (required && host[i] == nullptr) { set_error("%s[%d]: NULL device pointer", name, i); return false; }
+  }
+  return true;
+}
+
+#define TMF_CHECK_NG(ng)                                                          \
+  do {                                                                            \
+    if ((ng) < 1 || (ng) > TMF_MAX_GROUPS) {                                      \
+      tmf::set_error("%s: ng=%d out of range [1,%d]", __func__, (ng), TMF_MAX_GROUPS); \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+
+#define TMF_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      tmf::set_error(__VA_ARGS__);        \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+#define TMF_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      tmf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 2;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+#define TMF_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      tmf::set_error("%s:%d launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 3;                                                                         \
+    }                                                                                   \
+    tmf::count_launch();                                                                \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]);
+  v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]);
+  v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace tmf

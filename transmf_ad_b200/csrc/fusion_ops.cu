@@ -1,0 +1,602 @@
+// fusion_ops.cu -- kernels of the cross-modal fusion transformer and the small heads (fp32 tensors):
+//   Linear forward / dgrad / wgrad (one tiled GEMM with fused bias, exact GELU and residual epilogues),
+//   LayerNorm fwd/bwd (warp per row, float4), GELU backward, short-sequence multi-head cross attention fwd/bwd
+//   (K/V resident in shared memory, warp-level softmax reductions), token pooling (GAP + GMP) and the
+//   gradient-reversal scale.  Reference: models/networks.py:114-175, 215-281; models/gradient_reversal/functional.py.
+#include "common.cuh"
+
+namespace tmf {
+
+// ------------------------------------------------------------------------------------------------------------
+// C[M,N] (+)= epilogue( sum_k A(m,k) * B(k,n) ),  A(m,k) = A[m*sAm + k*sAk],  B(k,n) = B[k*sBk + n*sBn]
+// ------------------------------------------------------------------------------------------------------------
+constexpr int G_TM = 64, G_TN = 64, G_TK = 16, G_PAD = 4;
+
+struct GemmArgs {
+  const float* A; const float* B; float* C;
+  const float* bias; const float* residual; float* pre;
+  int M, N, K;
+  int64_t sAm, sAk, sBk, sBn;
+  int act, accumulate;
+};
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
+  __shared__ __align__(16) float As[G_TK][G_TM + G_PAD];
+  __shared__ __align__(16) float Bs[G_TK][G_TN + G_PAD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * G_TM, n0 = blockIdx.x * G_TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (p.sAk == 1);
+  const bool b_kfast = (p.sBk == 1);
+  for (int k0 = 0; k0 < p.K; k0 += G_TK) {
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int mm, kk;
+      if (a_kfast) { kk = tid & 15; mm = (tid >> 4) + 16 * i; } else { mm = tid & 63; kk = (tid >> 6) + 4 * i; }
+      const int m = m0 + mm, k = k0 + kk;
+      ra[i] = (m < p.M && k < p.K) ? __ldg(p.A + m * p.sAm + k * p.sAk) : 0.f;
+      int nn, kb;
+      if (b_kfast) { kb = tid & 15; nn = (tid >> 4) + 16 * i; } else { nn = tid & 63; kb = (tid >> 6) + 4 * i; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      rb[i] = (n < p.N && k2 < p.K) ? __ldg(p.B + k2 * p.sBk + n * p.sBn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (a_kfast) As[tid & 15][(tid >> 4) + 16 * i] = ra[i]; else As[(tid >> 6) + 4 * i][tid & 63] = ra[i];
+      if (b_kfast) Bs[tid & 15][(tid >> 4) + 16 * i] = rb[i]; else Bs[(tid >> 6) + 4 * i][tid & 63] = rb[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < G_TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      const int64_t o = (int64_t)m * p.N + n;
+      if (p.pre) p.pre[o] = v;
+      if (p.act == 1) v = gelu_exact(v);
+      if (p.residual) v += p.residual[o];
+      if (p.accumulate) v += p.C[o];
+      p.C[o] = v;
+    }
+  }
+}
+
+// column sums: out[n] = sum_m x[m,n]
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+  __shared__ float part[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r = threadIdx.x >> 5;
+  float s = 0.f;
+  if (n < N)
+    for (int m = r; m < M; m += 8) s += x[(int64_t)m * N + n];
+  part[r][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (r == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
+    out[n] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, dim % 4 == 0, dim <= 1024
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;  // float4 per lane
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ residual, float* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = dim >> 2;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * dim);
+    float4 v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) { v[i] = xr[c]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+    }
+    const float mean = warp_sum(s) / dim;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    float4* yr = reinterpret_cast<float4*>(y + (int64_t)row * dim);
+    const float4* rr = residual ? reinterpret_cast<const float4*>(residual + (int64_t)row * dim) : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 gm = reinterpret_cast<const float4*>(gamma)[c];
+        const float4 bt = reinterpret_cast<const float4*>(beta)[c];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+        o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+        o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+        o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+        if (rr) { const float4 r4 = rr[c]; o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+        yr[c] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim, int accumulate) {
+  extern __shared__ float sm[];  // [2][dim]
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv = dim >> 2;
+  float4 ag[LN_MAXV], ab[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * dim);
+    const float4* gr = reinterpret_cast<const float4*>(dy + (int64_t)row * dim);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAXV], gg[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 xv = xr[c], gv = gr[c], gm = reinterpret_cast<const float4*>(gamma)[c];
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gg[i] = make_float4(gv.x * gm.x, gv.y * gm.y, gv.z * gm.z, gv.w * gm.w);
+        s1 += gg[i].x + gg[i].y + gg[i].z + gg[i].w;
+        s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
+        ag[i].x += gv.x * xh[i].x; ag[i].y += gv.y * xh[i].y; ag[i].z += gv.z * xh[i].z; ag[i].w += gv.w * xh[i].w;
+        ab[i].x += gv.x; ab[i].y += gv.y; ab[i].z += gv.z; ab[i].w += gv.w;
+      }
+    }
+    s1 = warp_sum(s1) / dim;
+    s2 = warp_sum(s2) / dim;
+    float4* dr = reinterpret_cast<float4*>(dx + (int64_t)row * dim);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (gg[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (gg[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (gg[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (gg[i].w - s1 - xh[i].w * s2);
+        if (accumulate) { const float4 old = dr[c]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        dr[c] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) {
+      atomicAdd(&sm[c * 4 + 0], ag[i].x); atomicAdd(&sm[c * 4 + 1], ag[i].y);
+      atomicAdd(&sm[c * 4 + 2], ag[i].z); atomicAdd(&sm[c * 4 + 3], ag[i].w);
+      atomicAdd(&sm[dim + c * 4 + 0], ab[i].x); atomicAdd(&sm[dim + c * 4 + 1], ab[i].y);
+      atomicAdd(&sm[dim + c * 4 + 2], ab[i].z); atomicAdd(&sm[dim + c * 4 + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sm[i]);
+    atomicAdd(&dbeta[i], sm[dim + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gelu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ pre, float4* __restrict__ dx,
+                                int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = dy[i], x = pre[i];
+    float4 o;
+    const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
+    float os[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float cdf = 0.5f * (1.f + erff(xs[j] * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * __expf(-0.5f * xs[j] * xs[j]);
+      os[j] = gs[j] * (cdf + xs[j] * pdf);
+    }
+    o.x = os[0]; o.y = os[1]; o.z = os[2]; o.w = os[3];
+    dx[i] = o;
+  }
+}
+
+__global__ void scale_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha,
+                             const float* __restrict__ alpha_dev, int64_t n) {
+  if (alpha_dev != nullptr) alpha *= alpha_dev[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// attention.  grid = (B*heads, row splits); K,V (fwd, dq) or Q,dO (dk/dv) of one (batch, head) live in smem.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int AT_WARPS = 8;
+constexpr int AT_ROWS = 32;  // rows per block
+
+struct AttnArgs {
+  const float* q; const float* kv; const float* out; const float* lse_in; const float* dout;
+  float* o; float* lse; float* dq; float* dkv;
+  int B, Nq, Nk, heads, dh;
+  float scale;
+};
+
+// smem: Ks[Nk][dh+1], Vs[Nk][dh+1], sc[AT_WARPS][Nk], qs[AT_WARPS][dh]
+__global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(AttnArgs p) {
+  extern __shared__ float sm[];
+  const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
+  float* Ks = sm;
+  float* Vs = Ks + p.Nk * ld;
+  float* sc = Vs + p.Nk * ld;
+  float* qs = sc + AT_WARPS * p.Nk;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.Nk * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    const float* row = p.kv + ((int64_t)b * p.Nk + j) * 2 * inner;
+    Ks[j * ld + d] = row[h * dh + d];
+    Vs[j * ld + d] = row[inner + h * dh + d];
+  }
+  __syncthreads();
+  const int r0 = blockIdx.y * AT_ROWS;
+  for (int i = r0 + warp; i < min(p.Nq, r0 + AT_ROWS); i += AT_WARPS) {
+    const float* qrow = p.q + ((int64_t)b * p.Nq + i) * inner + h * dh;
+    for (int d = lane; d < dh; d += 32) qs[warp * dh + d] = qrow[d];
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < p.Nk; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < dh; ++d) s = fmaf(qs[warp * dh + d], Ks[j * ld + d], s);
+      s *= p.scale;
+      sc[warp * p.Nk + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < p.Nk; j += 32) {
+      const float e = __expf(sc[warp * p.Nk + j] - mx);
+      sc[warp * p.Nk + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < p.Nk; ++j) o = fmaf(sc[warp * p.Nk + j], Vs[j * ld + d], o);
+      p.o[((int64_t)b * p.Nq + i) * inner + h * dh + d] = o * inv;
+    }
+    if (lane == 0) p.lse[((int64_t)b * p.heads + h) * p.Nq + i] = mx + __logf(sum);
+    __syncwarp();
+  }
+}
+
+// dq: same staging as forward.  extra smem: dos[AT_WARPS][dh]
+__global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dq_kernel(AttnArgs p) {
+  extern __shared__ float sm[];
+  const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
+  float* Ks = sm;
+  float* Vs = Ks + p.Nk * ld;
+  float* sc = Vs + p.Nk * ld;
+  float* qs = sc + AT_WARPS * p.Nk;
+  float* dos = qs + AT_WARPS * dh;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.Nk * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    const float* row = p.kv + ((int64_t)b * p.Nk + j) * 2 * inner;
+    Ks[j * ld + d] = row[h * dh + d];
+    Vs[j * ld + d] = row[inner + h * dh + d];
+  }
+  __syncthreads();
+  const int r0 = blockIdx.y * AT_ROWS;
+  for (int i = r0 + warp; i < min(p.Nq, r0 + AT_ROWS); i += AT_WARPS) {
+    const int64_t ro = ((int64_t)b * p.Nq + i) * inner + h * dh;
+    float dsum = 0.f;
+    for (int d = lane; d < dh; d += 32) {
+      qs[warp * dh + d] = p.q[ro + d];
+      const float g = p.dout[ro + d];
+      dos[warp * dh + d] = g;
+      dsum = fmaf(g, p.out[ro + d], dsum);
+    }
+    const float Di = warp_sum(dsum);
+    const float lse = p.lse_in[((int64_t)b * p.heads + h) * p.Nq + i];
+    __syncwarp();
+    for (int j = lane; j < p.Nk; j += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(qs[warp * dh + d], Ks[j * ld + d], s);
+        dp = fmaf(dos[warp * dh + d], Vs[j * ld + d], dp);
+      }
+      const float pj = __expf(s * p.scale - lse);
+      sc[warp * p.Nk + j] = pj * (dp - Di);
+    }
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < p.Nk; ++j) a = fmaf(sc[warp * p.Nk + j], Ks[j * ld + d], a);
+      p.dq[ro + d] = a * p.scale;
+    }
+    __syncwarp();
+  }
+}
+
+// dk, dv: smem Qs[Nq][dh+1], dOs[Nq][dh+1], lses[Nq], Ds[Nq], pw[AT_WARPS][Nq], dsw[AT_WARPS][Nq], ks/vs[AT_WARPS][dh]
+__global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dkv_kernel(AttnArgs p) {
+  extern __shared__ float sm[];
+  const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
+  float* Qs = sm;
+  float* dOs = Qs + p.Nq * ld;
+  float* lses = dOs + p.Nq * ld;
+  float* Ds = lses + p.Nq;
+  float* pw = Ds + p.Nq;
+  float* dsw = pw + AT_WARPS * p.Nq;
+  float* ks = dsw + AT_WARPS * p.Nq;
+  float* vs = ks + AT_WARPS * dh;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.Nq * dh; i += blockDim.x) {
+    const int r = i / dh, d = i % dh;
+    const int64_t off = ((int64_t)b * p.Nq + r) * inner + h * dh + d;
+    Qs[r * ld + d] = p.q[off];
+    dOs[r * ld + d] = p.dout[off];
+  }
+  for (int r = threadIdx.x; r < p.Nq; r += blockDim.x) lses[r] = p.lse_in[((int64_t)b * p.heads + h) * p.Nq + r];
+  __syncthreads();
+  for (int r = warp; r < p.Nq; r += AT_WARPS) {
+    float s = 0.f;
+    for (int d = lane; d < dh; d += 32)
+      s = fmaf(dOs[r * ld + d], p.out[((int64_t)b * p.Nq + r) * inner + h * dh + d], s);
+    s = warp_sum(s);
+    if (lane == 0) Ds[r] = s;
+  }
+  __syncthreads();
+  const int j0 = blockIdx.y * AT_ROWS;
+  for (int j = j0 + warp; j < min(p.Nk, j0 + AT_ROWS); j += AT_WARPS) {
+    const float* row = p.kv + ((int64_t)b * p.Nk + j) * 2 * inner;
+    for (int d = lane; d < dh; d += 32) {
+      ks[warp * dh + d] = row[h * dh + d];
+      vs[warp * dh + d] = row[inner + h * dh + d];
+    }
+    __syncwarp();
+    for (int i = lane; i < p.Nq; i += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(Qs[i * ld + d], ks[warp * dh + d], s);
+        dp = fmaf(dOs[i * ld + d], vs[warp * dh + d], dp);
+      }
+      const float pij = __expf(s * p.scale - lses[i]);
+      pw[warp * p.Nq + i] = pij;
+      dsw[warp * p.Nq + i] = pij * (dp - Ds[i]);
+    }
+    __syncwarp();
+    float* drow = p.dkv + ((int64_t)b * p.Nk + j) * 2 * inner;
+    for (int d = lane; d < dh; d += 32) {
+      float dk = 0.f, dv = 0.f;
+      for (int i = 0; i < p.Nq; ++i) {
+        dk = fmaf(dsw[warp * p.Nq + i], Qs[i * ld + d], dk);
+        dv = fmaf(pw[warp * p.Nq + i], dOs[i * ld + d], dv);
+      }
+      drow[h * dh + d] = dk * p.scale;
+      drow[inner + h * dh + d] = dv;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void token_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ mx,
+                                      int32_t* __restrict__ amax, int B, int N, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int b = idx / C, c = idx % C;
+  const float* xp = x + (int64_t)b * N * C + c;
+  float s = 0.f, best = -INFINITY;
+  int bi = 0;
+  for (int n = 0; n < N; ++n) {
+    const float v = xp[(int64_t)n * C];
+    s += v;
+    if (v > best) { best = v; bi = n; }
+  }
+  if (mean) mean[idx] = s / N;
+  if (mx) { mx[idx] = best; amax[idx] = bi; }
+}
+
+__global__ void token_pool_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ dmax,
+                                      const int32_t* __restrict__ amax, float* __restrict__ dx, int B, int N, int C,
+                                      int accumulate) {
+  const int64_t total = (int64_t)B * N * C;
+  const float invn = 1.f / N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int n = (int)((i / C) % N);
+    const int b = (int)(i / ((int64_t)C * N));
+    float v = 0.f;
+    if (dmean) v += dmean[b * C + c] * invn;
+    if (dmax && amax[b * C + c] == n) v += dmax[b * C + c];
+    if (accumulate) v += dx[i];
+    dx[i] = v;
+  }
+}
+
+static int launch_gemm(GemmArgs& p, cudaStream_t st) {
+  dim3 grid(ceil_div(p.N, G_TN), ceil_div(p.M, G_TM), 1);
+  gemm_kernel<<<grid, 256, 0, st>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+extern "C" {
+
+int tmf_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* pre,
+                   int M, int K, int N, int act, void* stream) {
+  TMF_REQUIRE(x && w && y, "linear_fwd: NULL pointer");
+  TMF_REQUIRE(act == 0 || act == 1, "linear_fwd: unknown activation %d", act);
+  GemmArgs p{};
+  p.A = x; p.B = w; p.C = y; p.bias = bias; p.residual = residual; p.pre = pre;
+  p.M = M; p.N = N; p.K = K;
+  p.sAm = K; p.sAk = 1; p.sBk = 1; p.sBn = K;
+  p.act = act; p.accumulate = 0;
+  return launch_gemm(p, (cudaStream_t)stream);
+}
+
+int tmf_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, int accumulate, void* stream) {
+  TMF_REQUIRE(dy && w && dx, "linear_dgrad: NULL pointer");
+  GemmArgs p{};
+  p.A = dy; p.B = w; p.C = dx;
+  p.M = M; p.N = K; p.K = N;          // dx[M,K] = dy[M,N] . w[N,K]
+  p.sAm = N; p.sAk = 1; p.sBk = K; p.sBn = 1;
+  p.accumulate = accumulate;
+  return launch_gemm(p, (cudaStream_t)stream);
+}
+
+int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* stream) {
+  TMF_REQUIRE(dy && x && dw, "linear_wgrad: NULL pointer");
+  GemmArgs p{};
+  p.A = dy; p.B = x; p.C = dw;
+  p.M = N; p.N = K; p.K = M;          // dw[N,K] = dy^T[N,M] . x[M,K]
+  p.sAm = 1; p.sAk = N; p.sBk = K; p.sBn = 1;
+  if (launch_gemm(p, (cudaStream_t)stream)) return 3;
+  if (dbias) {
+    colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(dy, dbias, M, N);
+    TMF_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                      float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
+  TMF_REQUIRE(dim % 4 == 0 && dim <= 128 * LN_MAXV, "layernorm: dim must be a multiple of 4 and <= %d (got %d)",
+              128 * LN_MAXV, dim);
+  const int grid = max(1, min(ceil_div(rows, 8), 148 * 8));
+  layernorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, residual, y, mean, rstd, rows, dim, eps);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* stream) {
+  TMF_REQUIRE(dim % 4 == 0 && dim <= 128 * LN_MAXV, "layernorm: dim must be a multiple of 4 and <= %d (got %d)",
+              128 * LN_MAXV, dim);
+  const int grid = max(1, min(ceil_div(rows, 8 * 4), 148));
+  layernorm_bwd_kernel<<<grid, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx,
+                                                                                      dgamma, dbeta, rows, dim,
+                                                                                      accumulate);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream) {
+  TMF_REQUIRE(n % 4 == 0, "gelu_bwd: n must be a multiple of 4");
+  const int grid = max(1, min(ceil_div(n / 4, 256), 148 * 8));
+  gelu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)pre, (float4*)dx, n / 4);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int64_t n, void* stream) {
+  const int grid = max(1, min(ceil_div(n, 256), 148 * 8));
+  scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, alpha, alpha_dev, n);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+static int attn_smem_check(size_t bytes, const void* fn) {
+  TMF_REQUIRE(bytes <= 227 * 1024, "attention: sequence too long for the shared-memory resident kernel (%zu B)", bytes);
+  if (bytes > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int tmf_attn_fwd(const float* q, const float* kv, float* out, float* lse, int B, int Nq, int Nk, int heads, int dh,
+                 float scale, void* stream) {
+  AttnArgs p{};
+  p.q = q; p.kv = kv; p.o = out; p.lse = lse;
+  p.B = B; p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.dh = dh; p.scale = scale;
+  const size_t smem = sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)AT_WARPS * dh);
+  if (attn_smem_check(smem, (const void*)attn_fwd_kernel)) return 2;
+  dim3 grid(B * heads, ceil_div(Nq, AT_ROWS), 1);
+  attn_fwd_kernel<<<grid, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float* out, const float* lse, float* dq,
+                 float* dkv, int B, int Nq, int Nk, int heads, int dh, float scale, void* stream) {
+  AttnArgs p{};
+  p.q = q; p.kv = kv; p.out = out; p.lse_in = lse; p.dout = dout; p.dq = dq; p.dkv = dkv;
+  p.B = B; p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.dh = dh; p.scale = scale;
+  const size_t smem1 =
+      sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)2 * AT_WARPS * dh);
+  if (attn_smem_check(smem1, (const void*)attn_bwd_dq_kernel)) return 2;
+  dim3 grid1(B * heads, ceil_div(Nq, AT_ROWS), 1);
+  attn_bwd_dq_kernel<<<grid1, AT_WARPS * 32, smem1, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  const size_t smem2 = sizeof(float) * ((size_t)2 * Nq * (dh + 1) + (size_t)2 * Nq + (size_t)2 * AT_WARPS * Nq +
+                                        (size_t)2 * AT_WARPS * dh);
+  if (attn_smem_check(smem2, (const void*)attn_bwd_dkv_kernel)) return 2;
+  dim3 grid2(B * heads, ceil_div(Nk, AT_ROWS), 1);
+  attn_bwd_dkv_kernel<<<grid2, AT_WARPS * 32, smem2, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_token_pool_fwd(const float* x, float* mean, float* max, int32_t* argmax, int B, int N, int C, void* stream) {
+  TMF_REQUIRE(max == nullptr || argmax != nullptr, "token_pool_fwd: argmax buffer required with max");
+  token_pool_fwd_kernel<<<ceil_div((int64_t)B * C, 128), 128, 0, (cudaStream_t)stream>>>(x, mean, max, argmax, B, N, C);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_token_pool_bwd(const float* dmean, const float* dmax, const int32_t* argmax, float* dx, int B, int N, int C,
+                       int accumulate, void* stream) {
+  const int64_t total = (int64_t)B * N * C;
+  const int grid = max(1, min(ceil_div(total, 256), 148 * 8));
+  token_pool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dmean, dmax, argmax, dx, B, N, C, accumulate);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""Host-side operators: thin wrappers over the C ABI (include/tmf.h) plus the ``torch.autograd.Function``s that
+give the reference's ``nn.Module``s their forward and backward on the B200 kernels.
+
+Nothing here computes on the CPU or through a torch library kernel on the hot path: tensors are allocated with
+torch (caching allocator), every arithmetic op is a ``tmf_*`` launch on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib as L
+
+BN_EPS, BN_MOMENTUM, LRELU_SLOPE, LN_EPS = 1e-5, 0.1, 0.01, 1e-5
+
+
+def conv_impl():
+    """TMF_CONV_IMPL = auto | direct | umma  (bring-up / cross-check switch; default auto)."""
+    return {"auto": L.CONV_AUTO, "direct": L.CONV_DIRECT, "umma": L.CONV_UMMA}[os.environ.get("TMF_CONV_IMPL", "auto")]
+
+
+def _f32c(t):
+    """fp32, contiguous, plain torch.Tensor (MONAI MetaTensor inputs are unwrapped)."""
+    if hasattr(t, "as_tensor"):
+        t = t.as_tensor()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ==============================================================================================================
+# sNet conv stack  (reference models/networks.py:18-61)
+# ==============================================================================================================
+class SNetSpec:
+    """Static description of one sNet: per layer (Cin, Cout, ksize, pool)."""
+
+    def __init__(self, dim):
+        q, h = dim // 4, dim // 2
+        self.layers = [(1, q, 3, L.POOL_MAX), (q, q, 3, L.POOL_NONE), (q, h, 3, L.POOL_MAX), (h, h, 3, L.POOL_NONE),
+                       (h, dim, 3, L.POOL_MAX), (dim, 2 * dim, 3, L.POOL_NONE), (2 * dim, dim, 1, L.POOL_AVG)]
+        self.dim = dim
+
+
+def _pooled(D, H, W, pool):
+    return (D, H, W) if pool == L.POOL_NONE else (D // 2, H // 2, W // 2)
+
+
+class SNetFunction(torch.autograd.Function):
+    """Both towers (or one) of the 3D-CNN encoder as ONE autograd node.
+
+    apply(spec, training, buffers, x_0[, x_1], *params) with params = for each tower, for each of the 7 layers:
+    conv.weight, conv.bias, bn.weight, bn.bias;  buffers[t][l] = (running_mean, running_var, num_batches_tracked).
+    Returns one fp32 tensor per tower with logical shape (B, dim, d, h, w) in channels-last-3d memory, i.e. the
+    token matrix (B, d*h*w, dim) is a free view of it.
+    """
+
+    @staticmethod
+    def forward(ctx, spec, training, buffers, ng, *args):
+        xs = [_f32c(a) for a in args[:ng]]
+        params = args[ng:]
+        assert len(params) == ng * 7 * 4
+        B, cin0, D, H, W = xs[0].shape
+        if cin0 != 1:
+            raise RuntimeError(f"sNet expects single-channel volumes (B,1,D,H,W); got {tuple(xs[0].shape)}")
+        for x in xs:
+            if tuple(x.shape) != tuple(xs[0].shape):
+                raise RuntimeError("MRI and PET volumes must have the same shape")
+        dev = xs[0].device
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        impl = conv_impl()
+        P = lambda t, l, k: params[(t * 7 + l) * 4 + k]
+        saved = []
+        act = xs
+        dims = (D, H, W)
+        for l, (cin, cout, ks, pool) in enumerate(spec.layers):
+            Dl, Hl, Wl = dims
+            count = B * Dl * Hl * Wl
+            y = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+            stats = [torch.empty(2 * cout, dtype=torch.float64, device=dev) for _ in range(ng)] if training else None
+            w = [P(t, l, 0) for t in range(ng)]
+            b = [P(t, l, 1) for t in range(ng)]
+            wd = None
+            if l == 0:
+                L.call("tmf_conv1_fwd", ng, L.ptrs(act), L.ptrs(w), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
+                       B, Dl, Hl, Wl, cout)
+            else:
+                taps = ks ** 3
+                wf = [torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                if need_grad:
+                    wd = [torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
+                L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs(wf), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
+                       B, Dl, Hl, Wl, cin, cout, ks, impl)
+            coef = [torch.empty(4 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            L.call("tmf_bn_finalize", ng, L.ptrs(stats), L.ptrs([P(t, l, 2) for t in range(ng)]),
+                   L.ptrs([P(t, l, 3) for t in range(ng)]), L.ptrs([buffers[t][l][0] for t in range(ng)]),
+                   L.ptrs([buffers[t][l][1] for t in range(ng)]), L.ptrs([buffers[t][l][2] for t in range(ng)]),
+                   L.ptrs(coef), cout, count, BN_MOMENTUM, BN_EPS, int(training))
+            last = l == len(spec.layers) - 1
+            Do, Ho, Wo = _pooled(Dl, Hl, Wl, pool)
+            out = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if last else torch.bfloat16, device=dev)
+                   for _ in range(ng)]
+            L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), int(last), B, Dl, Hl, Wl, cout,
+                   pool, LRELU_SLOPE)
+            if need_grad:
+                saved.append((act, y, coef, wd, dims))
+            act = out
+            dims = (Do, Ho, Wo)
+        ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
+        ctx.impl = impl
+        outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)      # logical (B,C,d,h,w), channels-last memory
+        return outs if ng > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        spec, ng, B, training = ctx.spec, ctx.ng, ctx.B, ctx.training
+        saved = ctx.saved
+        dev = saved[0][1][0].device
+        dout = []
+        for t in range(ng):
+            g = grads[t]
+            cout = spec.layers[-1][1]
+            if g is None:
+                Dl, Hl, Wl = _pooled(*saved[-1][4], spec.layers[-1][3])
+                g = torch.zeros((B, Dl, Hl, Wl, cout), dtype=torch.float32, device=dev)
+            else:
+                g = _f32c(g.permute(0, 2, 3, 4, 1))
+            dout.append(g)
+        dout_fp32 = 1
+        pgrads = [None] * (ng * 7 * 4)
+        for l in range(len(spec.layers) - 1, -1, -1):
+            cin, cout, ks, pool = spec.layers[l]
+            act, y, coef, wd, (Dl, Hl, Wl) = saved[l]
+            count = B * Dl * Hl * Wl
+            sums = [torch.empty(2 * cout, dtype=torch.float64, device=dev) for _ in range(ng)]
+            L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
+                   B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE)
+            dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            bcoef = [torch.empty(2 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(dgamma), L.ptrs(dbeta),
+                   L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
+            dy = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+            L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef),
+                   L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE)
+            dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
+            if l == 0:
+                L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout)
+            else:
+                L.call("tmf_conv3d_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cin, cout, ks,
+                       ctx.impl)
+                da = [torch.empty((B, Dl, Hl, Wl, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                L.call("tmf_conv3d_fwd", ng, L.ptrs(dy), L.ptrs(wd), L.ptrs(None), L.ptrs(da), L.ptrs(None),
+                       B, Dl, Hl, Wl, cout, cin, ks, ctx.impl)
+                dout, dout_fp32 = da, 0
+            for t in range(ng):
+                base = (t * 7 + l) * 4
+                pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
+            saved[l] = None
+        ctx.saved = None
+        return (None, None, None, None) + (None,) * ng + tuple(pgrads)
+
+
+# ==============================================================================================================
+# Linear / LayerNorm / attention / pooling / GRL
+# ==============================================================================================================
+class LinearFunction(torch.autograd.Function):
+    """y = act(x W^T + b) + residual   (nn.Linear; act = exact GELU when gelu=True)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual, gelu):
+        x2 = _f32c(x).reshape(-1, x.shape[-1])
+        M, K = x2.shape
+        N = w.shape[0]
+        w = _f32c(w)
+        y = torch.empty((M, N), dtype=torch.float32, device=x2.device)
+        pre = torch.empty_like(y) if gelu else None
+        res2 = _f32c(residual).reshape(M, N) if residual is not None else None
+        L.call("tmf_linear_fwd", L.ptr(x2), L.ptr(w), L.ptr(None if b is None else _f32c(b)), L.ptr(res2), L.ptr(y),
+               L.ptr(pre), M, K, N, int(gelu))
+        ctx.save_for_backward(x2, w, pre)
+        ctx.has_bias, ctx.has_res, ctx.gelu = b is not None, residual is not None, gelu
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, pre = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = _f32c(dy).reshape(M, N)
+        dres = dy2.reshape(dy.shape) if ctx.has_res else None
+        if ctx.gelu:
+            dpre = torch.empty_like(dy2)
+            L.call("tmf_gelu_bwd", L.ptr(dy2), L.ptr(pre), L.ptr(dpre), M * N)
+            dy2 = dpre
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dy2.device)
+            L.call("tmf_linear_dgrad", L.ptr(dy2), L.ptr(w), L.ptr(dx), M, K, N, 0)
+            dx = dx.reshape(ctx.xshape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
+            db = torch.empty(N, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
+            L.call("tmf_linear_wgrad", L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, K, N)
+        return dx, dw, db, dres, None
+
+
+def linear(x, w, b=None, residual=None, gelu=False):
+    return LinearFunction.apply(x, w, b, residual, gelu)
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """y = LayerNorm(x) * gamma + beta (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, eps):
+        x2 = _f32c(x).reshape(-1, x.shape[-1])
+        rows, dim = x2.shape
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+        rstd = torch.empty_like(mean)
+        res2 = _f32c(residual).reshape(rows, dim) if residual is not None else None
+        g = _f32c(gamma)
+        L.call("tmf_layernorm_fwd", L.ptr(x2), L.ptr(g), L.ptr(_f32c(beta)), L.ptr(res2), L.ptr(y), L.ptr(mean),
+               L.ptr(rstd), rows, dim, eps)
+        ctx.save_for_backward(x2, g, mean, rstd)
+        ctx.has_res = residual is not None
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        rows, dim = x2.shape
+        dy2 = _f32c(dy).reshape(rows, dim)
+        dx = torch.empty_like(x2)
+        dgb = torch.zeros((2, dim), dtype=torch.float32, device=x2.device)
+        L.call("tmf_layernorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dgb[0]),
+               L.ptr(dgb[1]), rows, dim, 0)
+        return dx.reshape(dy.shape), dgb[0], dgb[1], (dy if ctx.has_res else None), None
+
+
+def layer_norm(x, gamma, beta, residual=None, eps=LN_EPS):
+    return LayerNormFunction.apply(x, gamma, beta, residual, eps)
+
+
+class AttentionCoreFunction(torch.autograd.Function):
+    """softmax(q k^T * scale) v per head on short token sequences; q (B,Nq,h*dh), kv (B,Nk,2*h*dh)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, heads, scale):
+        q, kv = _f32c(q), _f32c(kv)
+        B, Nq, inner = q.shape
+        Nk = kv.shape[1]
+        dh = inner // heads
+        out = torch.empty_like(q)
+        lse = torch.empty((B, heads, Nq), dtype=torch.float32, device=q.device)
+        L.call("tmf_attn_fwd", L.ptr(q), L.ptr(kv), L.ptr(out), L.ptr(lse), B, Nq, Nk, heads, dh, float(scale))
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.heads, ctx.scale = heads, float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, out, lse = ctx.saved_tensors
+        B, Nq, inner = q.shape
+        Nk = kv.shape[1]
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        L.call("tmf_attn_bwd", L.ptr(_f32c(dout)), L.ptr(q), L.ptr(kv), L.ptr(out), L.ptr(lse), L.ptr(dq), L.ptr(dkv),
+               B, Nq, Nk, ctx.heads, inner // ctx.heads, ctx.scale)
+        return dq, dkv, None, None
+
+
+def attention_core(q, kv, heads, scale):
+    return AttentionCoreFunction.apply(q, kv, heads, scale)
+
+
+class TokenPoolFunction(torch.autograd.Function):
+    """x (B,N,C) -> mean over N (B,C) and/or max over N (B,C) (first-maximum gradient routing)."""
+
+    @staticmethod
+    def forward(ctx, x, want_mean, want_max):
+        x = _f32c(x)
+        B, N, C = x.shape
+        mean = torch.empty((B, C), dtype=torch.float32, device=x.device) if want_mean else None
+        mx = torch.empty((B, C), dtype=torch.float32, device=x.device) if want_max else None
+        amax = torch.empty((B, C), dtype=torch.int32, device=x.device) if want_max else None
+        L.call("tmf_token_pool_fwd", L.ptr(x), L.ptr(mean), L.ptr(mx), L.ptr(amax), B, N, C)
+        ctx.shape, ctx.amax = (B, N, C), amax
+        ctx.want = (want_mean, want_max)
+        if want_mean and want_max:
+            return mean, mx
+        return mean if want_mean else mx
+
+    @staticmethod
+    def backward(ctx, *g):
+        B, N, C = ctx.shape
+        want_mean, want_max = ctx.want
+        if want_mean and want_max:
+            dmean, dmax = g
+        elif want_mean:
+            dmean, dmax = g[0], None
+        else:
+            dmean, dmax = None, g[0]
+        dmean = _f32c(dmean) if dmean is not None else None
+        dmax = _f32c(dmax) if dmax is not None else None
+        dx = torch.empty((B, N, C), dtype=torch.float32, device=(dmean if dmean is not None else dmax).device)
+        L.call("tmf_token_pool_bwd", L.ptr(dmean), L.ptr(dmax), L.ptr(ctx.amax), L.ptr(dx), B, N, C, 0)
+        return dx, None, None
+
+
+def token_pool(x, want_mean=True, want_max=True):
+    return TokenPoolFunction.apply(x, want_mean, want_max)
+
+
+class GradientReversalFunction(torch.autograd.Function):
+    """reference models/gradient_reversal/functional.py:4-19: identity forward, -alpha * grad backward."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        if torch.is_tensor(alpha):
+            if alpha.is_cuda:
+                ctx.alpha_dev, ctx.alpha = alpha.detach().reshape(-1).float(), 1.0
+            else:
+                ctx.alpha_dev, ctx.alpha = None, float(alpha.reshape(-1)[0])
+        else:
+            ctx.alpha_dev, ctx.alpha = None, float(alpha)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        g = _f32c(g)
+        out = torch.empty_like(g)
+        L.call("tmf_scale", L.ptr(g), L.ptr(out), -ctx.alpha, L.ptr(ctx.alpha_dev), g.numel())
+        return out, None
+
+
+def revgrad(x, alpha):
+    return GradientReversalFunction.apply(x, alpha)
