@@ -76,6 +76,10 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
 int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float* const* dw,
                      int B, int D, int H, int W, int cin, int cout, int ksize, int impl, void* stream);
 
+/* 1 if implementation `impl` (TMF_CONV_DIRECT / TMF_CONV_UMMA) handles this problem, else 0.
+ * op: 0 = forward / dgrad (tmf_conv3d_fwd), 1 = weight gradient (tmf_conv3d_wgrad). */
+int tmf_conv3d_supported(int op, int impl, int D, int H, int W, int cin, int cout, int ksize);
+
 /* BatchNorm statistics -> coefficients.  coef[4*C] = {scale = gamma*invstd, shift = beta - mean*scale, mean,
  * invstd}.  training != 0: batch statistics from stats (biased variance), running_mean/var updated with
  * momentum (unbiased variance) and num_batches_tracked += 1; training == 0: running statistics.

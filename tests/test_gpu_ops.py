@@ -1,0 +1,297 @@
+"""Op-level parity (GPU): every C-ABI kernel against the matching torch fp32 CPU op on identical (bf16-rounded)
+inputs.  bf16 outputs: <= 1 bf16 ulp (2^-8 relative) plus accumulation-order noise; fp32 outputs: <= 1e-4."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from transmf_ad_b200 import _lib as L
+from transmf_ad_b200 import functional as TF
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+IMPLS = [L.CONV_DIRECT] + ([L.CONV_UMMA] if os.environ.get("TMF_TEST_UMMA", "1") == "1" else [])
+
+
+def g_randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def to_ndhwc_bf16(x):
+    """(B,C,D,H,W) fp32 cpu -> (B,D,H,W,C) bf16 cuda."""
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+
+
+def from_ndhwc(y):
+    return y.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).float()
+
+
+def max_rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,cout", [((2, 17, 19, 18), 32), ((1, 16, 16, 16), 16), ((1, 9, 33, 70), 64)])
+def test_conv1_fwd_and_stats(shape, cout):
+    B, D, H, W = shape
+    x = torch.rand(B, 1, D, H, W, generator=torch.Generator().manual_seed(1))
+    w = g_randn(cout, 1, 3, 3, 3, seed=2, scale=0.3)
+    b = g_randn(cout, seed=3, scale=0.1)
+    xd, wd_, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    y = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(2 * cout, dtype=torch.float64, device=DEV)
+    L.call("tmf_conv1_fwd", 1, L.ptrs([xd]), L.ptrs([wd_]), L.ptrs([bd]), L.ptrs([y]), L.ptrs([stats]), B, D, H, W, cout)
+    ref = F.conv3d(x, w, b, padding=1)
+    got = from_ndhwc(y)
+    assert max_rel(got, ref) < 6e-3
+    yf = y.double()
+    assert torch.allclose(stats[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(stats[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape,cin,cout,ks", [
+    ((2, 9, 11, 10), 32, 32, 3), ((1, 12, 13, 11), 32, 64, 3), ((2, 6, 7, 5), 64, 128, 3), ((1, 5, 6, 5), 128, 256, 3),
+    ((2, 5, 6, 5), 256, 128, 1), ((1, 22, 27, 22), 64, 64, 3), ((1, 8, 8, 8), 16, 16, 3)])
+def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
+    B, D, H, W = shape
+    lib = L.load()
+    if impl == L.CONV_UMMA and not (lib.tmf_conv3d_supported(0, impl, D, H, W, cin, cout, ks)
+                                    and lib.tmf_conv3d_supported(0, impl, D, H, W, cout, cin, ks)
+                                    and lib.tmf_conv3d_supported(1, impl, D, H, W, cin, cout, ks)):
+        pytest.skip("shape not handled by the tcgen05 path")
+    a = bf16r(g_randn(B, cin, D, H, W, seed=4))
+    w = g_randn(cout, cin, ks, ks, ks, seed=5, scale=(2.0 / (cin * ks ** 3)) ** 0.5)
+    bias = g_randn(cout, seed=6, scale=0.1)
+    dy = bf16r(g_randn(B, cout, D, H, W, seed=7))
+    wdev = w.to(DEV)
+    taps = ks ** 3
+    wf = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=DEV)
+    wdg = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=DEV)
+    L.call("tmf_pack_conv_weights", 1, L.ptrs([wdev]), L.ptrs([wf]), L.ptrs([wdg]), cout, cin, ks)
+    a_d, dy_d, b_d = to_ndhwc_bf16(a), to_ndhwc_bf16(dy), bias.to(DEV)
+    # ---- forward (+ stats)
+    y = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(2 * cout, dtype=torch.float64, device=DEV)
+    L.call("tmf_conv3d_fwd", 1, L.ptrs([a_d]), L.ptrs([wf]), L.ptrs([b_d]), L.ptrs([y]), L.ptrs([stats]),
+           B, D, H, W, cin, cout, ks, impl)
+    a_ref = a.clone().requires_grad_(True)
+    w_ref = bf16r(w).requires_grad_(True)
+    ref = F.conv3d(a_ref, w_ref, bias, padding=ks // 2)
+    assert max_rel(from_ndhwc(y), ref.detach()) < 6e-3, "forward"
+    yf = y.double()
+    assert torch.allclose(stats[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(stats[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
+    # ---- dgrad and wgrad
+    ref.backward(dy)
+    da = torch.empty((B, D, H, W, cin), dtype=torch.bfloat16, device=DEV)
+    L.call("tmf_conv3d_fwd", 1, L.ptrs([dy_d]), L.ptrs([wdg]), L.ptrs(None), L.ptrs([da]), L.ptrs(None),
+           B, D, H, W, cout, cin, ks, impl)
+    assert max_rel(from_ndhwc(da), a_ref.grad) < 6e-3, "dgrad"
+    dw = torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=DEV)
+    L.call("tmf_conv3d_wgrad", 1, L.ptrs([dy_d]), L.ptrs([a_d]), L.ptrs([dw]), B, D, H, W, cin, cout, ks, impl)
+    assert rel_l2(dw.cpu(), w_ref.grad) < 2e-3, "wgrad"
+
+
+def test_conv_grouped_towers_match_single_launches():
+    B, D, H, W, cin, cout = 1, 7, 8, 9, 32, 32
+    outs = []
+    a = [to_ndhwc_bf16(g_randn(B, cin, D, H, W, seed=s)) for s in (1, 2)]
+    w = [g_randn(27, cout, cin, seed=s, scale=0.05).to(torch.bfloat16).to(DEV) for s in (3, 4)]
+    y2 = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV) for _ in range(2)]
+    L.call("tmf_conv3d_fwd", 2, L.ptrs(a), L.ptrs(w), L.ptrs(None), L.ptrs(y2), L.ptrs(None), B, D, H, W, cin, cout, 3,
+           L.CONV_DIRECT)
+    for t in range(2):
+        y1 = torch.empty_like(y2[t])
+        L.call("tmf_conv3d_fwd", 1, L.ptrs([a[t]]), L.ptrs([w[t]]), L.ptrs(None), L.ptrs([y1]), L.ptrs(None), B, D, H, W,
+               cin, cout, 3, L.CONV_DIRECT)
+        assert torch.equal(y1, y2[t])
+
+
+def test_conv1_wgrad():
+    B, D, H, W, cout = 2, 11, 13, 12, 32
+    x = torch.rand(B, 1, D, H, W, generator=torch.Generator().manual_seed(1))
+    dy = bf16r(g_randn(B, cout, D, H, W, seed=2))
+    w = g_randn(cout, 1, 3, 3, 3, seed=3).requires_grad_(True)
+    F.conv3d(x, w, None, padding=1).backward(dy)
+    dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=DEV)
+    L.call("tmf_conv1_wgrad", 1, L.ptrs([to_ndhwc_bf16(dy)]), L.ptrs([x.to(DEV)]), L.ptrs([dw]), B, D, H, W, cout)
+    assert rel_l2(dw.cpu(), w.grad) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pool,shape,C,training,last", [
+    (L.POOL_MAX, (2, 9, 11, 7), 32, True, False), (L.POOL_NONE, (2, 5, 6, 7), 64, True, False),
+    (L.POOL_AVG, (2, 5, 6, 5), 128, True, True), (L.POOL_MAX, (1, 8, 8, 8), 16, False, False),
+    (L.POOL_AVG, (3, 4, 5, 6), 24, False, True)])
+def test_bn_lrelu_pool_forward_backward(pool, shape, C, training, last):
+    """BatchNorm3d(train/eval) + LeakyReLU + pool: forward, running-stat update, and the full backward
+    (dgamma, dbeta, dy) against torch autograd on the same bf16 pre-BN tensor."""
+    B, D, H, W = shape
+    y = bf16r(g_randn(B, C, D, H, W, seed=1, scale=2.0) + 0.5)
+    gamma = (1 + 0.2 * g_randn(C, seed=2))
+    beta = 0.1 * g_randn(C, seed=3)
+    rm0, rv0 = 0.1 * g_randn(C, seed=4), 1 + 0.1 * torch.rand(C, generator=torch.Generator().manual_seed(5))
+    y_d = to_ndhwc_bf16(y)
+    count = B * D * H * W
+    yd64 = y_d.double()
+    stats = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))]).contiguous()
+    g_d, b_d = gamma.to(DEV), beta.to(DEV)
+    rm, rv = rm0.clone().to(DEV), rv0.clone().to(DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    coef = torch.empty(4 * C, dtype=torch.float32, device=DEV)
+    L.call("tmf_bn_finalize", 1, L.ptrs([stats]), L.ptrs([g_d]), L.ptrs([b_d]), L.ptrs([rm]), L.ptrs([rv]), L.ptrs([nbt]),
+           L.ptrs([coef]), C, count, 0.1, 1e-5, int(training))
+    Do, Ho, Wo = (D, H, W) if pool == L.POOL_NONE else (D // 2, H // 2, W // 2)
+    out = torch.empty((B, Do, Ho, Wo, C), dtype=torch.float32 if last else torch.bfloat16, device=DEV)
+    L.call("tmf_bn_act_pool_fwd", 1, L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([out]), int(last), B, D, H, W, C, pool, 0.01)
+    # reference
+    y_ref = y.clone().requires_grad_(True)
+    g_ref, b_ref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm0.clone(), rv0.clone()
+    z = F.batch_norm(y_ref, rm_ref, rv_ref, g_ref, b_ref, training, 0.1, 1e-5)
+    a = F.leaky_relu(z, 0.01)
+    if pool == L.POOL_MAX:
+        a = F.max_pool3d(a, 2, 2)
+    elif pool == L.POOL_AVG:
+        a = F.avg_pool3d(a, 2, 2)
+    tol = 1e-4 if last else 6e-3
+    assert max_rel(from_ndhwc(out), a.detach()) < tol
+    if training:
+        assert torch.allclose(rm.cpu(), rm_ref, atol=1e-5) and torch.allclose(rv.cpu(), rv_ref, atol=1e-5)
+        assert int(nbt) == 1
+    else:
+        assert torch.equal(rm.cpu(), rm0) and int(nbt) == 0
+    # backward
+    dout = g_randn(*a.shape, seed=9)
+    if not last:
+        dout = bf16r(dout)
+    a.backward(dout)
+    dout_d = dout.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    if not last:
+        dout_d = dout_d.to(torch.bfloat16)
+    sums = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    L.call("tmf_bn_act_pool_bwd_reduce", 1, L.ptrs([dout_d]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([sums]),
+           B, D, H, W, C, pool, 0.01)
+    dgamma, dbeta, dbias = (torch.empty(C, dtype=torch.float32, device=DEV) for _ in range(3))
+    bcoef = torch.empty(2 * C, dtype=torch.float32, device=DEV)
+    L.call("tmf_bn_bwd_finalize", 1, L.ptrs([sums]), L.ptrs([coef]), L.ptrs([dgamma]), L.ptrs([dbeta]), L.ptrs([dbias]),
+           L.ptrs([bcoef]), C, count, int(training))
+    dy = torch.empty((B, D, H, W, C), dtype=torch.bfloat16, device=DEV)
+    L.call("tmf_bn_act_pool_bwd_apply", 1, L.ptrs([dout_d]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([bcoef]),
+           L.ptrs([dy]), B, D, H, W, C, pool, 0.01)
+    assert rel_l2(dgamma.cpu(), g_ref.grad) < 1e-4
+    assert rel_l2(dbeta.cpu(), b_ref.grad) < 1e-4
+    assert rel_l2(from_ndhwc(dy), y_ref.grad) < 6e-3
+    if not training:
+        assert rel_l2(dbias.cpu(), y_ref.grad.sum(dim=(0, 2, 3, 4))) < 1e-3
+
+
+def test_maxpool_backward_routes_ties_to_first_maximum():
+    """bf16 storage makes ties common; torch sends the gradient to the first maximum in (d,h,w) scan order."""
+    B, D, H, W, C = 1, 2, 2, 2, 8
+    y = torch.ones(B, C, D, H, W)
+    y_d = to_ndhwc_bf16(y)
+    coef = torch.cat([torch.ones(C), torch.zeros(C), torch.zeros(C), torch.ones(C)]).to(DEV)
+    dout = torch.ones((B, 1, 1, 1, C), dtype=torch.bfloat16, device=DEV)
+    bcoef = torch.zeros(2 * C, dtype=torch.float32, device=DEV)
+    dy = torch.empty((B, D, H, W, C), dtype=torch.bfloat16, device=DEV)
+    L.call("tmf_bn_act_pool_bwd_apply", 1, L.ptrs([dout]), 0, L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([bcoef]), L.ptrs([dy]),
+           B, D, H, W, C, L.POOL_MAX, 0.01)
+    yr = y.clone().requires_grad_(True)
+    F.max_pool3d(yr, 2, 2).sum().backward()
+    assert torch.equal(from_ndhwc(dy), yr.grad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N,gelu,res", [(300, 128, 128, False, True), (300, 128, 512, True, False),
+                                            (2, 512, 512, False, False), (77, 64, 2, False, False), (150, 512, 128, False, True)])
+def test_linear_function(M, K, N, gelu, res):
+    x, w, b = g_randn(M, K, seed=1), g_randn(N, K, seed=2, scale=K ** -0.5), g_randn(N, seed=3, scale=0.1)
+    r = g_randn(M, N, seed=4) if res else None
+    dy = g_randn(M, N, seed=5)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, b)] + ([r.clone().requires_grad_(True)] if res else [])
+    ref = F.linear(leaves[0], leaves[1], leaves[2])
+    if gelu:
+        ref = F.gelu(ref)
+    if res:
+        ref = ref + leaves[3]
+    ref.backward(dy)
+    dl = [t.clone().to(DEV).requires_grad_(True) for t in (x, w, b)] + ([r.clone().to(DEV).requires_grad_(True)] if res else [])
+    out = TF.linear(dl[0], dl[1], dl[2], residual=dl[3] if res else None, gelu=gelu)
+    out.backward(dy.to(DEV))
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-5
+    for a, c in zip(dl, leaves):
+        assert rel_l2(a.grad.cpu(), c.grad) < 1e-4
+
+
+@pytest.mark.parametrize("rows,dim,res", [(300, 128, True), (7, 64, False), (33, 512, False)])
+def test_layernorm_function(rows, dim, res):
+    x, g, b = g_randn(rows, dim, seed=1) * 2 + 0.3, 1 + 0.1 * g_randn(dim, seed=2), 0.1 * g_randn(dim, seed=3)
+    r = g_randn(rows, dim, seed=4) if res else None
+    dy = g_randn(rows, dim, seed=5)
+    cl = [t.clone().requires_grad_(True) for t in (x, g, b)]
+    ref = F.layer_norm(cl[0], (dim,), cl[1], cl[2], 1e-5)
+    if res:
+        ref = ref + r
+    ref.backward(dy)
+    dl = [t.clone().to(DEV).requires_grad_(True) for t in (x, g, b)]
+    out = TF.layer_norm(dl[0], dl[1], dl[2], residual=r.to(DEV) if res else None)
+    out.backward(dy.to(DEV))
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-5
+    for a, c in zip(dl, cl):
+        assert rel_l2(a.grad.cpu(), c.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,Nq,Nk,heads,dh", [(2, 150, 150, 4, 32), (3, 8, 8, 8, 16), (2, 80, 160, 4, 32), (1, 37, 300, 2, 64)])
+def test_attention_core_function(B, Nq, Nk, heads, dh):
+    inner = heads * dh
+    q, kv, do = g_randn(B, Nq, inner, seed=1), g_randn(B, Nk, 2 * inner, seed=2), g_randn(B, Nq, inner, seed=3)
+    qc, kvc = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    k, v = kvc.chunk(2, dim=-1)
+    sp = lambda t: t.reshape(B, -1, heads, dh).permute(0, 2, 1, 3)
+    attn = torch.softmax(sp(qc) @ sp(k).transpose(-1, -2) * dh ** -0.5, dim=-1)
+    ref = (attn @ sp(v)).permute(0, 2, 1, 3).reshape(B, Nq, inner)
+    ref.backward(do)
+    qd, kvd = q.to(DEV).requires_grad_(True), kv.to(DEV).requires_grad_(True)
+    out = TF.attention_core(qd, kvd, heads, dh ** -0.5)
+    out.backward(do.to(DEV))
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-5
+    assert rel_l2(qd.grad.cpu(), qc.grad) < 1e-4
+    assert rel_l2(kvd.grad.cpu(), kvc.grad) < 1e-4
+
+
+def test_token_pool_and_revgrad():
+    x = g_randn(3, 20, 128, seed=1)
+    xc = x.clone().requires_grad_(True)
+    (xc.mean(1) * 2 + F.adaptive_max_pool1d(xc.transpose(1, 2), 1).squeeze(-1) * 3).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    m, mx = TF.token_pool(xd, True, True)
+    assert rel_l2(m.detach().cpu(), x.mean(1)) < 1e-6 and torch.equal(mx.detach().cpu(), x.amax(1))
+    (m * 2 + mx * 3).sum().backward()
+    assert rel_l2(xd.grad.cpu(), xc.grad) < 1e-6
+    yd = x.to(DEV).requires_grad_(True)
+    TF.revgrad(yd, 2.0).sum().backward()
+    assert torch.equal(yd.grad.cpu(), torch.full_like(x, -2.0))
+    zd = x.to(DEV).requires_grad_(True)
+    TF.revgrad(zd, torch.Tensor([2]).to(DEV)).sum().backward()        # the reference's call form (mymodel.py:209)
+    assert torch.equal(zd.grad.cpu(), torch.full_like(x, -2.0))
+
+
+def test_bad_arguments_fail_loudly():
+    with pytest.raises(RuntimeError, match="ksize"):
+        L.call("tmf_conv3d_fwd", 1, L.ptrs([None]), L.ptrs([None]), L.ptrs(None), L.ptrs([None]), L.ptrs(None),
+               1, 4, 4, 4, 32, 32, 5, L.CONV_DIRECT)
+    with pytest.raises(RuntimeError, match="NULL"):
+        L.call("tmf_conv3d_fwd", 1, L.ptrs([None]), L.ptrs([None]), L.ptrs(None), L.ptrs([None]), L.ptrs(None),
+               1, 4, 4, 4, 32, 32, 3, L.CONV_DIRECT)

@@ -44,7 +44,7 @@ SIGNATURES = {
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
 }
 PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
-         "tmf_launch_count": (_i64, [])}
+         "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8)}
 
 _lib = None
 _device_checked = False
@@ -105,9 +105,40 @@ def ptrs(ts):
     return C.cast(arr, _pp)
 
 
-def call(name, *args):
+class KernelTimer:
+    """Optional per-entry-point CUDA-event timing (bench.py's roofline leg).  Off unless ``start()`` is called;
+    events are recorded on the launching (current) stream around each C-ABI call."""
+
+    def __init__(self):
+        self.records = None
+
+    def start(self):
+        self.records = []
+
+    def stop(self):
+        """-> {tag: (total_ms, calls)}; synchronises."""
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1 in self.records or []:
+            ms, n = out.get(tag, (0.0, 0))
+            out[tag] = (ms + e0.elapsed_time(e1), n + 1)
+        self.records = None
+        return out
+
+
+TIMER = KernelTimer()
+
+
+def call(name, *args, tag=None):
     """Invoke an entry point on the current stream; raises RuntimeError(tmf_last_error()) on failure."""
     _require_device()
-    rc = getattr(load(), name)(*args, stream_ptr())
+    if TIMER.records is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args, stream_ptr())
+        e1.record()
+        TIMER.records.append((tag or name, e0, e1))
+    else:
+        rc = getattr(load(), name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")

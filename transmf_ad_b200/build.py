@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-lcuda"]
     subprocess.run(cmd, check=True)
     return LIB
 

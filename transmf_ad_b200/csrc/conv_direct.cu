@@ -440,6 +440,17 @@ bool tmf_conv3d_wgrad_umma_supported(int D, int H, int W, int cin, int cout, int
 
 extern "C" {
 
+int tmf_conv3d_supported(int op, int impl, int D, int H, int W, int cin, int cout, int ksize) {
+  if (ksize != 1 && ksize != 3) return 0;
+  if (impl == TMF_CONV_DIRECT) return (cin % 8 == 0 && cout % (op == 0 ? 4 : 8) == 0) ? 1 : 0;
+  if (impl == TMF_CONV_UMMA)
+    return (op == 0 ? tmf_conv3d_fwd_umma_supported(D, H, W, cin, cout, ksize)
+                    : tmf_conv3d_wgrad_umma_supported(D, H, W, cin, cout, ksize))
+               ? 1
+               : 0;
+  return 0;
+}
+
 int tmf_pack_conv_weights(int ng, const float* const* w, void* const* wf, void* const* wd, int cout, int cin,
                           int ksize, void* stream) {
   TMF_CHECK_NG(ng);

@@ -153,7 +153,7 @@ class SNetFunction(torch.autograd.Function):
                        ctx.impl)
                 da = [torch.empty((B, Dl, Hl, Wl, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(dy), L.ptrs(wd), L.ptrs(None), L.ptrs(da), L.ptrs(None),
-                       B, Dl, Hl, Wl, cout, cin, ks, ctx.impl)
+                       B, Dl, Hl, Wl, cout, cin, ks, ctx.impl, tag="tmf_conv3d_dgrad")
                 dout, dout_fp32 = da, 0
             for t in range(ng):
                 base = (t * 7 + l) * 4
