@@ -129,8 +129,9 @@ def transformer_encoder(sd, pfx, x, context, heads):
         depth += 1
     for l in range(depth):
         p = f"{pfx}.layers.{l}"
-        ctx = x if context is None else context
-        x = attention(sd, p + ".0.fn", layernorm(sd, p + ".0.norm", x), ctx, heads) + x
+        xn = layernorm(sd, p + ".0.norm", x)
+        ctx = xn if context is None else context      # default(context, x) is applied to the NORMED x (:160)
+        x = attention(sd, p + ".0.fn", xn, ctx, heads) + x
         x = feedforward(sd, p + ".1.fn", layernorm(sd, p + ".1.norm", x)) + x
     return layernorm(sd, pfx + ".norm", x)
 

@@ -67,7 +67,7 @@ class SNetFunction(torch.autograd.Function):
             if tuple(x.shape) != tuple(xs[0].shape):
                 raise RuntimeError("MRI and PET volumes must have the same shape")
         dev = xs[0].device
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad[4 + ng:])      # (grad mode is always off inside forward)
         impl = conv_impl()
         P = lambda t, l, k: params[(t * 7 + l) * 4 + k]
         saved = []
