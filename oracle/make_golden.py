@@ -32,15 +32,16 @@ from oracle import restatement as R                      # noqa: E402
 from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state   # noqa: E402
 
 CASES = {
-    # name: (model, ctor kwargs, batch, volume shape, weight seed)
-    "model_ad_h4": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 2, (35, 38, 33), 0),
-    "model_ad_h8": ("model_ad", dict(dim=128, depth=3, heads=8, dim_head=16, mlp_dim=512, dropout=0.), 3, (32, 33, 34), 1),
-    "model_cnn_ad": ("model_CNN_ad", dict(dim=128), 2, (33, 35, 34), 2),
+    # name: (model, ctor kwargs, batch, volume shape, weight seed).  Models with BatchNorm1d heads use B = 8: with two or
+    # three samples BatchNorm1d maps every feature to +-1 and turns rounding noise into O(1) logit changes.
+    "model_ad_h4": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 8, (35, 38, 33), 0),
+    "model_ad_h8": ("model_ad", dict(dim=128, depth=3, heads=8, dim_head=16, mlp_dim=512, dropout=0.), 8, (32, 33, 34), 1),
+    "model_cnn_ad": ("model_CNN_ad", dict(dim=128), 8, (33, 35, 34), 2),
     "model_single": ("model_single", dict(dim=128), 2, (34, 33, 37), 3),
-    "model_transformer": ("model_transformer", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=256, dropout=0.), 2, (32, 32, 32), 4),
-    "model_transformer_res": ("model_transformer_res", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=256, dropout=0.), 2, (32, 32, 32), 5),
+    "model_transformer": ("model_transformer", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=256, dropout=0.), 8, (32, 32, 32), 4),
+    "model_transformer_res": ("model_transformer_res", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=256, dropout=0.), 3, (32, 32, 32), 5),
     "model_cnn": ("model_CNN", dict(dim=128), 2, (32, 32, 32), 6),
-    "model_ad_dim64": ("model_ad", dict(dim=64, depth=1, heads=2, dim_head=16, mlp_dim=96, dropout=0.), 2, (32, 36, 32), 7),
+    "model_ad_dim64": ("model_ad", dict(dim=64, depth=1, heads=2, dim_head=16, mlp_dim=96, dropout=0.), 8, (32, 36, 32), 7),
 }
 GRAD_SAMPLE = 48
 

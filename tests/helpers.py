@@ -91,3 +91,86 @@ def set_head_dropout(module, p):
                 m._p0 = m.p
             if m._p0 == 0.5:
                 m.p = p
+
+
+def is_conv_bias(k):
+    """Conv3d biases inside the sNet towers: train-mode BatchNorm cancels them exactly (true gradient 0)."""
+    parts = k.split(".")
+    return k.endswith(".bias") and ".conv" in k and parts[-2] in ("0", "3")
+
+
+def parity_report(name, device="cuda"):
+    """Run one train step + eval forward of golden case ``name`` on the CUDA path and on the CPU oracle (with and
+    without bf16 rounding emulation); return a dict of error metrics (no assertions)."""
+    import copy
+    from transmf_ad_b200.models import mymodel as M
+    gold = load_golden(name)
+    mri, pet, label = case_inputs(gold)
+    kind, kwargs = gold["kind"], gold["kwargs"]
+    inputs = (mri,) if kind == "model_single" else (mri, pet)
+    state = case_state(gold)
+    model = getattr(M, kind)(**kwargs)
+    model.load_state_dict(state, strict=True)
+    model = model.to(device).train()
+    set_head_dropout(model, 0.0)
+    rep = {"name": name}
+    # ---- tower features (kernel exactness, upstream of the ill-conditioned BatchNorm1d heads)
+    towers = [("cnn", 0)] if kind == "model_single" else [("mri_cnn", 0), ("pet_cnn", 1)]
+    sd_feat = R.clone_state(state, requires_grad=False)
+    feat_err = {}
+    with torch.no_grad():
+        for pfx, idx in towers:
+            net = copy.deepcopy(getattr(model, pfx))
+            got = net(inputs[idx].to(device)).float().cpu()
+            want = R.snet_forward(sd_feat, pfx, inputs[idx], True, R.bf16_round)
+            want32 = R.snet_forward(R.clone_state(state, requires_grad=False), pfx, inputs[idx], True, None)
+            feat_err[pfx] = (rel_err(got, want), rel_err(got, want32), rel_err(want, want32))
+    rep["feat_rel(ours:A, ours:B, A:B)"] = feat_err
+    # ---- full train step
+    model.zero_grad(set_to_none=True)
+    outs = model(*[t.to(device) for t in inputs])
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    ce, ad, total = losses(outs, label.to(device))
+    total.backward()
+    sd = R.clone_state(state)
+    o_outs = oracle_forward(kind, sd, inputs, kwargs, True, 0.0, rnd=R.bf16_round)
+    o_total = losses(o_outs, label)[2]
+    o_total.backward()
+    rep["logit_err_A"] = [float((o.detach().cpu() - a.detach()).abs().max()) for o, a in zip(outs, o_outs)]
+    rep["logit_err_B"] = [float((o.detach().cpu() - b).abs().max()) for o, b in zip(outs, gold["train_outs"])]
+    rep["logit_err_A_vs_B"] = [float((a.detach() - b).abs().max()) for a, b in zip(o_outs, gold["train_outs"])]
+    rep["loss"] = (float(total.detach()), float(o_total.detach()), gold["train_losses"][2])
+    grads = {}
+    for k, p in model.named_parameters():
+        g = None if p.grad is None else p.grad.detach().cpu()
+        ga = sd[k].grad
+        gs = gold["grad_sample"][k]
+        entry = {"missing": g is None}
+        if g is not None:
+            entry.update(finite=bool(torch.isfinite(g).all()), norm=float(g.norm()), norm_A=float(ga.norm()),
+                         norm_B=gold["grad_norm"][k], rel_A=rel_err(g, ga), cos_A=cosine(g, ga),
+                         cos_B=cosine(sample(g), gs), cos_A_vs_B=cosine(sample(ga), gs), conv_bias=is_conv_bias(k),
+                         absmax=float(g.abs().max()))
+        grads[k] = entry
+    rep["grads"] = grads
+    msd = model.state_dict()
+    rep["buffers"] = {k: (int(msd[k]) == int(v)) if k.endswith("num_batches_tracked")
+                      else float((msd[k].cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))
+                      for k, v in gold["buffers_after"].items()}
+    # ---- eval forward with the updated statistics
+    model.eval()
+    with torch.no_grad():
+        e = model(*[t.to(device) for t in inputs])
+    e = e if isinstance(e, tuple) else (e,)
+    sd_eval = R.clone_state({k: v.cpu() for k, v in model.state_dict().items()}, requires_grad=False)
+    with torch.no_grad():
+        oe = oracle_forward(kind, sd_eval, inputs, kwargs, False, rnd=R.bf16_round)
+        oe32 = oracle_forward(kind, R.clone_state(sd_eval, requires_grad=False), inputs, kwargs, False, rnd=None)
+    rep["eval_err_A"] = [float((a.cpu() - b).abs().max()) for a, b in zip(e, oe)]
+    rep["eval_err_B"] = [float((a.cpu() - b).abs().max()) for a, b in zip(e, oe32)]
+    margin = (oe32[0][:, 0] - oe32[0][:, 1]).abs()
+    rep["eval_margin_min"] = float(margin.min())
+    rep["eval_argmax_equal"] = bool(torch.equal(e[0].cpu().argmax(1), oe32[0].argmax(1)))
+    rep["eval_argmax_equal_sure"] = lambda tol: bool(torch.equal(e[0].cpu().argmax(1)[margin > 2 * tol],
+                                                                 oe32[0].argmax(1)[margin > 2 * tol]))
+    return rep

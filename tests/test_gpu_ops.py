@@ -125,7 +125,8 @@ def test_conv1_wgrad():
     w = g_randn(cout, 1, 3, 3, 3, seed=3).requires_grad_(True)
     F.conv3d(x, w, None, padding=1).backward(dy)
     dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=DEV)
-    L.call("tmf_conv1_wgrad", 1, L.ptrs([to_ndhwc_bf16(dy)]), L.ptrs([x.to(DEV)]), L.ptrs([dw]), B, D, H, W, cout)
+    dy_d, x_d = to_ndhwc_bf16(dy), x.to(DEV)          # keep references: L.ptrs() only takes raw addresses
+    L.call("tmf_conv1_wgrad", 1, L.ptrs([dy_d]), L.ptrs([x_d]), L.ptrs([dw]), B, D, H, W, cout)
     assert rel_l2(dw.cpu(), w.grad) < 1e-4
 
 
