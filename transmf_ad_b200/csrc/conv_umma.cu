@@ -1,15 +1,432 @@
-// conv_umma.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution kernels (placeholder until bring-up).
-#include "common.cuh"
+// conv_umma.cu -- implicit-GEMM Conv3d (3x3x3 pad 1, or 1x1x1) forward / dgrad on the 5th-gen tensor cores:
+// TMA-staged NDHWC bf16 operands, tcgen05.mma with fp32 accumulators in TMEM, fused bias + bf16 store +
+// BatchNorm statistics epilogue.  One persistent, warp-specialised CTA per SM.
+//
+// Mapping.  For one sample n and output plane d the (h,w) positions are linearised with a padded row pitch
+// Wp = W + 2*hw (hw = ks/2):  q = h*Wp + w'.  An M tile is 128 consecutive q.  For tap (kd,kh,kw) the A operand of the
+// tile is the same 128-row window of the *padded* input plane d+kd-hw shifted by kh*Wp + kw rows, so ONE TMA box
+// (channels x Wp x NH rows, out-of-bounds zero fill = the convolution padding) per (kd, 64-channel chunk) feeds all
+// ks*ks taps of that plane from shared memory: each tap's tcgen05.mma simply uses a shared-memory descriptor whose
+// start address is advanced by (shift * row bytes).  Rows with w' >= W (2 per output row) or h >= H are computed and
+// discarded in the epilogue.  Weights wf[tap][Cout][Cin] are the K-major B operand, one TMA box per (tap, chunk);
+// they stay resident in shared memory for the whole kernel when they fit (the two 32-channel layers) and are streamed
+// through a ring otherwise.
+#include <cuda.h>
 
-bool tmf_conv3d_fwd_umma_supported(int, int, int, int, int, int) { return false; }
-int tmf_conv3d_fwd_umma(int, const void* const*, const void* const*, const float* const*, void* const*,
-                        double* const*, int, int, int, int, int, int, int, void*) {
-  tmf::set_error("conv3d_fwd: tcgen05 path not built");
-  return 1;
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace tmf {
+using namespace umma;
+
+constexpr int UC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int UC_TILE_M = 128;
+constexpr int UC_MAX_BSTAGES = 27 * 4;
+constexpr int UC_MAX_ASTAGES = 4;
+constexpr uint32_t UC_SMEM_BUDGET = 227 * 1024;
+
+struct alignas(64) UmmaConvParams {
+  CUtensorMap tmA[TMF_MAX_GROUPS];
+  CUtensorMap tmB[TMF_MAX_GROUPS];
+  const float* bias[TMF_MAX_GROUPS];
+  __nv_bfloat16* y[TMF_MAX_GROUPS];
+  double* stats[TMF_MAX_GROUPS];
+  int ng, B, D, H, W, cin, cout, ks, hw;
+  int Wp, NH, QT;                 // padded row pitch, slab rows (in h), q tiles per plane
+  int tiles_per_group;
+  int nchunk, chunk, row_bytes;   // K chunks per tap, channels per chunk, bytes per smem row
+  uint32_t layout;                // UMMA layout type (SW128 / SW64)
+  int SA, SB, b_resident;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  int bo_mode;                    // how the descriptor base-offset field is derived (bring-up switch)
+};
+
+__device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
+  if (mode == 1) return (saddr >> 7) & 7u;
+  if (mode == 2) return (saddr >> 7) & 3u;
+  return 0u;
 }
+
+__global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smA = smem_base;
+  const uint32_t smB = smA + (uint32_t)p.SA * p.a_stage_bytes;
+  const uint32_t bars = smB + (uint32_t)p.SB * p.b_stage_bytes;       // 8-byte barriers
+  const uint32_t a_full = bars, a_empty = a_full + 8 * UC_MAX_ASTAGES;
+  const uint32_t b_full = a_empty + 8 * UC_MAX_ASTAGES, b_empty = b_full + 8 * UC_MAX_BSTAGES;
+  const uint32_t acc_full = b_empty + 8 * UC_MAX_BSTAGES, acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t stats_sm = tmem_slot + 16;                             // float [2][256]
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  float* stats_ptr = reinterpret_cast<float*>(gen_base + (stats_sm - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % p.ng;
+  const int cta = blockIdx.x / p.ng, ncta = gridDim.x / p.ng;
+  const int taps2 = p.ks * p.ks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    fence_barrier_init();
+    prefetch_tmap(&p.tmA[g]);
+    prefetch_tmap(&p.tmB[g]);
+  }
+  for (int i = threadIdx.x; i < 512; i += UC_THREADS) stats_ptr[i] = 0.f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      unsigned long long loaded_lo = 0ull, loaded_hi = 0ull;   // resident-B bookkeeping (<= 108 stages)
+      for (int tile = cta; tile < p.tiles_per_group; tile += ncta) {
+        int r = tile;
+        const int qt = r % p.QT; r /= p.QT;
+        const int d = r % p.D;
+        const int n = r / p.D;
+        const int h0 = (qt * UC_TILE_M) / p.Wp;
+        for (int kd = 0; kd < p.ks; ++kd) {
+          const int dd = d + kd - p.hw;
+          if (dd < 0 || dd >= p.D) continue;
+          for (int c = 0; c < p.nchunk; ++c) {
+            mbar_wait(a_empty + 8 * sa, pa ^ 1u);
+            mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
+            tma_load_5d(smA + (uint32_t)sa * p.a_stage_bytes, &p.tmA[g], a_full + 8 * sa, c * p.chunk, -p.hw,
+                        h0 - p.hw, dd, n);
+            if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+            for (int t = 0; t < taps2; ++t) {
+              const int tap = kd * taps2 + t;
+              if (p.b_resident) {
+                const int idx = tap * p.nchunk + c;
+                const bool have = idx < 64 ? ((loaded_lo >> idx) & 1ull) : ((loaded_hi >> (idx - 64)) & 1ull);
+                if (!have) {
+                  if (idx < 64) loaded_lo |= 1ull << idx; else loaded_hi |= 1ull << (idx - 64);
+                  mbar_expect_tx(b_full + 8 * idx, p.b_tx_bytes);
+                  tma_load_3d(smB + (uint32_t)idx * p.b_stage_bytes, &p.tmB[g], b_full + 8 * idx, c * p.chunk, 0, tap);
+                }
+              } else {
+                mbar_wait(b_empty + 8 * sb, pb ^ 1u);
+                mbar_expect_tx(b_full + 8 * sb, p.b_tx_bytes);
+                tma_load_3d(smB + (uint32_t)sb * p.b_stage_bytes, &p.tmB[g], b_full + 8 * sb, c * p.chunk, 0, tap);
+                if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================== MMA issuer =============================================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
+      const int ksteps = p.chunk / 16;
+      int it = 0;
+      for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
+        int r = tile;
+        const int qt = r % p.QT; r /= p.QT;
+        const int d = r % p.D;
+        const int q0 = qt * UC_TILE_M;
+        const int qoff = q0 % p.Wp;
+        const int as = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
+        uint32_t accumulate = 0;
+        for (int kd = 0; kd < p.ks; ++kd) {
+          const int dd = d + kd - p.hw;
+          if (dd < 0 || dd >= p.D) continue;
+          for (int c = 0; c < p.nchunk; ++c) {
+            mbar_wait(a_full + 8 * sa, pa);
+            tc_fence_after();
+            const uint32_t a_base = smA + (uint32_t)sa * p.a_stage_bytes;
+            for (int t = 0; t < taps2; ++t) {
+              const int tap = kd * taps2 + t;
+              const int kh = t / p.ks, kw = t % p.ks;
+              uint32_t b_base;
+              if (p.b_resident) {
+                const int idx = tap * p.nchunk + c;
+                mbar_wait(b_full + 8 * idx, 0u);
+                b_base = smB + (uint32_t)idx * p.b_stage_bytes;
+              } else {
+                mbar_wait(b_full + 8 * sb, pb);
+                b_base = smB + (uint32_t)sb * p.b_stage_bytes;
+              }
+              tc_fence_after();
+              const uint32_t a_tap = a_base + (uint32_t)(qoff + kh * p.Wp + kw) * (uint32_t)p.row_bytes;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t a_addr = a_tap + 32u * k, b_addr = b_base + 32u * k;
+                const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, p.layout, desc_base_offset(a_addr, p.bo_mode));
+                const uint64_t bdesc = make_smem_desc(b_addr, 16, sbo, p.layout, 0);
+                mma_bf16_ss(d_tmem, adesc, bdesc, p.idesc, accumulate);
+                accumulate = 1;
+              }
+              if (!p.b_resident) {
+                mma_commit(b_empty + 8 * sb);
+                if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+              }
+            }
+            mma_commit(a_empty + 8 * sa);
+            if (++sa == p.SA) { sa = 0; pa ^= 1u; }
+          }
+        }
+        mma_commit(acc_full + 8 * as);
+      }
+    }
+  } else {
+    // =========================================== epilogue ================================================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const float* bias = p.bias[g];
+    __nv_bfloat16* yg = p.y[g];
+    const bool want_stats = p.stats[g] != nullptr;
+    int it = 0;
+    for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
+      int r = tile;
+      const int qt = r % p.QT; r /= p.QT;
+      const int d = r % p.D;
+      const int n = r / p.D;
+      const int q = qt * UC_TILE_M + row;
+      const int h = q / p.Wp, w = q - h * p.Wp;
+      const bool valid = (h < p.H) && (w < p.W);
+      const int as = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(acc_full + 8 * as, acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout);
+      __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout;
+      for (int c0 = 0; c0 < p.cout; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(taddr + (uint32_t)c0, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(raw[j]);
+          if (bias != nullptr) a += __ldg(bias + c0 + j);
+          v[j] = valid ? round_bf16(a) : 0.f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) *reinterpret_cast<uint4*>(yrow + c0 + qd * 8) = pack8(&v[qd * 8]);
+        }
+        if (want_stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          // transpose-reduce: lane l ends with the warp total of column c0 + l
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float s_send = upper ? v[i] : v[i + off];
+              const float s_keep = upper ? v[i + off] : v[i];
+              v[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+              const float q_send = upper ? sq[i] : sq[i + off];
+              const float q_keep = upper ? sq[i + off] : sq[i];
+              sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+            }
+          }
+          atomicAdd(&stats_ptr[c0 + lane], v[0]);
+          atomicAdd(&stats_ptr[256 + c0 + lane], sq[0]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty + 8 * as);
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < p.cout; i += 128) {
+        atomicAdd(&p.stats[g][i], (double)stats_ptr[i]);
+        atomicAdd(&p.stats[g][p.cout + i], (double)stats_ptr[256 + i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct UmmaPlan {
+  bool ok;
+  int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident;
+  uint32_t layout, a_stage_bytes, b_stage_bytes, a_tx, b_tx, tmem_cols, smem_bytes;
+  CUtensorMapSwizzle swz;
+};
+
+static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
+  UmmaPlan pl{};
+  pl.ok = false;
+  if (ks != 1 && ks != 3) return pl;
+  if (cin % 32 != 0 || cout % 32 != 0 || cout < 32 || cout > 256 || cin < 32) return pl;
+  const int hw = ks / 2;
+  pl.chunk = (cin % 64 == 0) ? 64 : 32;
+  pl.nchunk = cin / pl.chunk;
+  pl.row_bytes = pl.chunk * 2;
+  pl.layout = (pl.chunk == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+  pl.swz = (pl.chunk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  pl.Wp = W + 2 * hw;
+  const int rmax = (pl.Wp - 1) + (ks - 1) * pl.Wp + (ks - 1) + (UC_TILE_M - 1);
+  pl.NH = rmax / pl.Wp + 1;
+  if (pl.Wp > 256 || pl.NH > 256) return pl;
+  pl.QT = (H * pl.Wp + UC_TILE_M - 1) / UC_TILE_M;
+  pl.a_tx = (uint32_t)pl.NH * pl.Wp * pl.row_bytes;
+  pl.a_stage_bytes = (pl.a_tx + 1023u) & ~1023u;
+  pl.b_tx = (uint32_t)cout * pl.row_bytes;
+  pl.b_stage_bytes = (pl.b_tx + 1023u) & ~1023u;
+  const int taps = ks * ks * ks;
+  const uint32_t fixed = 1024 /*align slack*/ + 8 * (2 * UC_MAX_ASTAGES + 2 * UC_MAX_BSTAGES) + 64 + 2048 + 256;
+  const uint32_t budget = UC_SMEM_BUDGET - fixed;
+  const uint32_t total_b = (uint32_t)taps * pl.nchunk * pl.b_stage_bytes;
+  if (taps * pl.nchunk <= UC_MAX_BSTAGES && total_b + 2 * pl.a_stage_bytes <= budget) {
+    pl.b_resident = 1;
+    pl.SB = taps * pl.nchunk;
+    pl.SA = (int)((budget - total_b) / pl.a_stage_bytes);
+    if (pl.SA > UC_MAX_ASTAGES) pl.SA = UC_MAX_ASTAGES;
+  } else {
+    pl.b_resident = 0;
+    pl.SA = 3;
+    if (3 * pl.a_stage_bytes + 2 * pl.b_stage_bytes > budget) pl.SA = 2;
+    if ((uint32_t)pl.SA * pl.a_stage_bytes + 2 * pl.b_stage_bytes > budget) return pl;
+    pl.SB = (int)((budget - (uint32_t)pl.SA * pl.a_stage_bytes) / pl.b_stage_bytes);
+    if (pl.SB > 8) pl.SB = 8;
+  }
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * cout)) cols <<= 1;
+  if (cols > 512) return pl;
+  pl.tmem_cols = cols;
+  pl.smem_bytes = fixed + (uint32_t)pl.SA * pl.a_stage_bytes + (uint32_t)pl.SB * pl.b_stage_bytes;
+  pl.ok = pl.smem_bytes <= UC_SMEM_BUDGET;
+  return pl;
+}
+
+static int umma_bo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TMF_UMMA_BO");
+    mode = e ? atoi(e) : 0;   // hardware swizzles on absolute smem address bits: verified on B200 (scripts/umma_bringup.py)
+  }
+  return mode;
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+bool tmf_conv3d_fwd_umma_supported(int D, int H, int W, int cin, int cout, int ksize) {
+  if (getenv("TMF_DISABLE_UMMA") != nullptr) return false;
+  return make_plan(D, H, W, cin, cout, ksize).ok;
+}
+
+int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, const float* const* bias,
+                        void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize,
+                        void* stream) {
+  TMF_CHECK_NG(ng);
+  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize);
+  TMF_REQUIRE(pl.ok, "conv3d_fwd_umma: unsupported problem");
+  EncodeTiledFn encode = get_encode_fn();
+  TMF_REQUIRE(encode != nullptr, "conv3d_fwd_umma: cuTensorMapEncodeTiled entry point not available");
+  UmmaConvParams p{};
+  p.ng = ng; p.B = B; p.D = D; p.H = H; p.W = W; p.cin = cin; p.cout = cout; p.ks = ksize; p.hw = ksize / 2;
+  p.Wp = pl.Wp; p.NH = pl.NH; p.QT = pl.QT;
+  p.tiles_per_group = B * D * pl.QT;
+  p.nchunk = pl.nchunk; p.chunk = pl.chunk; p.row_bytes = pl.row_bytes; p.layout = pl.layout;
+  p.SA = pl.SA; p.SB = pl.SB; p.b_resident = pl.b_resident;
+  p.a_stage_bytes = pl.a_stage_bytes; p.b_stage_bytes = pl.b_stage_bytes; p.a_tx_bytes = pl.a_tx; p.b_tx_bytes = pl.b_tx;
+  p.idesc = make_idesc_bf16(UC_TILE_M, cout, 0, 0);
+  p.tmem_cols = pl.tmem_cols;
+  p.bo_mode = umma_bo_mode();
+  const int taps = ksize * ksize * ksize;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < ng; ++g) {
+    TMF_REQUIRE(a[g] && wf[g] && y[g], "conv3d_fwd_umma: NULL device pointer");
+    TMF_REQUIRE(((uintptr_t)a[g] & 15) == 0 && ((uintptr_t)wf[g] & 15) == 0 && ((uintptr_t)y[g] & 15) == 0,
+                "conv3d_fwd_umma: tensors must be 16-byte aligned");
+    p.bias[g] = bias ? bias[g] : nullptr;
+    p.y[g] = (__nv_bfloat16*)y[g];
+    p.stats[g] = stats ? stats[g] : nullptr;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+      cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2,
+                               (cuuint64_t)D * H * W * cin * 2};
+      cuuint32_t box[5] = {(cuuint32_t)pl.chunk, (cuuint32_t)pl.Wp, (cuuint32_t)pl.NH, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&p.tmA[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a[g]), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
+      cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+      cuuint32_t box[3] = {(cuuint32_t)pl.chunk, (cuuint32_t)cout, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&p.tmB[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wf[g]), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_umma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    if (stats && stats[g]) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UC_SMEM_BUDGET));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_group = sms / ng;
+  if (per_group > p.tiles_per_group) per_group = p.tiles_per_group;
+  if (per_group < 1) per_group = 1;
+  dim3 grid(per_group * ng, 1, 1);
+  conv3d_umma_kernel<<<grid, UC_THREADS, pl.smem_bytes, st>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
 bool tmf_conv3d_wgrad_umma_supported(int, int, int, int, int, int) { return false; }
 int tmf_conv3d_wgrad_umma(int, const void* const*, const void* const*, float* const*, int, int, int, int, int, int,
                           int, void*) {
-  tmf::set_error("conv3d_wgrad: tcgen05 path not built");
+  tmf::set_error("conv3d_wgrad: tcgen05 path not built yet");
   return 1;
 }
