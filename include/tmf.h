@@ -72,9 +72,13 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
                    void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
                    int ksize, int impl, void* stream);
 
-/* dW (fp32, reference layout (Cout,Cin,k,k,k), overwritten) = sum_v dy[v,co] * a[v+tap,ci]. */
+/* dW (fp32, reference layout (Cout,Cin,k,k,k), overwritten) = sum_v dy[v,co] * a[v+tap,ci].
+ * `ws` is caller-owned scratch of at least tmf_conv3d_wgrad_workspace_bytes(...) bytes (fp32 split-K partials of the
+ * tcgen05 path, reduced in a fixed order -> deterministic); may be NULL when that returns 0. */
 int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float* const* dw,
-                     int B, int D, int H, int W, int cin, int cout, int ksize, int impl, void* stream);
+                     int B, int D, int H, int W, int cin, int cout, int ksize, int impl,
+                     void* ws, size_t ws_bytes, void* stream);
+int64_t tmf_conv3d_wgrad_workspace_bytes(int ng, int impl, int B, int D, int H, int W, int cin, int cout, int ksize);
 
 /* 1 if implementation `impl` (TMF_CONV_DIRECT / TMF_CONV_UMMA) handles this problem, else 0.
  * op: 0 = forward / dgrad (tmf_conv3d_fwd), 1 = weight gradient (tmf_conv3d_wgrad). */

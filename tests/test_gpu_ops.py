@@ -99,7 +99,9 @@ def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
            B, D, H, W, cout, cin, ks, impl)
     assert max_rel(from_ndhwc(da), a_ref.grad) < 6e-3, "dgrad"
     dw = torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=DEV)
-    L.call("tmf_conv3d_wgrad", 1, L.ptrs([dy_d]), L.ptrs([a_d]), L.ptrs([dw]), B, D, H, W, cin, cout, ks, impl)
+    ws = TF.wgrad_workspace(1, impl, B, D, H, W, cin, cout, ks, DEV)
+    L.call("tmf_conv3d_wgrad", 1, L.ptrs([dy_d]), L.ptrs([a_d]), L.ptrs([dw]), B, D, H, W, cin, cout, ks, impl,
+           L.ptr(ws), 0 if ws is None else ws.numel())
     assert rel_l2(dw.cpu(), w_ref.grad) < 2e-3, "wgrad"
 
 

@@ -435,7 +435,8 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                         int ksize, void* stream);
 bool tmf_conv3d_fwd_umma_supported(int D, int H, int W, int cin, int cout, int ksize);
 int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H,
-                          int W, int cin, int cout, int ksize, void* stream);
+                          int W, int cin, int cout, int ksize, void* ws, size_t ws_bytes, void* stream);
+size_t tmf_conv3d_wgrad_umma_workspace(int ng, int B, int D, int H, int W, int cin, int cout, int ksize);
 bool tmf_conv3d_wgrad_umma_supported(int D, int H, int W, int cin, int cout, int ksize);
 
 extern "C" {
@@ -545,8 +546,14 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
   return 0;
 }
 
+int64_t tmf_conv3d_wgrad_workspace_bytes(int ng, int impl, int B, int D, int H, int W, int cin, int cout, int ksize) {
+  if (impl == TMF_CONV_DIRECT) return 0;
+  if (!tmf_conv3d_wgrad_umma_supported(D, H, W, cin, cout, ksize)) return 0;
+  return (int64_t)tmf_conv3d_wgrad_umma_workspace(ng, B, D, H, W, cin, cout, ksize);
+}
+
 int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H,
-                     int W, int cin, int cout, int ksize, int impl, void* stream) {
+                     int W, int cin, int cout, int ksize, int impl, void* ws, size_t ws_bytes, void* stream) {
   TMF_CHECK_NG(ng);
   TMF_REQUIRE(ksize == 1 || ksize == 3, "conv3d_wgrad: ksize must be 1 or 3 (got %d)", ksize);
   TMF_REQUIRE(cin % 8 == 0 && cout % 8 == 0, "conv3d_wgrad: need Cin %% 8 == 0 and Cout %% 8 == 0 (got %d, %d)", cin,
@@ -557,7 +564,7 @@ int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float*
     TMF_REQUIRE(tmf_conv3d_wgrad_umma_supported(D, H, W, cin, cout, ksize),
                 "conv3d_wgrad: tcgen05 path does not support D,H,W=%d,%d,%d Cin=%d Cout=%d k=%d", D, H, W, cin, cout,
                 ksize);
-    return tmf_conv3d_wgrad_umma(ng, dy, a, dw, B, D, H, W, cin, cout, ksize, stream);
+    return tmf_conv3d_wgrad_umma(ng, dy, a, dw, B, D, H, W, cin, cout, ksize, ws, ws_bytes, stream);
   }
   WgradDirectArgs p;
   if (!load_group(p.dy, (const __nv_bfloat16* const*)dy, ng, true, "dy") ||

@@ -423,10 +423,3 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   TMF_LAUNCH_CHECK();
   return 0;
 }
-
-bool tmf_conv3d_wgrad_umma_supported(int, int, int, int, int, int) { return false; }
-int tmf_conv3d_wgrad_umma(int, const void* const*, const void* const*, float* const*, int, int, int, int, int, int,
-                          int, void*) {
-  tmf::set_error("conv3d_wgrad: tcgen05 path not built yet");
-  return 1;
-}

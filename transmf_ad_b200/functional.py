@@ -42,6 +42,12 @@ class SNetSpec:
         self.dim = dim
 
 
+def wgrad_workspace(ng, impl, B, D, H, W, cin, cout, ks, dev):
+    """Caller-owned scratch for the split-K partials of the tcgen05 weight-gradient kernel (None if not needed)."""
+    n = int(L.load().tmf_conv3d_wgrad_workspace_bytes(ng, impl, B, D, H, W, cin, cout, ks))
+    return torch.empty(n, dtype=torch.uint8, device=dev) if n > 0 else None
+
+
 def _pooled(D, H, W, pool):
     return (D, H, W) if pool == L.POOL_NONE else (D // 2, H // 2, W // 2)
 
@@ -149,8 +155,9 @@ class SNetFunction(torch.autograd.Function):
             if l == 0:
                 L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout)
             else:
+                ws = wgrad_workspace(ng, ctx.impl, B, Dl, Hl, Wl, cin, cout, ks, dev)
                 L.call("tmf_conv3d_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cin, cout, ks,
-                       ctx.impl)
+                       ctx.impl, L.ptr(ws), 0 if ws is None else ws.numel())
                 da = [torch.empty((B, Dl, Hl, Wl, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(dy), L.ptrs(wd), L.ptrs(None), L.ptrs(da), L.ptrs(None),
                        B, Dl, Hl, Wl, cout, cin, ks, ctx.impl, tag="tmf_conv3d_dgrad")
