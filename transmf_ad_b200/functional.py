@@ -97,7 +97,7 @@ class SNetFunction(torch.autograd.Function):
                     wd = [torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
                 L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs(wf), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
-                       B, Dl, Hl, Wl, cin, cout, ks, impl)
+                       B, Dl, Hl, Wl, cin, cout, ks, impl, tag=f"tmf_conv3d_fwd@L{l}")
             coef = [torch.empty(4 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             L.call("tmf_bn_finalize", ng, L.ptrs(stats), L.ptrs([P(t, l, 2) for t in range(ng)]),
                    L.ptrs([P(t, l, 3) for t in range(ng)]), L.ptrs([buffers[t][l][0] for t in range(ng)]),
@@ -108,7 +108,7 @@ class SNetFunction(torch.autograd.Function):
             out = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if last else torch.bfloat16, device=dev)
                    for _ in range(ng)]
             L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), int(last), B, Dl, Hl, Wl, cout,
-                   pool, LRELU_SLOPE)
+                   pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
             if need_grad:
                 saved.append((act, y, coef, wd, dims))
             act = out
@@ -141,7 +141,7 @@ class SNetFunction(torch.autograd.Function):
             count = B * Dl * Hl * Wl
             sums = [torch.empty(2 * cout, dtype=torch.float64, device=dev) for _ in range(ng)]
             L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
-                   B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE)
+                   B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
             dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
@@ -150,17 +150,17 @@ class SNetFunction(torch.autograd.Function):
                    L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
             dy = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
             L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef),
-                   L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE)
+                   L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_apply@L{l}")
             dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
             if l == 0:
                 L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout)
             else:
                 ws = wgrad_workspace(ng, ctx.impl, B, Dl, Hl, Wl, cin, cout, ks, dev)
                 L.call("tmf_conv3d_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cin, cout, ks,
-                       ctx.impl, L.ptr(ws), 0 if ws is None else ws.numel())
+                       ctx.impl, L.ptr(ws), 0 if ws is None else ws.numel(), tag=f"tmf_conv3d_wgrad@L{l}")
                 da = [torch.empty((B, Dl, Hl, Wl, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(dy), L.ptrs(wd), L.ptrs(None), L.ptrs(da), L.ptrs(None),
-                       B, Dl, Hl, Wl, cout, cin, ks, ctx.impl, tag="tmf_conv3d_dgrad")
+                       B, Dl, Hl, Wl, cout, cin, ks, ctx.impl, tag=f"tmf_conv3d_dgrad@L{l}")
                 dout, dout_fp32 = da, 0
             for t in range(ng):
                 base = (t * 7 + l) * 4
