@@ -129,94 +129,60 @@ conv1_fwd_kernel(GroupPtr<const float> x, GroupPtr<const float> w, GroupPtr<cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// conv1.0 weight gradient: dW[co][tap] = sum_v dy[v,co] * x[v + shift(tap)]
+// conv1.0 weight gradient: dW[co][tap] = sum_v dy[v,co] * x[v + shift(tap)]      (fp32 accumulate, fp32 x)
+// lane = voxel (coalesced x / dy reads), each warp owns 4 output channels x 27 taps = 108 register accumulators
+// over all the voxels its block visits; one transposing warp reduction + 108 atomics per warp at the very end.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int C1W_CHUNK = 64;
+constexpr int C1W_THREADS = 256;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(C1W_THREADS)
 conv1_wgrad_kernel(GroupPtr<const __nv_bfloat16> dy, GroupPtr<const float> x, GroupPtr<float> dw, int B, int D,
-                   int H, int W, int cout, int chunks_per_block) {
+                   int H, int W, int cout) {
   const int g = blockIdx.z;
-  __shared__ float dys[C1W_CHUNK][65];
-  __shared__ int cd[C1W_CHUNK], chh[C1W_CHUNK], cw[C1W_CHUNK];
   const int64_t M = (int64_t)B * D * H * W;
-  const int lane_co = threadIdx.x & 31;
-  const int tg = threadIdx.x >> 5;  // 0..7 -> taps tg, tg+8, tg+16, tg+24
-  float acc[2][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
-  int tkd[4], tkh[4], tkw[4];
-  bool tok[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int t = tg + 8 * j;
-    tok[j] = t < 27;
-    tkd[j] = t / 9 - 1;
-    tkh[j] = (t / 3) % 3 - 1;
-    tkw[j] = t % 3 - 1;
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ngroups = cout >> 2;                                  // groups of 4 output channels
   const float* xg = x.p[g];
-  for (int c = 0; c < chunks_per_block; ++c) {
-    const int64_t m0 = ((int64_t)blockIdx.x * chunks_per_block + c) * C1W_CHUNK;
-    if (m0 >= M) break;
-    __syncthreads();
-    // stage dy chunk (64 voxels x cout) as fp32
-    for (int i = threadIdx.x; i < C1W_CHUNK * (cout / 8); i += 256) {
-      const int v = i / (cout / 8), q = i % (cout / 8);
-      float f[8];
-      if (m0 + v < M) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(dy.p[g] + (m0 + v) * cout + q * 8);
-        unpack8(raw, f);
-      } else {
+  const __nv_bfloat16* dyg = dy.p[g];
+  for (int cg = warp; cg < ngroups; cg += C1W_THREADS / 32) {
+    float acc[4][27];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-      }
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dys[v][q * 8 + j] = f[j];
+      for (int t = 0; t < 27; ++t) acc[c][t] = 0.f;
+    for (int64_t m0 = (int64_t)blockIdx.x * 32; m0 < M; m0 += (int64_t)gridDim.x * 32) {
+      const int64_t m = m0 + lane;
+      if (m >= M) continue;
+      const int wq = (int)(m % W);
+      const int hq = (int)((m / W) % H);
+      const int dq = (int)((m / ((int64_t)W * H)) % D);
+      const uint2 raw = *reinterpret_cast<const uint2*>(dyg + m * cout + cg * 4);
+      const float d0 = bf16_lo(raw.x), d1 = bf16_hi(raw.x), d2 = bf16_lo(raw.y), d3 = bf16_hi(raw.y);
+      const float* xp = xg + m;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int dd = dq + kd - 1, hh = hq + kh - 1, ww = wq + kw - 1;
+            const bool ok = dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const float xv = ok ? __ldg(xp + ((int64_t)(kd - 1) * H + (kh - 1)) * W + (kw - 1)) : 0.f;
+            const int t = (kd * 3 + kh) * 3 + kw;
+            acc[0][t] = fmaf(d0, xv, acc[0][t]);
+            acc[1][t] = fmaf(d1, xv, acc[1][t]);
+            acc[2][t] = fmaf(d2, xv, acc[2][t]);
+            acc[3][t] = fmaf(d3, xv, acc[3][t]);
+          }
     }
-    if (threadIdx.x < C1W_CHUNK) {
-      const int64_t m = m0 + threadIdx.x;
-      if (m < M) {
-        cw[threadIdx.x] = (int)(m % W);
-        chh[threadIdx.x] = (int)((m / W) % H);
-        cd[threadIdx.x] = (int)((m / ((int64_t)W * H)) % D);
-      } else {
-        cw[threadIdx.x] = -100000;  // every tap out of bounds
-        chh[threadIdx.x] = 0;
-        cd[threadIdx.x] = 0;
-      }
-    }
-    __syncthreads();
-    for (int v = 0; v < C1W_CHUNK; ++v) {
-      const int dq = cd[v], hq = chh[v], wq = cw[v];
-      const float* xp = xg + m0 + v;
-      float xv[4];
+    // reduce across the 32 lanes: 4 rounds of the 32-value transposing butterfly (27 taps + 5 zero slots)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int dd = dq + tkd[j], hh = hq + tkh[j], ww = wq + tkw[j];
-        const bool ok = tok[j] && dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W;
-        xv[j] = ok ? __ldg(xp + ((int64_t)tkd[j] * H + tkh[j]) * W + tkw[j]) : 0.f;
-      }
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const int co = lane_co + 32 * a;
-        if (co < cout) {
-          const float d = dys[v][co];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[a][j] = fmaf(d, xv[j], acc[a][j]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int co = lane_co + 32 * a;
-    if (co < cout) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (tok[j]) atomicAdd(&dw.p[g][co * 27 + tg + 8 * j], acc[a][j]);
+      for (int t = 0; t < 32; ++t) v[t] = (t < 27) ? acc[c][t] : 0.f;
+      const float tot = warp_transpose_reduce32(v, lane);
+      if (lane < 27) atomicAdd(&dw.p[g][(cg * 4 + c) * 27 + lane], tot);
     }
   }
 }
@@ -505,11 +471,8 @@ int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float*
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(dw[g], 0, sizeof(float) * 27 * cout, st));
   const int64_t M = (int64_t)B * D * H * W;
-  const int64_t nchunks = ceil_div(M, C1W_CHUNK);
-  const int blocks = (int)(nchunks < 148 * 8 ? nchunks : 148 * 8);
-  const int cpb = ceil_div(nchunks, blocks);
-  dim3 grid(ceil_div(nchunks, cpb), 1, ng);
-  conv1_wgrad_kernel<<<grid, 256, 0, st>>>(gdy, gx, gdw, B, D, H, W, cout, cpb);
+  dim3 grid((unsigned)min(ceil_div(M, 32), 148 * 4), 1, ng);
+  conv1_wgrad_kernel<<<grid, C1W_THREADS, 0, st>>>(gdy, gx, gdw, B, D, H, W, cout);
   TMF_LAUNCH_CHECK();
   return 0;
 }

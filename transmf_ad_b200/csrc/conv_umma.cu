@@ -131,18 +131,24 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
     }
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
+    // One thread issues every tcgen05.mma of the CTA, so its scalar work per MMA is the limiter for the narrow
+    // layers: descriptors are split into a constant high word and a low word that only needs an add per MMA.
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
       const int ksteps = p.chunk / 16;
+      const uint64_t desc_hi = make_smem_desc(0, 16, sbo, p.layout, 0) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo_const = (uint32_t)(make_smem_desc(0, 16, sbo, p.layout, 0) & 0xFFFF0000ull);
+      const uint32_t row_units = (uint32_t)p.row_bytes >> 4;
+      unsigned long long waited_lo = 0ull, waited_hi = 0ull;   // resident-B stages already known to be loaded
       int it = 0;
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
         const int d = r % p.D;
         const int q0 = qt * UC_TILE_M;
-        const int qoff = q0 % p.Wp;
+        const uint32_t qoff_units = (uint32_t)(q0 % p.Wp) * row_units;
         const int as = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
@@ -155,31 +161,37 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
           for (int c = 0; c < p.nchunk; ++c) {
             mbar_wait(a_full + 8 * sa, pa);
             tc_fence_after();
-            const uint32_t a_base = smA + (uint32_t)sa * p.a_stage_bytes;
-            for (int t = 0; t < taps2; ++t) {
-              const int tap = kd * taps2 + t;
-              const int kh = t / p.ks, kw = t % p.ks;
-              uint32_t b_base;
-              if (p.b_resident) {
-                const int idx = tap * p.nchunk + c;
-                mbar_wait(b_full + 8 * idx, 0u);
-                b_base = smB + (uint32_t)idx * p.b_stage_bytes;
-              } else {
-                mbar_wait(b_full + 8 * sb, pb);
-                b_base = smB + (uint32_t)sb * p.b_stage_bytes;
-              }
-              tc_fence_after();
-              const uint32_t a_tap = a_base + (uint32_t)(qoff + kh * p.Wp + kw) * (uint32_t)p.row_bytes;
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t a_addr = a_tap + 32u * k, b_addr = b_base + 32u * k;
-                const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, p.layout, desc_base_offset(a_addr, p.bo_mode));
-                const uint64_t bdesc = make_smem_desc(b_addr, 16, sbo, p.layout, 0);
-                mma_bf16_ss(d_tmem, adesc, bdesc, p.idesc, accumulate);
-                accumulate = 1;
-              }
-              if (!p.b_resident) {
-                mma_commit(b_empty + 8 * sb);
-                if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+            const uint32_t a_slab_lo = desc_lo_const | (((smA + (uint32_t)sa * p.a_stage_bytes) & 0x3FFFFu) >> 4);
+            int tap = kd * taps2;
+            for (int kh = 0; kh < p.ks; ++kh) {
+              uint32_t a_lo = a_slab_lo + qoff_units + (uint32_t)(kh * p.Wp) * row_units;
+              for (int kw = 0; kw < p.ks; ++kw, ++tap, a_lo += row_units) {
+                uint32_t b_addr;
+                if (p.b_resident) {
+                  const int idx = tap * p.nchunk + c;
+                  const bool seen = idx < 64 ? ((waited_lo >> idx) & 1ull) : ((waited_hi >> (idx - 64)) & 1ull);
+                  if (!seen) {
+                    mbar_wait(b_full + 8 * idx, 0u);
+                    tc_fence_after();
+                    if (idx < 64) waited_lo |= 1ull << idx; else waited_hi |= 1ull << (idx - 64);
+                  }
+                  b_addr = smB + (uint32_t)idx * p.b_stage_bytes;
+                } else {
+                  mbar_wait(b_full + 8 * sb, pb);
+                  tc_fence_after();
+                  b_addr = smB + (uint32_t)sb * p.b_stage_bytes;
+                }
+                const uint32_t b_lo = desc_lo_const | ((b_addr & 0x3FFFFu) >> 4);
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
+                              accumulate);
+                  accumulate = 1;
+                }
+                if (!p.b_resident) {
+                  mma_commit(b_empty + 8 * sb);
+                  if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+                }
               }
             }
             mma_commit(a_empty + 8 * sa);

@@ -119,23 +119,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_umma_kernel(const 
       uint32_t ph = 0;
       const uint32_t sbo_x = 8u * p.rbx, sbo_y = 8u * p.rby;
       const int ksteps = p.TK / 16;
+      // descriptors: constant high word; low word = start address (16-byte units) | LBO << 16
+      const uint64_t hi_x = make_smem_desc(0, 0, sbo_x, p.layx, 0) & 0xFFFFFFFF00000000ull;
+      const uint64_t hi_y = make_smem_desc(0, 0, sbo_y, p.layy, 0) & 0xFFFFFFFF00000000ull;
+      const uint32_t y_lo_const = ((p.y_slab_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t kstep_x = (16u * p.rbx) >> 4, kstep_y = (16u * p.rby) >> 4;
       uint32_t accumulate = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         const int qt = kt % p.QT;
-        const int qoff = (qt * p.TK) % p.Wp;
+        const uint32_t qoff = (uint32_t)((qt * p.TK) % p.Wp);
         mbar_wait(full + 8 * s, ph);
         tc_fence_after();
         const uint32_t st = smem_base + (uint32_t)s * p.stage_bytes;
-        const uint32_t ybase = st + p.y_region_off + (uint32_t)qoff * p.rby;
+        const uint32_t y_lo = y_lo_const | (((st + p.y_region_off + qoff * p.rby) & 0x3FFFFu) >> 4);
+        const uint32_t x_units = ((st + qoff * p.rbx) & 0x3FFFFu) >> 4;
         for (int gi = 0; gi < S.ng; ++gi) {
           const WgGroup& G = p.grp[S.g0 + gi];
-          const uint32_t abase = st + G.a_off + (uint32_t)qoff * p.rbx;
+          const uint32_t a_lo = ((((G.a_lbo >> 4) & 0x3FFFu) << 16) | x_units) + (G.a_off >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.cout);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = make_smem_desc(abase + (uint32_t)k * 16u * p.rbx, G.a_lbo, sbo_x, p.layx, 0);
-            const uint64_t bdesc = make_smem_desc(ybase + (uint32_t)k * 16u * p.rby, p.y_slab_bytes, sbo_y, p.layy, 0);
-            mma_bf16_ss(d_tmem, adesc, bdesc, p.idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
-          }
+          mma_bf16_ss(d_tmem, hi_x | (uint64_t)a_lo, hi_y | (uint64_t)y_lo, p.idesc, accumulate);
+#pragma unroll 7
+          for (int k = 1; k < ksteps; ++k)
+            mma_bf16_ss(d_tmem, hi_x | (uint64_t)(a_lo + k * kstep_x), hi_y | (uint64_t)(y_lo + k * kstep_y), p.idesc, 1u);
         }
         accumulate = 1;
         mma_commit(empty + 8 * s);
