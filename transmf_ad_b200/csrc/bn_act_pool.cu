@@ -148,7 +148,14 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
 
 // Backward over 2x2x2 windows (or single voxels when pool == NONE).  REDUCE: accumulate sum dz, sum dz*xhat.
 // APPLY: write dy = scale * (dz - m1 - xhat*m2) for every existing input voxel (incl. those dropped by floor pooling).
-template <bool APPLY>
+//
+// ALU diet (these passes are instruction-bound, not HBM-bound, if written naively):
+//  * LeakyReLU and the BatchNorm affine map are monotonic, so the max-pool arg-max is found on the raw y values
+//    (times sign(scale)), first maximum in (d,h,w) scan order with a strict compare exactly like torch;
+//  * only the arg-max position carries dz for a max pool, so REDUCE touches one position per channel;
+//  * APPLY folds the constant part into one FMA per element:  dy = A + Bc*y (+ scale*dz at the arg-max),
+//    A = scale*(m2*invstd*mean - m1),  Bc = -scale*m2*invstd.
+template <bool APPLY, int POOL>
 __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
   const int g = blockIdx.z;
   extern __shared__ float red[];  // [2][C] (REDUCE only)
@@ -160,11 +167,12 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
   const int Dw = APPLY ? p.Dc : p.Do, Hw = APPLY ? p.Hc : p.Ho, Ww = APPLY ? p.Wc : p.Wo;
   const int64_t total = (int64_t)p.B * Dw * Hw * Ww * CQ;
   const __nv_bfloat16* yg = p.y.p[g];
+  constexpr int NPOS = (POOL == TMF_POOL_NONE) ? 1 : 8;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int last_cq = -1;
-  const int npos = (p.pool == TMF_POOL_NONE) ? 1 : 8;
+  float sc[8], sh[8], mu[8], is[8], cA[8], cB[8], sg[8];
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int cq = (int)(idx % CQ);
@@ -174,8 +182,8 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
     const int dw = (int)(r % Dw);
     const int n = (int)(r / Dw);
     const int c0 = cq * 8;
-    if (!APPLY && cq != last_cq) {
-      if (last_cq >= 0) {
+    if (cq != last_cq) {                       // (host keeps a thread's channel chunk loop-invariant)
+      if (!APPLY && last_cq >= 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           atomicAdd(&red[last_cq * 8 + j], s1[j]);
@@ -184,74 +192,104 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
         }
       }
       last_cq = cq;
-    }
-    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = p.coef.p[g][c0 + j];
-      sh[j] = p.coef.p[g][p.C + c0 + j];
-      mu[j] = p.coef.p[g][2 * p.C + c0 + j];
-      is[j] = p.coef.p[g][3 * p.C + c0 + j];
-      if (APPLY) { m1[j] = p.bcoef.p[g][c0 + j]; m2[j] = p.bcoef.p[g][p.C + c0 + j]; }
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = p.coef.p[g][c0 + j];
+        sh[j] = p.coef.p[g][p.C + c0 + j];
+        mu[j] = p.coef.p[g][2 * p.C + c0 + j];
+        is[j] = p.coef.p[g][3 * p.C + c0 + j];
+        sg[j] = sc[j] > 0.f ? 1.f : (sc[j] < 0.f ? -1.f : 0.f);
+        if (APPLY) {
+          const float m1 = p.bcoef.p[g][c0 + j], m2 = p.bcoef.p[g][p.C + c0 + j];
+          cB[j] = -sc[j] * m2 * is[j];
+          cA[j] = -sc[j] * m1 - cB[j] * mu[j];
+        }
+      }
     }
-    const bool win_ok = (p.pool == TMF_POOL_NONE) || (dw < p.Do && hw < p.Ho && ww < p.Wo);
+    const bool win_ok = (POOL == TMF_POOL_NONE) || (dw < p.Do && hw < p.Ho && ww < p.Wo);
     float go[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) go[j] = 0.f;
     if (win_ok) {
-      const int64_t ooff = (p.pool == TMF_POOL_NONE)
+      const int64_t ooff = (POOL == TMF_POOL_NONE)
                                ? ((((int64_t)n * p.D + dw) * p.H + hw) * p.W + ww) * p.C + c0
                                : ((((int64_t)n * p.Do + dw) * p.Ho + hw) * p.Wo + ww) * p.C + c0;
       load8f(p.dout.p[g], ooff, p.fp32io, go);
     }
-    // pass 1 (max only): locate the first maximum of the activation per channel
-    int amax[8];
+    // gather the window (existing positions only)
+    uint4 raw[NPOS];
+    bool ex[NPOS];
+    int64_t off[NPOS];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) amax[j] = 0;
-    if (p.pool == TMF_POOL_MAX && win_ok) {
-      float best[8];
+    for (int q = 0; q < NPOS; ++q) {
+      int di, hi, wi;
+      if (POOL == TMF_POOL_NONE) { di = dw; hi = hw; wi = ww; }
+      else { di = 2 * dw + (q >> 2); hi = 2 * hw + ((q >> 1) & 1); wi = 2 * ww + (q & 1); }
+      ex[q] = di < p.D && hi < p.H && wi < p.W;
+      off[q] = ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0;
+      raw[q] = ex[q] ? *reinterpret_cast<const uint4*>(yg + off[q]) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (POOL == TMF_POOL_MAX) {
+      // arg-max per channel on sign(scale)*y; dz only at the arg-max
+      float best[8], ybest[8];
+      int amax[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; ybest[j] = 0.f; amax[j] = 0; }
+      if (win_ok) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int di = 2 * dw + (q >> 2), hi = 2 * hw + ((q >> 1) & 1), wi = 2 * ww + (q & 1);
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(yg + ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0), f);
+        for (int q = 0; q < NPOS; ++q) {
+          float f[8];
+          unpack8(raw[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float key = f[j] * sg[j];
+            if (key > best[j]) { best[j] = key; ybest[j] = f[j]; amax[j] = q; }
+          }
+        }
+      }
+      float dzs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(ybest[j], sc[j], sh[j]);
+        const float dz = win_ok ? (z > 0.f ? go[j] : go[j] * p.slope) : 0.f;
+        if (APPLY) {
+          dzs[j] = sc[j] * dz;
+        } else {
+          s1[j] += dz;
+          s2[j] = fmaf(dz, (ybest[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
+      if (APPLY) {
+#pragma unroll
+        for (int q = 0; q < NPOS; ++q) {
+          if (!ex[q]) continue;
+          float f[8], o[8];
+          unpack8(raw[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(cB[j], f[j], cA[j]) + ((win_ok && amax[j] == q) ? dzs[j] : 0.f);
+          *reinterpret_cast<uint4*>(p.dy.p[g] + off[q]) = pack8(o);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < NPOS; ++q) {
+        if (!ex[q]) continue;
+        float f[8], o[8];
+        unpack8(raw[q], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[j], sc[j], sh[j]);
-          const float a = z > 0.f ? z : z * p.slope;
-          if (a > best[j]) { best[j] = a; amax[j] = q; }
+          const float gsel = (POOL == TMF_POOL_AVG) ? go[j] * 0.125f : go[j];
+          const float dz = z > 0.f ? gsel : gsel * p.slope;
+          if (APPLY) {
+            o[j] = fmaf(cB[j], f[j], cA[j]) + sc[j] * dz;
+          } else {
+            s1[j] += dz;
+            s2[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s2[j]);
+          }
         }
+        if (APPLY) *reinterpret_cast<uint4*>(p.dy.p[g] + off[q]) = pack8(o);
       }
-    }
-    // pass 2: per position dz -> reduce or apply
-    for (int q = 0; q < npos; ++q) {
-      int di, hi, wi;
-      if (p.pool == TMF_POOL_NONE) { di = dw; hi = hw; wi = ww; }
-      else { di = 2 * dw + (q >> 2); hi = 2 * hw + ((q >> 1) & 1); wi = 2 * ww + (q & 1); }
-      if (di >= p.D || hi >= p.H || wi >= p.W) continue;
-      const int64_t ioff = ((((int64_t)n * p.D + di) * p.H + hi) * p.W + wi) * p.C + c0;
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(yg + ioff), f);
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(f[j], sc[j], sh[j]);
-        const float xhat = (f[j] - mu[j]) * is[j];
-        float gsel;
-        if (p.pool == TMF_POOL_MAX) gsel = (win_ok && amax[j] == q) ? go[j] : 0.f;
-        else if (p.pool == TMF_POOL_AVG) gsel = go[j] * 0.125f;
-        else gsel = go[j];
-        const float dz = z > 0.f ? gsel : gsel * p.slope;
-        if (APPLY) {
-          o[j] = sc[j] * (dz - m1[j] - xhat * m2[j]);
-        } else {
-          s1[j] += dz;
-          s2[j] = fmaf(dz, xhat, s2[j]);
-        }
-      }
-      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p[g] + ioff) = pack8(o);
     }
   }
   if (!APPLY) {
@@ -265,6 +303,13 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
   }
+}
+
+template <bool APPLY>
+static void launch_bwd(const ActPoolArgs& p, dim3 grid, size_t smem, cudaStream_t st) {
+  if (p.pool == TMF_POOL_MAX) bn_act_pool_bwd_kernel<APPLY, TMF_POOL_MAX><<<grid, 256, smem, st>>>(p);
+  else if (p.pool == TMF_POOL_AVG) bn_act_pool_bwd_kernel<APPLY, TMF_POOL_AVG><<<grid, 256, smem, st>>>(p);
+  else bn_act_pool_bwd_kernel<APPLY, TMF_POOL_NONE><<<grid, 256, smem, st>>>(p);
 }
 
 static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool, float slope, int fp32io) {
@@ -349,7 +394,7 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
   for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(sums[g], 0, sizeof(double) * 2 * C, st));
   const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
   dim3 grid(pick_grid(total, C / 8), 1, ng);
-  bn_act_pool_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), st>>>(p);
+  launch_bwd<false>(p, grid, 2 * C * sizeof(float), st);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -385,7 +430,7 @@ int tmf_bn_act_pool_bwd_apply(int ng, const void* const* dout, int dout_fp32, co
     return 1;
   const int64_t total = (int64_t)B * p.Dc * p.Hc * p.Wc * (C / 8);
   dim3 grid(pick_grid(total, C / 8), 1, ng);
-  bn_act_pool_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  launch_bwd<true>(p, grid, 0, (cudaStream_t)stream);
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -130,59 +130,105 @@ conv1_fwd_kernel(GroupPtr<const float> x, GroupPtr<const float> w, GroupPtr<cons
 
 // ------------------------------------------------------------------------------------------------------------
 // conv1.0 weight gradient: dW[co][tap] = sum_v dy[v,co] * x[v + shift(tap)]      (fp32 accumulate, fp32 x)
-// lane = voxel (coalesced x / dy reads), each warp owns 4 output channels x 27 taps = 108 register accumulators
-// over all the voxels its block visits; one transposing warp reduction + 108 atomics per warp at the very end.
+// A block walks strips of C1W_ROWS output rows of one (sample, plane): the zero-padded x neighbourhood (3 planes x
+// (rows+2) x (W+2) floats) and the dy strip are staged in shared memory, so the inner loop has no index arithmetic
+// and no bounds checks.  lane = a PAIR of adjacent voxels along w, warp = 4 output channels: 108 register
+// accumulators per thread (4 co x 27 taps), 20 shared loads per 216 FMAs.  One transposing warp reduction and 108
+// atomics per warp at the very end.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int C1W_THREADS = 256;
+constexpr int C1W_ROWS = 4;
 
 __global__ void __launch_bounds__(C1W_THREADS)
 conv1_wgrad_kernel(GroupPtr<const __nv_bfloat16> dy, GroupPtr<const float> x, GroupPtr<float> dw, int B, int D,
-                   int H, int W, int cout) {
+                   int H, int W, int cout, int xpitch, int dypitch) {
+  extern __shared__ __align__(16) uint8_t c1w_smem[];
+  float* xs = reinterpret_cast<float*>(c1w_smem);                                  // [3][ROWS+2][xpitch]
+  uint8_t* dys = c1w_smem + sizeof(float) * 3 * (C1W_ROWS + 2) * xpitch;           // [ROWS][W] x dypitch bytes
   const int g = blockIdx.z;
-  const int64_t M = (int64_t)B * D * H * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ngroups = cout >> 2;                                  // groups of 4 output channels
+  const int ngroups = cout >> 2;
+  const int strips_h = (H + C1W_ROWS - 1) / C1W_ROWS;
+  const int64_t nstrips = (int64_t)B * D * strips_h;
   const float* xg = x.p[g];
   const __nv_bfloat16* dyg = dy.p[g];
-  for (int cg = warp; cg < ngroups; cg += C1W_THREADS / 32) {
+  const int cq = cout >> 3;                                                          // 16-byte chunks per voxel
+  for (int cg0 = 0; cg0 < ngroups; cg0 += C1W_THREADS / 32) {
+    const int cg = cg0 + warp;
     float acc[4][27];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int t = 0; t < 27; ++t) acc[c][t] = 0.f;
-    for (int64_t m0 = (int64_t)blockIdx.x * 32; m0 < M; m0 += (int64_t)gridDim.x * 32) {
-      const int64_t m = m0 + lane;
-      if (m >= M) continue;
-      const int wq = (int)(m % W);
-      const int hq = (int)((m / W) % H);
-      const int dq = (int)((m / ((int64_t)W * H)) % D);
-      const uint2 raw = *reinterpret_cast<const uint2*>(dyg + m * cout + cg * 4);
-      const float d0 = bf16_lo(raw.x), d1 = bf16_hi(raw.x), d2 = bf16_lo(raw.y), d3 = bf16_hi(raw.y);
-      const float* xp = xg + m;
+    for (int64_t sidx = blockIdx.x; sidx < nstrips; sidx += gridDim.x) {
+      const int hs = (int)(sidx % strips_h);
+      const int d = (int)((sidx / strips_h) % D);
+      const int n = (int)(sidx / ((int64_t)strips_h * D));
+      const int h0 = hs * C1W_ROWS;
+      const int rows = min(C1W_ROWS, H - h0);
+      __syncthreads();
+      // ---- stage x (zero padded) ----
+      for (int i = threadIdx.x; i < 3 * (C1W_ROWS + 2) * xpitch; i += C1W_THREADS) {
+        const int col = i % xpitch;
+        const int rr = (i / xpitch) % (C1W_ROWS + 2);
+        const int pl = i / (xpitch * (C1W_ROWS + 2));
+        const int dd = d + pl - 1, hh = h0 + rr - 1, ww = col - 1;
+        float v = 0.f;
+        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+          v = __ldg(xg + (((int64_t)n * D + dd) * H + hh) * W + ww);
+        xs[i] = v;
+      }
+      // ---- stage dy strip (rows x W voxels x cout bf16), 16-byte chunks ----
+      for (int i = threadIdx.x; i < rows * W * cq; i += C1W_THREADS) {
+        const int q = i % cq;
+        const int vox = i / cq;                                   // row-major (row, w)
+        const int64_t src = ((((int64_t)n * D + d) * H + h0) * W + vox) * cout + q * 8;
+        const uint4 v4 = *reinterpret_cast<const uint4*>(dyg + src);
+        uint2* dst = reinterpret_cast<uint2*>(dys + (size_t)vox * dypitch + q * 16);   // pitch is only 8-byte aligned
+        dst[0] = make_uint2(v4.x, v4.y);
+        dst[1] = make_uint2(v4.z, v4.w);
+      }
+      __syncthreads();
+      if (cg < ngroups) {
+        for (int r = 0; r < rows; ++r) {
+          for (int w0 = 2 * lane; w0 < W; w0 += 64) {
+            const bool two = (w0 + 1) < W;
+            const uint2 r0 = *reinterpret_cast<const uint2*>(dys + (size_t)(r * W + w0) * dypitch + cg * 8);
+            uint2 r1 = make_uint2(0u, 0u);
+            if (two) r1 = *reinterpret_cast<const uint2*>(dys + (size_t)(r * W + w0 + 1) * dypitch + cg * 8);
+            const float a0[4] = {bf16_lo(r0.x), bf16_hi(r0.x), bf16_lo(r0.y), bf16_hi(r0.y)};
+            const float a1[4] = {bf16_lo(r1.x), bf16_hi(r1.x), bf16_lo(r1.y), bf16_hi(r1.y)};
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd)
+            for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+              for (int kh = 0; kh < 3; ++kh) {
+                const float* xr = xs + ((kd * (C1W_ROWS + 2)) + r + kh) * xpitch + w0;   // x[w0-1 .. w0+2]
+                const float2 lo = *reinterpret_cast<const float2*>(xr);
+                const float2 hi = *reinterpret_cast<const float2*>(xr + 2);
+                const float xv[4] = {lo.x, lo.y, hi.x, hi.y};
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int dd = dq + kd - 1, hh = hq + kh - 1, ww = wq + kw - 1;
-            const bool ok = dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W;
-            const float xv = ok ? __ldg(xp + ((int64_t)(kd - 1) * H + (kh - 1)) * W + (kw - 1)) : 0.f;
-            const int t = (kd * 3 + kh) * 3 + kw;
-            acc[0][t] = fmaf(d0, xv, acc[0][t]);
-            acc[1][t] = fmaf(d1, xv, acc[1][t]);
-            acc[2][t] = fmaf(d2, xv, acc[2][t]);
-            acc[3][t] = fmaf(d3, xv, acc[3][t]);
+                for (int kw = 0; kw < 3; ++kw) {
+                  const int t = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    acc[c][t] = fmaf(a0[c], xv[kw], acc[c][t]);
+                    acc[c][t] = fmaf(a1[c], xv[kw + 1], acc[c][t]);
+                  }
+                }
+              }
           }
+        }
+      }
     }
-    // reduce across the 32 lanes: 4 rounds of the 32-value transposing butterfly (27 taps + 5 zero slots)
+    if (cg < ngroups) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[32];
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) v[t] = (t < 27) ? acc[c][t] : 0.f;
-      const float tot = warp_transpose_reduce32(v, lane);
-      if (lane < 27) atomicAdd(&dw.p[g][(cg * 4 + c) * 27 + lane], tot);
+        for (int t = 0; t < 32; ++t) v[t] = (t < 27) ? acc[c][t] : 0.f;
+        const float tot = warp_transpose_reduce32(v, lane);
+        if (lane < 27) atomicAdd(&dw.p[g][(cg * 4 + c) * 27 + lane], tot);
+      }
     }
   }
 }
@@ -470,9 +516,15 @@ int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float*
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(dw[g], 0, sizeof(float) * 27 * cout, st));
-  const int64_t M = (int64_t)B * D * H * W;
-  dim3 grid((unsigned)min(ceil_div(M, 32), 148 * 4), 1, ng);
-  conv1_wgrad_kernel<<<grid, C1W_THREADS, 0, st>>>(gdy, gx, gdw, B, D, H, W, cout);
+  const int xpitch = (W + 2 + 3) & ~1;                 // even, >= W + 4 (pairs read x[w0-1 .. w0+2])
+  const int dypitch = cout * 2 + 8;                    // bytes per voxel row in smem (+8: spreads banks)
+  const size_t smem = sizeof(float) * 3 * (C1W_ROWS + 2) * xpitch + (size_t)C1W_ROWS * W * dypitch;
+  TMF_REQUIRE(smem <= 227 * 1024, "conv1_wgrad: W=%d too wide for the shared-memory strip", W);
+  if (smem > 48 * 1024)
+    TMF_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nstrips = (int64_t)B * D * ceil_div(H, C1W_ROWS);
+  dim3 grid((unsigned)min(nstrips, (int64_t)148 * 2), 1, ng);
+  conv1_wgrad_kernel<<<grid, C1W_THREADS, smem, st>>>(gdy, gx, gdw, B, D, H, W, cout, xpitch, dypitch);
   TMF_LAUNCH_CHECK();
   return 0;
 }

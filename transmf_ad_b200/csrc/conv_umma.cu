@@ -49,6 +49,7 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
   return 0u;
 }
 
+template <int KSTEPS, int KS, bool RES>
 __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid_constant__ UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      unsigned long long loaded_lo = 0ull, loaded_hi = 0ull;   // resident-B bookkeeping (<= 108 stages)
+      uint32_t kd_loaded = 0;                                  // resident weights: planes already requested
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta) {
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
@@ -102,23 +103,24 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
         for (int kd = 0; kd < p.ks; ++kd) {
           const int dd = d + kd - p.hw;
           if (dd < 0 || dd >= p.D) continue;
+          if (p.b_resident && !((kd_loaded >> kd) & 1u)) {     // all (tap, chunk) boxes of this plane, once per CTA
+            kd_loaded |= 1u << kd;
+            for (int t = 0; t < taps2; ++t)
+              for (int c = 0; c < p.nchunk; ++c) {
+                const int tap = kd * taps2 + t, idx = tap * p.nchunk + c;
+                mbar_expect_tx(b_full + 8 * idx, p.b_tx_bytes);
+                tma_load_3d(smB + (uint32_t)idx * p.b_stage_bytes, &p.tmB[g], b_full + 8 * idx, c * p.chunk, 0, tap);
+              }
+          }
           for (int c = 0; c < p.nchunk; ++c) {
             mbar_wait(a_empty + 8 * sa, pa ^ 1u);
             mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
             tma_load_5d(smA + (uint32_t)sa * p.a_stage_bytes, &p.tmA[g], a_full + 8 * sa, c * p.chunk, -p.hw,
                         h0 - p.hw, dd, n);
             if (++sa == p.SA) { sa = 0; pa ^= 1u; }
-            for (int t = 0; t < taps2; ++t) {
-              const int tap = kd * taps2 + t;
-              if (p.b_resident) {
-                const int idx = tap * p.nchunk + c;
-                const bool have = idx < 64 ? ((loaded_lo >> idx) & 1ull) : ((loaded_hi >> (idx - 64)) & 1ull);
-                if (!have) {
-                  if (idx < 64) loaded_lo |= 1ull << idx; else loaded_hi |= 1ull << (idx - 64);
-                  mbar_expect_tx(b_full + 8 * idx, p.b_tx_bytes);
-                  tma_load_3d(smB + (uint32_t)idx * p.b_stage_bytes, &p.tmB[g], b_full + 8 * idx, c * p.chunk, 0, tap);
-                }
-              } else {
+            if (!p.b_resident) {
+              for (int t = 0; t < taps2; ++t) {
+                const int tap = kd * taps2 + t;
                 mbar_wait(b_empty + 8 * sb, pb ^ 1u);
                 mbar_expect_tx(b_full + 8 * sb, p.b_tx_bytes);
                 tma_load_3d(smB + (uint32_t)sb * p.b_stage_bytes, &p.tmB[g], b_full + 8 * sb, c * p.chunk, 0, tap);
@@ -131,74 +133,87 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
     }
   } else if (warp == 1) {
     // =========================================== MMA issuer =============================================
-    // One thread issues every tcgen05.mma of the CTA, so its scalar work per MMA is the limiter for the narrow
-    // layers: descriptors are split into a constant high word and a low word that only needs an add per MMA.
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
+    // one elected lane issues tcgen05.mma / tcgen05.commit.  KSTEPS (16-element K steps per smem row), the kernel
+    // size and the weight residency are compile-time, so a tap is a handful of adds plus its MMAs.
+    {
+      constexpr uint32_t ROW_UNITS = KSTEPS * 2;                 // row bytes / 16
+      constexpr uint32_t SBO = 8u * KSTEPS * 32u;
+      constexpr int TAPS2 = KS * KS;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
-      const int ksteps = p.chunk / 16;
-      const uint64_t desc_hi = make_smem_desc(0, 16, sbo, p.layout, 0) & 0xFFFFFFFF00000000ull;
-      const uint32_t desc_lo_const = (uint32_t)(make_smem_desc(0, 16, sbo, p.layout, 0) & 0xFFFF0000ull);
-      const uint32_t row_units = (uint32_t)p.row_bytes >> 4;
-      unsigned long long waited_lo = 0ull, waited_hi = 0ull;   // resident-B stages already known to be loaded
+      const uint64_t desc_hi = make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo_const = (uint32_t)(make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFF0000ull);
+      const uint32_t b_units = p.b_stage_bytes >> 4;
+      const uint32_t a0_lo = desc_lo_const | ((smA & 0x3FFFFu) >> 4);
+      const uint32_t b0_lo = desc_lo_const | ((smB & 0x3FFFFu) >> 4);
+      const uint32_t a_units = p.a_stage_bytes >> 4;
+      const uint32_t wp_units = (uint32_t)p.Wp * ROW_UNITS;
+      uint32_t kd_ready = 0;                                     // resident weights of plane kd known to be loaded
       int it = 0;
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
         const int d = r % p.D;
-        const int q0 = qt * UC_TILE_M;
-        const uint32_t qoff_units = (uint32_t)(q0 % p.Wp) * row_units;
+        const uint32_t qoff_units = (uint32_t)((qt * UC_TILE_M) % p.Wp) * ROW_UNITS;
         const int as = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
         uint32_t accumulate = 0;
-        for (int kd = 0; kd < p.ks; ++kd) {
+#pragma unroll 1
+        for (int kd = 0; kd < KS; ++kd) {
           const int dd = d + kd - p.hw;
           if (dd < 0 || dd >= p.D) continue;
+          if (RES && !((kd_ready >> kd) & 1u)) {
+            for (int i = 0; i < TAPS2 * p.nchunk; ++i) mbar_wait(b_full + 8 * (kd * TAPS2 * p.nchunk + i), 0u);
+            kd_ready |= 1u << kd;
+          }
+#pragma unroll 1
           for (int c = 0; c < p.nchunk; ++c) {
             mbar_wait(a_full + 8 * sa, pa);
             tc_fence_after();
-            const uint32_t a_slab_lo = desc_lo_const | (((smA + (uint32_t)sa * p.a_stage_bytes) & 0x3FFFFu) >> 4);
-            int tap = kd * taps2;
-            for (int kh = 0; kh < p.ks; ++kh) {
-              uint32_t a_lo = a_slab_lo + qoff_units + (uint32_t)(kh * p.Wp) * row_units;
-              for (int kw = 0; kw < p.ks; ++kw, ++tap, a_lo += row_units) {
-                uint32_t b_addr;
-                if (p.b_resident) {
-                  const int idx = tap * p.nchunk + c;
-                  const bool seen = idx < 64 ? ((waited_lo >> idx) & 1ull) : ((waited_hi >> (idx - 64)) & 1ull);
-                  if (!seen) {
-                    mbar_wait(b_full + 8 * idx, 0u);
-                    tc_fence_after();
-                    if (idx < 64) waited_lo |= 1ull << idx; else waited_hi |= 1ull << (idx - 64);
-                  }
-                  b_addr = smB + (uint32_t)idx * p.b_stage_bytes;
+            const uint32_t a_slab = a0_lo + (uint32_t)sa * a_units + qoff_units;
+            uint32_t b_res = b0_lo + (uint32_t)((kd * TAPS2) * p.nchunk + c) * b_units;   // resident: stage of tap 0
+            const uint32_t b_res_step = (uint32_t)p.nchunk * b_units;
+#pragma unroll
+            for (int kh = 0; kh < KS; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < KS; ++kw) {
+                const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units + (uint32_t)kw * ROW_UNITS;
+                uint32_t b_lo;
+                if (RES) {
+                  b_lo = b_res;
+                  b_res += b_res_step;
                 } else {
                   mbar_wait(b_full + 8 * sb, pb);
                   tc_fence_after();
-                  b_addr = smB + (uint32_t)sb * p.b_stage_bytes;
+                  b_lo = b0_lo + (uint32_t)sb * b_units;
                 }
-                const uint32_t b_lo = desc_lo_const | ((b_addr & 0x3FFFFu) >> 4);
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
-                              accumulate);
-                  accumulate = 1;
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
+                                accumulate);
+                    accumulate = 1;
+                  }
+                  if (!RES) mma_commit(b_empty + 8 * sb);
                 }
-                if (!p.b_resident) {
-                  mma_commit(b_empty + 8 * sb);
+                accumulate = 1;
+                __syncwarp();
+                if (!RES) {
                   if (++sb == p.SB) { sb = 0; pb ^= 1u; }
                 }
               }
             }
-            mma_commit(a_empty + 8 * sa);
+            if (elect_one()) mma_commit(a_empty + 8 * sa);
+            __syncwarp();
             if (++sa == p.SA) { sa = 0; pa ^= 1u; }
           }
         }
-        mma_commit(acc_full + 8 * as);
+        if (elect_one()) mma_commit(acc_full + 8 * as);
+        __syncwarp();
       }
     }
   } else {
@@ -419,11 +434,6 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
     }
     if (stats && stats[g]) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UC_SMEM_BUDGET));
-    attr_set = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -431,7 +441,26 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   if (per_group > p.tiles_per_group) per_group = p.tiles_per_group;
   if (per_group < 1) per_group = 1;
   dim3 grid(per_group * ng, 1, 1);
-  conv3d_umma_kernel<<<grid, UC_THREADS, pl.smem_bytes, st>>>(p);
+  const int ksteps = pl.chunk / 16;
+#define TMF_LAUNCH_CONV(KST, KSZ, RES)                                                                              \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<KST, KSZ, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)UC_SMEM_BUDGET));                                                         \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    conv3d_umma_kernel<KST, KSZ, RES><<<grid, UC_THREADS, pl.smem_bytes, st>>>(p);                                 \
+  } while (0)
+  if (ksteps == 4 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(4, 3, true);
+  else if (ksteps == 4 && ksize == 3) TMF_LAUNCH_CONV(4, 3, false);
+  else if (ksteps == 2 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(2, 3, true);
+  else if (ksteps == 2 && ksize == 3) TMF_LAUNCH_CONV(2, 3, false);
+  else if (ksteps == 4 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(4, 1, true);
+  else if (ksteps == 4 && ksize == 1) TMF_LAUNCH_CONV(4, 1, false);
+  else if (ksteps == 2 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(2, 1, true);
+  else TMF_LAUNCH_CONV(2, 1, false);
+#undef TMF_LAUNCH_CONV
   TMF_LAUNCH_CHECK();
   return 0;
 }

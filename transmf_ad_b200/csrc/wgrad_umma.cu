@@ -56,6 +56,7 @@ struct alignas(64) WgradParams {
   WgGroup grp[WG_MAX_GROUPS];
 };
 
+template <int KSTEPS>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,39 +115,49 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_umma_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (see conv_umma.cu)
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t sbo_x = 8u * p.rbx, sbo_y = 8u * p.rby;
-      const int ksteps = p.TK / 16;
       // descriptors: constant high word; low word = start address (16-byte units) | LBO << 16
       const uint64_t hi_x = make_smem_desc(0, 0, sbo_x, p.layx, 0) & 0xFFFFFFFF00000000ull;
       const uint64_t hi_y = make_smem_desc(0, 0, sbo_y, p.layy, 0) & 0xFFFFFFFF00000000ull;
       const uint32_t y_lo_const = ((p.y_slab_bytes >> 4) & 0x3FFFu) << 16;
       const uint32_t kstep_x = (16u * p.rbx) >> 4, kstep_y = (16u * p.rby) >> 4;
+      const uint32_t rbx_units = p.rbx >> 4, rby_units = p.rby >> 4;
+      const uint32_t stage_units = p.stage_bytes >> 4;
+      const uint32_t base_units = (smem_base & 0x3FFFFu) >> 4;
+      const uint32_t yreg_units = p.y_region_off >> 4;
       uint32_t accumulate = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         const int qt = kt % p.QT;
         const uint32_t qoff = (uint32_t)((qt * p.TK) % p.Wp);
         mbar_wait(full + 8 * s, ph);
         tc_fence_after();
-        const uint32_t st = smem_base + (uint32_t)s * p.stage_bytes;
-        const uint32_t y_lo = y_lo_const | (((st + p.y_region_off + qoff * p.rby) & 0x3FFFFu) >> 4);
-        const uint32_t x_units = ((st + qoff * p.rbx) & 0x3FFFFu) >> 4;
+        const uint32_t st_units = base_units + (uint32_t)s * stage_units;
+        const uint32_t y_lo = y_lo_const | (st_units + yreg_units + qoff * rby_units);
+        const uint32_t x_units = st_units + qoff * rbx_units;
+#pragma unroll 1
         for (int gi = 0; gi < S.ng; ++gi) {
           const WgGroup& G = p.grp[S.g0 + gi];
           const uint32_t a_lo = ((((G.a_lbo >> 4) & 0x3FFFu) << 16) | x_units) + (G.a_off >> 4);
           const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.cout);
-          mma_bf16_ss(d_tmem, hi_x | (uint64_t)a_lo, hi_y | (uint64_t)y_lo, p.idesc, accumulate);
-#pragma unroll 7
-          for (int k = 1; k < ksteps; ++k)
-            mma_bf16_ss(d_tmem, hi_x | (uint64_t)(a_lo + k * kstep_x), hi_y | (uint64_t)(y_lo + k * kstep_y), p.idesc, 1u);
+          if (elect_one()) {
+            mma_bf16_ss(d_tmem, hi_x | (uint64_t)a_lo, hi_y | (uint64_t)y_lo, p.idesc, accumulate);
+#pragma unroll
+            for (int k = 1; k < KSTEPS; ++k)
+              mma_bf16_ss(d_tmem, hi_x | (uint64_t)(a_lo + k * kstep_x), hi_y | (uint64_t)(y_lo + k * kstep_y), p.idesc, 1u);
+          }
+          __syncwarp();
         }
         accumulate = 1;
-        mma_commit(empty + 8 * s);
+        if (elect_one()) mma_commit(empty + 8 * s);
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      mma_commit(acc_full);
+      if (elect_one()) mma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // epilogue: TMEM -> fp32 partial ws[split][tap][ci][co]
@@ -421,15 +432,20 @@ int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, f
       TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_wgrad_umma: cuTensorMapEncodeTiled(dY) failed with %d", (int)r);
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TMF_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)WG_SMEM_BUDGET));
-    attr_set = true;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ng * p.nsub * p.nsplit, 1, 1);
-  conv3d_wgrad_umma_kernel<<<grid, WG_THREADS, smem, st>>>(p);
+#define TMF_LAUNCH_WG(KST)                                                                                        \
+  do {                                                                                                           \
+    static bool attr_done = false;                                                                               \
+    if (!attr_done) {                                                                                            \
+      TMF_CUDA(cudaFuncSetAttribute(conv3d_wgrad_umma_kernel<KST>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    (int)WG_SMEM_BUDGET));                                                       \
+      attr_done = true;                                                                                          \
+    }                                                                                                            \
+    conv3d_wgrad_umma_kernel<KST><<<grid, WG_THREADS, smem, st>>>(p);                                            \
+  } while (0)
+  if (p.TK == 128) TMF_LAUNCH_WG(8); else TMF_LAUNCH_WG(4);
+#undef TMF_LAUNCH_WG
   TMF_LAUNCH_CHECK();
   const int64_t total = (int64_t)p.taps * cin * cout;
   dim3 rgrid(min(ceil_div(total, 256), 148 * 4), 1, ng);
