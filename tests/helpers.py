@@ -153,6 +153,13 @@ def parity_report(name, device="cuda"):
                          absmax=float(g.abs().max()))
         grads[k] = entry
     rep["grads"] = grads
+    # whole-model gradient direction (all non-trivial tensors concatenated)
+    ours = torch.cat([p.grad.detach().cpu().flatten() for k, p in model.named_parameters()
+                      if not is_conv_bias(k) and float(sd[k].grad.norm()) >= 1e-5])
+    ref = torch.cat([sd[k].grad.flatten() for k, p in model.named_parameters()
+                     if not is_conv_bias(k) and float(sd[k].grad.norm()) >= 1e-5])
+    rep["global_grad_cos_A"] = cosine(ours, ref)
+    rep["global_grad_rel_A"] = rel_err(ours, ref)
     msd = model.state_dict()
     rep["buffers"] = {k: (int(msd[k]) == int(v)) if k.endswith("num_batches_tracked")
                       else float((msd[k].cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))

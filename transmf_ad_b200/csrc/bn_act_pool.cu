@@ -327,9 +327,8 @@ static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool
   return 0;
 }
 
-static int pick_grid(int64_t total_threads, int CQ) {
+static int pick_grid(int64_t total_threads, int CQ, int64_t cap = 148 * 16) {
   int64_t blocks = (total_threads + 255) / 256;
-  const int64_t cap = 148 * 16;
   if (blocks > cap) blocks = cap;
   // keep (gridDim.x * 256) a multiple of CQ so that a thread's channel chunk is loop-invariant
   int64_t a = 256, b = CQ;
@@ -393,7 +392,7 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(sums[g], 0, sizeof(double) * 2 * C, st));
   const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
-  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  dim3 grid(pick_grid(total, C / 8, 148 * 4), 1, ng);
   launch_bwd<false>(p, grid, 2 * C * sizeof(float), st);
   TMF_LAUNCH_CHECK();
   return 0;

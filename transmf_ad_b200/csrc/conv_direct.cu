@@ -46,11 +46,13 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 
 constexpr int C1_THREADS = 256;
 
+// Persistent blocks (grid-stride over 256-voxel chunks) so that the per-channel statistics cost ONE flush of
+// 2*Cout double atomics per block instead of one per 256 voxels.
 __global__ void __launch_bounds__(C1_THREADS)
 conv1_fwd_kernel(GroupPtr<const float> x, GroupPtr<const float> w, GroupPtr<const float> bias,
                  GroupPtr<__nv_bfloat16> y, GroupPtr<double> stats, int B, int D, int H, int W, int cout) {
   const int g = blockIdx.z;
-  __shared__ float ws[27][64];
+  __shared__ __align__(16) float ws[27][64];
   __shared__ float bs[64];
   __shared__ float red[2][64];
   for (int i = threadIdx.x; i < 27 * 64; i += C1_THREADS) {
@@ -65,61 +67,73 @@ conv1_fwd_kernel(GroupPtr<const float> x, GroupPtr<const float> w, GroupPtr<cons
   __syncthreads();
 
   const int64_t M = (int64_t)B * D * H * W;
-  const int64_t m = blockIdx.x * (int64_t)C1_THREADS + threadIdx.x;
-  const bool active = m < M;
-  float in[27];
-  if (active) {
-    const int wq = (int)(m % W);
-    const int hq = (int)((m / W) % H);
-    const int dq = (int)((m / ((int64_t)W * H)) % D);
-    const float* xp = x.p[g] + m;
-#pragma unroll
-    for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int dd = dq + kd - 1, hh = hq + kh - 1, ww = wq + kw - 1;
-          const bool ok = dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W;
-          in[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + ((int64_t)(kd - 1) * H + (kh - 1)) * W + (kw - 1)) : 0.f;
-        }
-  } else {
-#pragma unroll
-    for (int t = 0; t < 27; ++t) in[t] = 0.f;
-  }
   const int lane = threadIdx.x & 31;
-  for (int c0 = 0; c0 < cout; c0 += 32) {
-    float acc[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = bs[c0 + c];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float xv = in[t];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = fmaf(xv, ws[t][c0 + c], acc[c]);
-    }
-    float sq[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      acc[c] = active ? round_bf16(acc[c]) : 0.f;
-      sq[c] = acc[c] * acc[c];
-    }
+  const bool want_stats = stats.p[g] != nullptr;
+  float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};           // lane-owned channel totals (channel = 32*i + lane)
+  for (int64_t m0 = (int64_t)blockIdx.x * C1_THREADS; m0 < M; m0 += (int64_t)gridDim.x * C1_THREADS) {
+    const int64_t m = m0 + threadIdx.x;
+    const bool active = m < M;
+    float in[27];
     if (active) {
-      __nv_bfloat16* yp = y.p[g] + m * cout + c0;
-      const int nvalid = min(32, cout - c0);
+      const int wq = (int)(m % W);
+      const int hq = (int)((m / W) % H);
+      const int dq = (int)((m / ((int64_t)W * H)) % D);
+      const float* xp = x.p[g] + m;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < nvalid) *reinterpret_cast<uint4*>(yp + q * 8) = pack8(&acc[q * 8]);
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int dd = dq + kd - 1, hh = hq + kh - 1, ww = wq + kw - 1;
+            const bool ok = dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            in[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + ((int64_t)(kd - 1) * H + (kh - 1)) * W + (kw - 1)) : 0.f;
+          }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 27; ++t) in[t] = 0.f;
+    }
+    for (int c0 = 0; c0 < cout; c0 += 32) {
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = bs[c0 + c];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const float xv = in[t];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[t][c0 + c4 * 4]);
+          acc[c4 * 4 + 0] = fmaf(xv, wv.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(xv, wv.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(xv, wv.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(xv, wv.w, acc[c4 * 4 + 3]);
+        }
+      }
+      float sq[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        acc[c] = active ? round_bf16(acc[c]) : 0.f;
+        sq[c] = acc[c] * acc[c];
+      }
+      if (active) {
+        __nv_bfloat16* yp = y.p[g] + m * cout + c0;
+        const int nvalid = min(32, cout - c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q * 8 < nvalid) *reinterpret_cast<uint4*>(yp + q * 8) = pack8(&acc[q * 8]);
+        }
+      }
+      if (want_stats) {
+        ssum[c0 >> 5] += warp_transpose_reduce32(acc, lane);
+        ssq[c0 >> 5] += warp_transpose_reduce32(sq, lane);
       }
     }
-    if (stats.p[g] != nullptr) {
-      const float s = warp_transpose_reduce32(acc, lane);
-      const float ss = warp_transpose_reduce32(sq, lane);
-      atomicAdd(&red[0][c0 + lane], s);
-      atomicAdd(&red[1][c0 + lane], ss);
-    }
   }
-  if (stats.p[g] != nullptr) {
+  if (want_stats) {
+    for (int i = 0; i * 32 < cout; ++i) {
+      atomicAdd(&red[0][i * 32 + lane], ssum[i]);
+      atomicAdd(&red[1][i * 32 + lane], ssq[i]);
+    }
     __syncthreads();
     if (threadIdx.x < cout) {
       atomicAdd(&stats.p[g][threadIdx.x], (double)red[0][threadIdx.x]);
@@ -497,7 +511,7 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
   if (stats != nullptr)
     for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
   const int64_t M = (int64_t)B * D * H * W;
-  dim3 grid(ceil_div(M, C1_THREADS), 1, ng);
+  dim3 grid(min(ceil_div(M, C1_THREADS), 148 * 6), 1, ng);
   conv1_fwd_kernel<<<grid, C1_THREADS, 0, st>>>(gx, gw, gb, gy, gs, B, D, H, W, cout);
   TMF_LAUNCH_CHECK();
   return 0;
