@@ -56,9 +56,10 @@ int tmf_pack_conv_weights(int ng, const float* const* w, void* const* wf, void* 
 
 /* conv1.0 (Cin = 1, 3x3x3, pad 1), fp32 input and weights, bf16 output y[B,D,H,W,Cout], per-channel
  * sum / sum-of-squares of the stored (rounded) y into stats[2*Cout] (double; zeroed by the call).
- * reference models/networks.py:22 */
+ * impl: TMF_CONV_AUTO / _DIRECT (CUDA cores, fp32) / _UMMA (tcgen05 on an in-smem im2col with a bf16 hi/lo split of
+ * both operands, fp32-level accuracy).   reference models/networks.py:22 */
 int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const float* const* bias,
-                  void* const* y, double* const* stats, int B, int D, int H, int W, int cout, void* stream);
+                  void* const* y, double* const* stats, int B, int D, int H, int W, int cout, int impl, void* stream);
 
 /* dW[Cout][27] (+ optionally dbias) of conv1.0 from dy (bf16) and x (fp32); dw is overwritten. */
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw,

@@ -22,7 +22,7 @@ _pp = C.POINTER(C.c_void_p)          # host array of device pointers
 # name -> argtypes  (must mirror include/tmf.h; tests/test_abi.py checks every symbol is exported)
 SIGNATURES = {
     "tmf_pack_conv_weights": [_i, _pp, _pp, _pp, _i, _i, _i, _vp],
-    "tmf_conv1_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv1_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp],
     "tmf_conv1_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _vp],
     "tmf_conv3d_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "tmf_conv3d_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],

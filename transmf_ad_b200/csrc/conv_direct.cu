@@ -455,6 +455,10 @@ __global__ void __launch_bounds__(256) conv3d_wgrad_direct_kernel(WgradDirectArg
 
 using namespace tmf;
 
+// implemented in conv1_umma.cu
+bool tmf_conv1_fwd_umma_supported(int cout);
+int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, const float* const* bias, void* const* y,
+                       double* const* stats, int B, int D, int H, int W, int cout, void* stream);
 // implemented in conv_umma.cu
 int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, const float* const* bias,
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
@@ -496,8 +500,13 @@ int tmf_pack_conv_weights(int ng, const float* const* w, void* const* wf, void* 
 }
 
 int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const float* const* bias, void* const* y,
-                  double* const* stats, int B, int D, int H, int W, int cout, void* stream) {
+                  double* const* stats, int B, int D, int H, int W, int cout, int impl, void* stream) {
   TMF_CHECK_NG(ng);
+  if (impl == TMF_CONV_AUTO) impl = tmf_conv1_fwd_umma_supported(cout) ? TMF_CONV_UMMA : TMF_CONV_DIRECT;
+  if (impl == TMF_CONV_UMMA) {
+    TMF_REQUIRE(tmf_conv1_fwd_umma_supported(cout), "conv1_fwd: tcgen05 path needs Cout 32 or 64 (got %d)", cout);
+    return tmf_conv1_fwd_umma(ng, x, w, bias, y, stats, B, D, H, W, cout, stream);
+  }
   TMF_REQUIRE(cout >= 8 && cout <= 64 && cout % 8 == 0, "conv1_fwd: Cout must be a multiple of 8 in [8,64] (got %d)",
               cout);
   GroupPtr<const float> gx, gw, gb;

@@ -89,7 +89,7 @@ class SNetFunction(torch.autograd.Function):
             wd = None
             if l == 0:
                 L.call("tmf_conv1_fwd", ng, L.ptrs(act), L.ptrs(w), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
-                       B, Dl, Hl, Wl, cout)
+                       B, Dl, Hl, Wl, cout, impl)
             else:
                 taps = ks ** 3
                 wf = [torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
