@@ -63,7 +63,7 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
 
 /* dW[Cout][27] (+ optionally dbias) of conv1.0 from dy (bf16) and x (fp32); dw is overwritten. */
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw,
-                    int B, int D, int H, int W, int cout, void* stream);
+                    int B, int D, int H, int W, int cout, int impl, void* stream);
 
 /* 3x3x3 (pad 1) or 1x1x1 convolution, bf16 NDHWC input a[B,D,H,W,Cin], packed bf16 weights wf[tap][Cout][Cin],
  * optional fp32 bias, bf16 output y[B,D,H,W,Cout], optional stats (as above; NULL array = none).

@@ -123,15 +123,18 @@ def test_conv_grouped_towers_match_single_launches():
         assert torch.equal(y1, y2[t])
 
 
-def test_conv1_wgrad():
-    B, D, H, W, cout = 2, 11, 13, 12, 32
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(2, 11, 13, 12), (1, 9, 21, 45), (1, 3, 5, 91)])
+def test_conv1_wgrad(impl, shape):
+    B, D, H, W = shape
+    cout = 32
     x = torch.rand(B, 1, D, H, W, generator=torch.Generator().manual_seed(1))
     dy = bf16r(g_randn(B, cout, D, H, W, seed=2))
     w = g_randn(cout, 1, 3, 3, 3, seed=3).requires_grad_(True)
     F.conv3d(x, w, None, padding=1).backward(dy)
     dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=DEV)
     dy_d, x_d = to_ndhwc_bf16(dy), x.to(DEV)          # keep references: L.ptrs() only takes raw addresses
-    L.call("tmf_conv1_wgrad", 1, L.ptrs([dy_d]), L.ptrs([x_d]), L.ptrs([dw]), B, D, H, W, cout)
+    L.call("tmf_conv1_wgrad", 1, L.ptrs([dy_d]), L.ptrs([x_d]), L.ptrs([dw]), B, D, H, W, cout, impl)
     assert rel_l2(dw.cpu(), w.grad) < 1e-4
 
 

@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
   const int CQ = p.C >> 3;
   const int64_t total = (int64_t)p.B * p.Do * p.Ho * p.Wo * CQ;
   const __nv_bfloat16* yg = p.y.p[g];
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % CQ);
-    int64_t r = idx / CQ;
+  // 32-bit index arithmetic (host checks total < 2^31): 64-bit div/mod would cost more than the useful work
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % (unsigned)CQ);
+    unsigned r = idx / (unsigned)CQ;
     const int wo = (int)(r % p.Wo); r /= p.Wo;
     const int ho = (int)(r % p.Ho); r /= p.Ho;
     const int dd = (int)(r % p.Do);
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int last_cq = -1;
   float sc[8], sh[8], mu[8], is[8], cA[8], cB[8], sg[8];
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % CQ);
-    int64_t r = idx / CQ;
+  // 32-bit index arithmetic (host checks total < 2^31): 64-bit div/mod would cost more than the useful work
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % (unsigned)CQ);
+    unsigned r = idx / (unsigned)CQ;
     const int ww = (int)(r % Ww); r /= Ww;
     const int hw = (int)(r % Hw); r /= Hw;
     const int dw = (int)(r % Dw);
@@ -316,6 +316,7 @@ static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool
   TMF_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "bn_act_pool: C must be a multiple of 8 in [8,1024] (got %d)", C);
   TMF_REQUIRE(pool == TMF_POOL_NONE || pool == TMF_POOL_MAX || pool == TMF_POOL_AVG, "bn_act_pool: bad pool mode %d",
               pool);
+  TMF_REQUIRE((int64_t)B * D * H * W * (C / 8) < (1ll << 31), "bn_act_pool: tensor too large for 32-bit work indices");
   p.B = B; p.D = D; p.H = H; p.W = W; p.C = C; p.pool = pool; p.slope = slope; p.fp32io = fp32io;
   if (pool == TMF_POOL_NONE) {
     p.Do = p.Dc = D; p.Ho = p.Hc = H; p.Wo = p.Wc = W;

@@ -15,8 +15,9 @@
 namespace tmf {
 using namespace umma;
 
-constexpr int C1U_PRODUCERS = 128;                 // warps 0-3: one im2col row (voxel) per thread
-constexpr int C1U_THREADS = 288;                   // + warp 4: MMA issuer / TMEM owner, warps 5-8: epilogue
+constexpr int C1U_PRODUCERS = 128;                 // one im2col row (voxel) per thread; two producer groups (warps 0-3,
+                                                   // 4-7) alternate tiles so global-load latency of one hides behind the other
+constexpr int C1U_THREADS = 416;                   // + warp 8: MMA issuer / TMEM owner, warps 9-12: epilogue
 constexpr int C1U_STAGES = 4;
 constexpr uint32_t C1U_TILE_BYTES = 128 * 64;      // one [128 x 32] bf16 operand tile
 
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
     *reinterpret_cast<uint4*>(gen + (smW + 4096 - smem_base) + sw64_off(co, j)) = pack8(lo);
   }
   fence_proxy_async();
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
@@ -86,31 +87,38 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ======================================= im2col producers =======================================
-    const int r = threadIdx.x;                       // row of the tile
+    const int grp = warp >> 2;                       // producer group: handles every other tile of this CTA
+    const int r = threadIdx.x & 127;                 // row of the tile
     const float* xg = p.x[g];
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = cta; tile < p.ntiles; tile += ncta) {
-      const long long m = (long long)tile * 128 + r;
+    const unsigned W = (unsigned)p.W, H = (unsigned)p.H, D = (unsigned)p.D;
+    const unsigned M32 = (unsigned)p.M;              // host guarantees M < 2^31
+    int it = grp;
+    for (int tile = cta + grp * ncta; tile < p.ntiles; tile += 2 * ncta, it += 2) {
+      const int s = it % C1U_STAGES;
+      const uint32_t ph = (uint32_t)(it / C1U_STAGES) & 1u;
+      const unsigned m = (unsigned)tile * 128u + (unsigned)r;
       float in[32];
 #pragma unroll
       for (int t = 27; t < 32; ++t) in[t] = 0.f;
-      if (m < p.M) {
-        const int wq = (int)(m % p.W);
-        const int hq = (int)((m / p.W) % p.H);
-        const int dq = (int)((m / ((long long)p.W * p.H)) % p.D);
+      if (m < M32) {
+        const unsigned wq = m % W, t1 = m / W;
+        const unsigned hq = t1 % H, t2 = t1 / H;
+        const unsigned dq = t2 % D;
+        const bool dok[3] = {dq > 0, true, dq + 1 < D};
+        const bool hok[3] = {hq > 0, true, hq + 1 < H};
+        const bool wok[3] = {wq > 0, true, wq + 1 < W};
         const float* xp = xg + m;
+        const int sH = (int)(W * H), sW = (int)W;
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const int dd = dq + kd - 1, hh = hq + kh - 1, ww = wq + kw - 1;
-              const bool ok = dd >= 0 && dd < p.D && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
-              in[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + ((long long)(kd - 1) * p.H + (kh - 1)) * p.W + (kw - 1)) : 0.f;
+              const bool ok = dok[kd] && hok[kh] && wok[kw];
+              in[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
             }
       } else {
 #pragma unroll
@@ -130,9 +138,8 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       }
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
       mbar_arrive(full + 8 * s);
-      if (++s == C1U_STAGES) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ======================================= MMA issuer =============================================
     int s = 0;
     uint32_t ph = 0;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
         atomicAdd(&stats_ptr[64 + i * 32 + lane], ssq[i]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 160;             // 0..127 over the four epilogue warps
+      const int e = threadIdx.x - 288;             // 0..127 over the four epilogue warps
       if (e < p.cout) {
         atomicAdd(&p.stats[g][e], (double)stats_ptr[e]);
         atomicAdd(&p.stats[g][p.cout + e], (double)stats_ptr[64 + e]);
@@ -234,9 +241,184 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// conv1.0 weight gradient on tcgen05:   dW[co][kd][kh][kw] = sum_v dy[v,co] * x[v + (kd-1,kh-1,kw-1)]
+//
+// K = voxels (padded-row linearisation q = h*Wp + c of one (n,d) plane, Wp = W + 2, 128 voxels per tile).
+//   A (M = 128 lanes) = the dY slab [voxel rows][32 channels] exactly as TMA lands it (MN-major, 64B swizzle), loaded
+//       two columns early (slab column c <-> dy voxel w = c - 2); the four 32-channel M atoms start one row apart
+//       (LBO = 64 B), i.e. atom j sees dy shifted by j voxels along w  ->  j = 0,1,2 are the taps kw = 2,1,0.
+//   B (N = 16)        = x patches, K-major: row n = kd*3+kh holds x(d+kd-1, h+kh-1, c-1) for the tile's 128 voxels --
+//       contiguous pieces of image rows, written by builder warps as bf16 hi / lo tiles (128B swizzle), so the fp32
+//       image enters as xh + xl (two MMAs per K step).
+// Accumulation stays in TMEM (16 columns) over the CTA's whole tile range; 864 atomics per CTA at the end.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int C1W_U_THREADS = 320;          // warp 0: TMA (dY), warps 1-8: patch builders (two groups), warp 9: MMA
+constexpr int C1W_U_STAGES = 4;
+constexpr uint32_t C1W_U_PTILE = 2 * 16 * 128;     // [2 K-blocks][16 rows][128 B]
+
+struct alignas(64) C1WParams {
+  CUtensorMap tmY[TMF_MAX_GROUPS];
+  const float* x[TMF_MAX_GROUPS];
+  float* dw[TMF_MAX_GROUPS];
+  int ng, B, D, H, W, Wp, NHy, QT, ntiles;
+  uint32_t y_tx, y_slab_bytes, stage_bytes, idesc;
+};
+
+__global__ void __launch_bounds__(C1W_U_THREADS, 1) conv1_umma_wgrad_kernel(const __grid_constant__ C1WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + C1W_U_STAGES * p.stage_bytes;
+  const uint32_t y_full = bars, p_full = bars + 8 * C1W_U_STAGES, empty = p_full + 8 * C1W_U_STAGES;
+  const uint32_t acc_full = empty + 8 * C1W_U_STAGES, tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % p.ng;
+  const int cta = blockIdx.x / p.ng, ncta = gridDim.x / p.ng;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C1W_U_STAGES; ++i) {
+      mbar_init(y_full + 8 * i, 1);
+      mbar_init(p_full + 8 * i, 128);
+      mbar_init(empty + 8 * i, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.tmY[g]);
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 32);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cta; tile < p.ntiles; tile += ncta) {
+        int t = tile;
+        const int qt = t % p.QT; t /= p.QT;
+        const int d = t % p.D;
+        const int n = t / p.D;
+        const int h0 = (qt * 128) / p.Wp;
+        mbar_wait(empty + 8 * s, ph ^ 1u);
+        mbar_expect_tx(y_full + 8 * s, p.y_tx);
+        tma_load_5d(smem_base + (uint32_t)s * p.stage_bytes, &p.tmY[g], y_full + 8 * s, 0, -2, h0, d, n);
+        if (++s == C1W_U_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp <= 8) {
+    // ---- patch builders: thread -> (row n = kd*3+kh, two 8-voxel chunks) of the K-major B tile
+    const int grp = (warp - 1) >> 2;
+    const int tb = (threadIdx.x - 32) & 127;
+    const int n = tb >> 3, qc = tb & 7;
+    const int kd = n / 3, kh = n % 3;
+    const float* xg = p.x[g];
+    int it = grp;
+    for (int tile = cta + grp * ncta; tile < p.ntiles; tile += 2 * ncta, it += 2) {
+      const int s = it % C1W_U_STAGES;
+      const uint32_t ph = (uint32_t)(it / C1W_U_STAGES) & 1u;
+      int t = tile;
+      const int qt = t % p.QT; t /= p.QT;
+      const int d = t % p.D;
+      const int nb = t / p.D;
+      float v[2][8];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int q = qt * 128 + (qc + 8 * half) * 8;
+        int h = q / p.Wp, c = q - h * p.Wp;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int dd = d + kd - 1, hh = h + kh - 1, ww = c - 1;
+          const bool ok = n < 9 && dd >= 0 && dd < p.D && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+          v[half][e] = ok ? __ldg(xg + (((long long)nb * p.D + dd) * p.H + hh) * p.W + ww) : 0.f;
+          if (++c == p.Wp) { c = 0; ++h; }
+        }
+      }
+      mbar_wait(empty + 8 * s, ph ^ 1u);
+      uint8_t* ptile = gen + (size_t)s * p.stage_bytes + p.y_slab_bytes;       // P_hi, then P_lo
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(v[half][e], hi[e], lo[e]);
+        const uint32_t off = (uint32_t)half * 2048u + (uint32_t)n * 128u + (uint32_t)((qc ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(ptile + off) = pack8(hi);
+        *reinterpret_cast<uint4*>(ptile + C1W_U_PTILE + off) = pack8(lo);
+      }
+      fence_proxy_async();
+      mbar_arrive(p_full + 8 * s);
+    }
+    if (warp <= 4) {
+      // ---- epilogue (after the whole range): lane m = (j, co) -> taps kw = 2 - j; column n = kd*3+kh
+      mbar_wait(acc_full, 0u);
+      tc_fence_after();
+      const int quarter = warp & 3;
+      const int m = quarter * 32 + lane;
+      const int j = m >> 5, co = m & 31;
+      uint32_t raw[32];
+      // 16 valid columns; the x32 load reads 16 unallocated-but-in-range columns of our 32-column allocation
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16), raw);
+      tmem_ld_wait();
+      if (j < 3) {
+#pragma unroll
+        for (int nn = 0; nn < 9; ++nn) atomicAdd(&p.dw[g][co * 27 + nn * 3 + (2 - j)], __uint_as_float(raw[nn]));
+      }
+    }
+  } else {
+    // ---- MMA issuer (warp 9)
+    int s = 0;
+    uint32_t ph = 0;
+    const uint64_t hi_a = make_smem_desc(0, 64, 512, LAYOUT_SW64, 0) & 0xFFFFFFFF00000000ull;      // MN-major dY slab
+    const uint32_t a_const = (uint32_t)(make_smem_desc(0, 64, 512, LAYOUT_SW64, 0) & 0xFFFF0000ull);
+    const uint64_t hi_b = make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0) & 0xFFFFFFFF00000000ull;    // K-major patches
+    const uint32_t b_const = (uint32_t)(make_smem_desc(0, 16, 1024, LAYOUT_SW128, 0) & 0xFFFF0000ull);
+    uint32_t accumulate = 0;
+    for (int tile = cta; tile < p.ntiles; tile += ncta) {
+      const int qt = tile % p.QT;
+      const uint32_t qoff = (uint32_t)((qt * 128) % p.Wp);
+      mbar_wait(y_full + 8 * s, ph);
+      mbar_wait(p_full + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t st = smem_base + (uint32_t)s * p.stage_bytes;
+      const uint32_t a_lo = a_const | (((st + qoff * 64u) & 0x3FFFFu) >> 4);
+      const uint32_t bh_lo = b_const | (((st + p.y_slab_bytes) & 0x3FFFFu) >> 4);
+      const uint32_t bl_lo = bh_lo + (C1W_U_PTILE >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t boff = (uint32_t)(k >> 2) * (2048u >> 4) + (uint32_t)(k & 3) * 2u;
+          const uint32_t aoff = (uint32_t)k * ((16u * 64u) >> 4);
+          mma_bf16_ss(tmem_base, hi_a | (uint64_t)(a_lo + aoff), hi_b | (uint64_t)(bh_lo + boff), p.idesc,
+                      (accumulate | (uint32_t)k) ? 1u : 0u);
+          mma_bf16_ss(tmem_base, hi_a | (uint64_t)(a_lo + aoff), hi_b | (uint64_t)(bl_lo + boff), p.idesc, 1u);
+        }
+        mma_commit(empty + 8 * s);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++s == C1W_U_STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (elect_one()) mma_commit(acc_full);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
   }
 }
 
@@ -253,6 +435,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
                        double* const* stats, int B, int D, int H, int W, int cout, void* stream) {
   TMF_CHECK_NG(ng);
   TMF_REQUIRE(cout == 32 || cout == 64, "conv1_fwd_umma: Cout must be 32 or 64 (got %d)", cout);
+  TMF_REQUIRE((long long)B * D * H * W < (1ll << 31), "conv1_fwd_umma: volume batch too large for 32-bit voxel indices");
   C1UParams p{};
   p.ng = ng; p.B = B; p.D = D; p.H = H; p.W = W; p.cout = cout;
   p.M = (long long)B * D * H * W;
@@ -281,6 +464,72 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   if (per_group > p.ntiles) per_group = p.ntiles;
   if (per_group < 1) per_group = 1;
   conv1_umma_fwd_kernel<<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+
+bool tmf_conv1_wgrad_umma_supported(int W, int cout) {
+  if (getenv("TMF_DISABLE_UMMA") != nullptr || getenv("TMF_DISABLE_UMMA_CONV1") != nullptr) return false;
+  return cout == 32 && W + 2 <= 256;
+}
+
+int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
+                         int W, int cout, void* stream) {
+  TMF_CHECK_NG(ng);
+  TMF_REQUIRE(tmf_conv1_wgrad_umma_supported(W, cout) || cout == 32, "conv1_wgrad_umma: needs Cout = 32 (got %d)", cout);
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  TMF_REQUIRE(encode != nullptr, "conv1_wgrad_umma: cuTensorMapEncodeTiled entry point not available");
+  C1WParams p{};
+  p.ng = ng; p.B = B; p.D = D; p.H = H; p.W = W;
+  p.Wp = W + 2;
+  p.NHy = ((p.Wp - 1) + 127 + 3) / p.Wp + 1;
+  p.QT = (H * p.Wp + 127) / 128;
+  p.ntiles = B * D * p.QT;
+  p.y_tx = (uint32_t)p.NHy * p.Wp * 64u;
+  p.y_slab_bytes = (p.y_tx + 1023u) & ~1023u;
+  p.stage_bytes = p.y_slab_bytes + 2 * C1W_U_PTILE;
+  p.idesc = make_idesc_bf16(128, 16, /*A MN-major*/ 1, /*B K-major*/ 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < ng; ++g) {
+    TMF_REQUIRE(dy[g] && x[g] && dw[g], "conv1_wgrad_umma: NULL device pointer");
+    p.x[g] = x[g];
+    p.dw[g] = dw[g];
+    TMF_CUDA(cudaMemsetAsync(dw[g], 0, sizeof(float) * 27 * cout, st));
+    cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)cout * 2, (cuuint64_t)W * cout * 2, (cuuint64_t)H * W * cout * 2,
+                             (cuuint64_t)D * H * W * cout * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.Wp, (cuuint32_t)p.NHy, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&p.tmY[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy[g]), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TMF_REQUIRE(r == CUDA_SUCCESS, "conv1_wgrad_umma: cuTensorMapEncodeTiled(dY) failed with %d", (int)r);
+  }
+  const uint32_t smem = 1024 + C1W_U_STAGES * p.stage_bytes + 8 * (3 * C1W_U_STAGES) + 64;
+  TMF_REQUIRE(smem <= 227 * 1024, "conv1_wgrad_umma: W=%d too wide", W);
+  static bool attr_done = false;
+  if (!attr_done) {
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_group = sms / ng;
+  if (per_group > p.ntiles) per_group = p.ntiles;
+  if (per_group < 1) per_group = 1;
+  conv1_umma_wgrad_kernel<<<dim3(per_group * ng), C1W_U_THREADS, smem, st>>>(p);
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -459,6 +459,9 @@ using namespace tmf;
 bool tmf_conv1_fwd_umma_supported(int cout);
 int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, const float* const* bias, void* const* y,
                        double* const* stats, int B, int D, int H, int W, int cout, void* stream);
+bool tmf_conv1_wgrad_umma_supported(int W, int cout);
+int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
+                         int W, int cout, void* stream);
 // implemented in conv_umma.cu
 int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, const float* const* bias,
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
@@ -527,8 +530,13 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
 }
 
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
-                    int W, int cout, void* stream) {
+                    int W, int cout, int impl, void* stream) {
   TMF_CHECK_NG(ng);
+  if (impl == TMF_CONV_AUTO) impl = tmf_conv1_wgrad_umma_supported(W, cout) ? TMF_CONV_UMMA : TMF_CONV_DIRECT;
+  if (impl == TMF_CONV_UMMA) {
+    TMF_REQUIRE(tmf_conv1_wgrad_umma_supported(W, cout), "conv1_wgrad: tcgen05 path needs Cout = 32 (got %d)", cout);
+    return tmf_conv1_wgrad_umma(ng, dy, x, dw, B, D, H, W, cout, stream);
+  }
   TMF_REQUIRE(cout >= 8 && cout <= 64 && cout % 8 == 0, "conv1_wgrad: Cout must be a multiple of 8 in [8,64] (got %d)",
               cout);
   GroupPtr<const __nv_bfloat16> gdy;

@@ -153,7 +153,7 @@ class SNetFunction(torch.autograd.Function):
                    L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_apply@L{l}")
             dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
             if l == 0:
-                L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout)
+                L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout, ctx.impl)
             else:
                 ws = wgrad_workspace(ng, ctx.impl, B, Dl, Hl, Wl, cin, cout, ks, dev)
                 L.call("tmf_conv3d_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cin, cout, ks,
