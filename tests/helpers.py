@@ -160,6 +160,13 @@ def parity_report(name, device="cuda"):
                      if not is_conv_bias(k) and float(sd[k].grad.norm()) >= 1e-5])
     rep["global_grad_cos_A"] = cosine(ours, ref)
     rep["global_grad_rel_A"] = rel_err(ours, ref)
+    # the same direction for the fp32 oracle (no rounding emulation): how far bf16 rounding ALONE moves the gradient
+    sd32 = R.clone_state(state)
+    losses(oracle_forward(kind, sd32, inputs, kwargs, True, 0.0, rnd=None), label)[2].backward()
+    ref32 = torch.cat([sd32[k].grad.flatten() for k, p in model.named_parameters()
+                       if not is_conv_bias(k) and float(sd[k].grad.norm()) >= 1e-5])
+    rep["global_grad_cos_B"] = cosine(ours, ref32)
+    rep["global_grad_cos_A_vs_B"] = cosine(ref, ref32)
     msd = model.state_dict()
     rep["buffers"] = {k: (int(msd[k]) == int(v)) if k.endswith("num_batches_tracked")
                       else float((msd[k].cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))

