@@ -41,6 +41,8 @@ __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
   lo = v - hi;
 }
 
+// NCH = Cout / 32 (1 for dim 128, the benchmark path; 2 for dim 256 -- that variant spills some statistics registers)
+template <int NCH>
 __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __grid_constant__ C1UParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,7 +73,8 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int t = j * 8 + e;
-      const float v = (t < 27) ? p.w[g][co * 27 + t] : 0.f;
+      float v = (t < 27) ? p.w[g][co * 27 + t] : 0.f;
+      if (t == 27 && p.bias[g] != nullptr) v = p.bias[g][co];      // bias rides on K column 27 (im2col value 1)
       split_bf16(v, hi[e], lo[e]);
     }
     *reinterpret_cast<uint4*>(gen + (smW - smem_base) + sw64_off(co, j)) = pack8(hi);
@@ -101,7 +104,8 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       const unsigned m = (unsigned)tile * 128u + (unsigned)r;
       float in[32];
 #pragma unroll
-      for (int t = 27; t < 32; ++t) in[t] = 0.f;
+      for (int t = 28; t < 32; ++t) in[t] = 0.f;
+      in[27] = (m < M32) ? 1.f : 0.f;                 // bias column; rows past the end stay all-zero
       if (m < M32) {
         const unsigned wq = m % W, t1 = m / W;
         const unsigned hq = t1 % H, t2 = t1 / H;
@@ -173,12 +177,19 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
     }
   } else {
     // ======================================= epilogue ===============================================
+    // Per tile and thread (= one voxel row): TMEM -> 32 fp32 -> packed bf16 (cvt.rn.bf16x2) -> 16-byte stores; the
+    // BatchNorm sums of the STORED values accumulate in per-thread registers over the whole tile range and are
+    // reduced across lanes / warps once, at the end (no per-tile shuffles or atomics).  Bias is already in the
+    // accumulator (K column 27).
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const float* bias = p.bias[g];
     __nv_bfloat16* yg = p.y[g];
     const bool want_stats = p.stats[g] != nullptr;
-    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
+    float ssum[NCH][32], ssq[NCH][32];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { ssum[c][j] = 0.f; ssq[c][j] = 0.f; }
     int it = 0;
     for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
       const long long m = (long long)tile * 128 + row;
@@ -188,48 +199,58 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       mbar_wait(acc_full + 8 * as, acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout);
-      for (int c0 = 0; c0 < p.cout; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(taddr + (uint32_t)c0, raw);
-        tmem_ld_wait();
-        float v[32], sq[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(raw[j]);
-          if (bias != nullptr) a += __ldg(bias + c0 + j);
-          v[j] = valid ? round_bf16(a) : 0.f;
-          sq[j] = v[j] * v[j];
-        }
-        if (valid) {
-          __nv_bfloat16* yrow = yg + m * p.cout + c0;
+      for (int c = 0; c < NCH; ++c) {
+        {
+          uint32_t raw[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), raw);
+          tmem_ld_wait();
+          if (c == NCH - 1) {                       // accumulator drained: hand the buffer back before the stores
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8 * as);
+          }
+          uint32_t pk[16];
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) *reinterpret_cast<uint4*>(yrow + qd * 8) = pack8(&v[qd * 8]);
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+          if (valid) {
+            uint4* yrow = reinterpret_cast<uint4*>(yg + m * p.cout + c * 32);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) yrow[qd] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+          }
+          if (want_stats) {                         // rows past the end are exact zeros (all-zero im2col row)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+              ssum[c][2 * j] += lo;
+              ssum[c][2 * j + 1] += hi;
+              ssq[c][2 * j] = fmaf(lo, lo, ssq[c][2 * j]);
+              ssq[c][2 * j + 1] = fmaf(hi, hi, ssq[c][2 * j + 1]);
+            }
+          }
         }
-        if (want_stats) {
+      }
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        {
+          // transpose-reduce: lane l ends with the warp total of column c*32 + l
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             const bool upper = (lane & off) != 0;
 #pragma unroll
             for (int i = 0; i < off; ++i) {
-              const float s_send = upper ? v[i] : v[i + off];
-              const float s_keep = upper ? v[i + off] : v[i];
-              v[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
-              const float q_send = upper ? sq[i] : sq[i + off];
-              const float q_keep = upper ? sq[i + off] : sq[i];
-              sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+              const float s_send = upper ? ssum[c][i] : ssum[c][i + off];
+              const float s_keep = upper ? ssum[c][i + off] : ssum[c][i];
+              ssum[c][i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+              const float q_send = upper ? ssq[c][i] : ssq[c][i + off];
+              const float q_keep = upper ? ssq[c][i + off] : ssq[c][i];
+              ssq[c][i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
             }
           }
-          ssum[c0 >> 5] += v[0];
-          ssq[c0 >> 5] += sq[0];
+          atomicAdd(&stats_ptr[c * 32 + lane], ssum[c][0]);
+          atomicAdd(&stats_ptr[64 + c * 32 + lane], ssq[c][0]);
         }
-      }
-      tc_fence_before();
-      mbar_arrive(acc_empty + 8 * as);
-    }
-    if (want_stats) {
-      for (int i = 0; i * 32 < p.cout; ++i) {
-        atomicAdd(&stats_ptr[i * 32 + lane], ssum[i]);
-        atomicAdd(&stats_ptr[64 + i * 32 + lane], ssq[i]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 288;             // 0..127 over the four epilogue warps
@@ -454,7 +475,8 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 512 + 64;
   static bool attr_done = false;
   if (!attr_done) {
-    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   int dev = 0, sms = 148;
@@ -463,7 +485,8 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   int per_group = sms / ng;
   if (per_group > p.ntiles) per_group = p.ntiles;
   if (per_group < 1) per_group = 1;
-  conv1_umma_fwd_kernel<<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
+  if (cout == 32) conv1_umma_fwd_kernel<1><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
+  else conv1_umma_fwd_kernel<2><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
