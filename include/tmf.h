@@ -65,6 +65,19 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw,
                     int B, int D, int H, int W, int cout, int impl, void* stream);
 
+/* Block-1 backward in one pass over y: the BatchNorm + LeakyReLU + MaxPool3d(2,2) backward "apply" (what
+ * tmf_bn_act_pool_bwd_apply computes with pool = TMF_POOL_MAX) fused with the conv1.0 weight gradient, so dy of
+ * block 1 (which feeds nothing else: conv1.0's input is the image) never goes to HBM.  dout: bf16 pooled gradient
+ * [B,D/2,H/2,W/2,32]; y: bf16 conv1.0 output [B,D,H,W,32]; coef / bcoef as below; x: fp32 image; dw (32,1,3,3,3) is
+ * overwritten (deterministic reduction).  `ws`: caller-owned, 256-byte aligned scratch of at least
+ * tmf_conv1_bwd_fused_workspace_bytes(...) bytes; that function returns 0 when the problem is not supported
+ * (Cout != 32, W > 240, ...) -- callers then use tmf_bn_act_pool_bwd_apply + tmf_conv1_wgrad.
+ * reference models/networks.py:22-25 (autograd backward of Conv3d(1,32,3,p1) / BatchNorm3d / LeakyReLU / MaxPool3d) */
+int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, const float* const* coef,
+                        const float* const* bcoef, const float* const* x, float* const* dw, int B, int D, int H,
+                        int W, int cout, float slope, void* ws, size_t ws_bytes, void* stream);
+int64_t tmf_conv1_bwd_fused_workspace_bytes(int ng, int B, int D, int H, int W, int cout);
+
 /* 3x3x3 (pad 1) or 1x1x1 convolution, bf16 NDHWC input a[B,D,H,W,Cin], packed bf16 weights wf[tap][Cout][Cin],
  * optional fp32 bias, bf16 output y[B,D,H,W,Cout], optional stats (as above; NULL array = none).
  * Also used for dgrad (a = dy, wf = flipped/transposed pack, bias = stats = NULL).

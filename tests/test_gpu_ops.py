@@ -304,3 +304,76 @@ def test_bad_arguments_fail_loudly():
     with pytest.raises(RuntimeError, match="NULL"):
         L.call("tmf_conv3d_fwd", 1, L.ptrs([None]), L.ptrs([None]), L.ptrs(None), L.ptrs([None]), L.ptrs(None),
                1, 4, 4, 4, 32, 32, 3, L.CONV_DIRECT)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,ng,training", [((2, 17, 19, 18), 1, 1), ((1, 16, 22, 33), 2, 1), ((1, 9, 12, 91), 1, 1),
+                                               ((2, 10, 11, 21), 2, 0)])
+def test_conv1_bwd_fused_matches_two_step_path_and_torch(shape, ng, training):
+    """Block-1 backward in one pass (BN/LeakyReLU/MaxPool apply + conv1.0 wgrad) == apply kernel + conv1_wgrad kernel
+    (same dy rounding to bf16), and both match the torch fp32 autograd of the same block on the stored bf16 y."""
+    B, D, H, W = shape
+    cout = 32
+    lib = L.load()
+    nws = int(lib.tmf_conv1_bwd_fused_workspace_bytes(ng, B, D, H, W, cout))
+    assert nws > 0
+    xs, ys, douts, coefs, bcoefs, dw_f, dw_2, dys = [], [], [], [], [], [], [], []
+    refs = []
+    for t in range(ng):
+        x = torch.rand(B, 1, D, H, W, generator=torch.Generator().manual_seed(11 + t))
+        w = g_randn(cout, 1, 3, 3, 3, seed=12 + t, scale=0.3)
+        gamma = 1.0 + 0.3 * g_randn(cout, seed=13 + t)
+        gamma[3] = -gamma[3]                       # a negative scale exercises the arg-min branch of the pool routing
+        beta = 0.2 * g_randn(cout, seed=14 + t)
+        y32 = F.conv3d(x, w, None, padding=1)
+        yb = bf16r(y32)                            # the stored conv output
+        dout = bf16r(g_randn(B, cout, D // 2, H // 2, W // 2, seed=15 + t))
+        # torch reference of BN -> LeakyReLU -> MaxPool on the stored y, autograd for dy
+        yv = yb.clone().requires_grad_(True)
+        if training:
+            z = F.batch_norm(yv, None, None, gamma, beta, True, 0.1, 1e-5)
+            mean = yb.mean(dim=(0, 2, 3, 4)); var = yb.var(dim=(0, 2, 3, 4), unbiased=False)
+        else:
+            mean = 0.1 * g_randn(cout, seed=16 + t); var = 1.0 + 0.2 * torch.rand(cout, generator=torch.Generator().manual_seed(17 + t))
+            z = F.batch_norm(yv, mean.clone(), var.clone(), gamma, beta, False, 0.1, 1e-5)
+        out = F.max_pool3d(F.leaky_relu(z, 0.01), 2, 2)
+        out.backward(dout)
+        dy_ref = yv.grad
+        dw_ref = torch.nn.grad.conv3d_weight(x, w.shape, bf16r(dy_ref), padding=1)
+        refs.append((dy_ref, dw_ref))
+        invstd = 1.0 / torch.sqrt(var + 1e-5)
+        scale = gamma * invstd
+        coef = torch.cat([scale, beta - mean * scale, mean, invstd]).float()
+        xs.append(x.to(DEV)); ys.append(to_ndhwc_bf16(yb)); douts.append(to_ndhwc_bf16(dout)); coefs.append(coef.to(DEV))
+        dw_f.append(torch.zeros(cout, 1, 3, 3, 3, device=DEV)); dw_2.append(torch.zeros(cout, 1, 3, 3, 3, device=DEV))
+        dys.append(torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV))
+    # bcoef through the library's own reduce + finalize
+    sums = [torch.empty(2 * cout, dtype=torch.float64, device=DEV) for _ in range(ng)]
+    L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(douts), 0, L.ptrs(ys), L.ptrs(coefs), L.ptrs(sums), B, D, H, W, cout,
+           L.POOL_MAX, 0.01)
+    dgamma = [torch.empty(cout, device=DEV) for _ in range(ng)]
+    dbeta = [torch.empty(cout, device=DEV) for _ in range(ng)]
+    bcoefs = [torch.empty(2 * cout, device=DEV) for _ in range(ng)]
+    L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coefs), L.ptrs(dgamma), L.ptrs(dbeta), L.ptrs(None),
+           L.ptrs(bcoefs), cout, B * D * H * W, training)
+    # two-step path
+    L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(douts), 0, L.ptrs(ys), L.ptrs(coefs), L.ptrs(bcoefs), L.ptrs(dys),
+           B, D, H, W, cout, L.POOL_MAX, 0.01)
+    L.call("tmf_conv1_wgrad", ng, L.ptrs(dys), L.ptrs(xs), L.ptrs(dw_2), B, D, H, W, cout, L.CONV_DIRECT)
+    # fused path
+    ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+    L.call("tmf_conv1_bwd_fused", ng, L.ptrs(douts), L.ptrs(ys), L.ptrs(coefs), L.ptrs(bcoefs), L.ptrs(xs), L.ptrs(dw_f),
+           B, D, H, W, cout, 0.01, L.ptr(ws), nws)
+    torch.cuda.synchronize()
+    for t in range(ng):
+        dy_ref, dw_ref = refs[t]
+        assert rel_l2(from_ndhwc(dys[t]), dy_ref) < 6e-3, "two-step dy vs torch"
+        assert rel_l2(dw_2[t].cpu(), dw_ref) < 5e-3, "two-step dW vs torch"
+        assert rel_l2(dw_f[t].cpu(), dw_2[t].cpu()) < 1e-3, "fused dW vs two-step dW"
+        assert rel_l2(dw_f[t].cpu(), dw_ref) < 5e-3, "fused dW vs torch"
+    # deterministic (fixed-order reduction)
+    dw_again = [torch.zeros_like(d) for d in dw_f]
+    L.call("tmf_conv1_bwd_fused", ng, L.ptrs(douts), L.ptrs(ys), L.ptrs(coefs), L.ptrs(bcoefs), L.ptrs(xs), L.ptrs(dw_again),
+           B, D, H, W, cout, 0.01, L.ptr(ws), nws)
+    for t in range(ng):
+        assert torch.equal(dw_again[t], dw_f[t])

@@ -24,6 +24,7 @@ SIGNATURES = {
     "tmf_pack_conv_weights": [_i, _pp, _pp, _pp, _i, _i, _i, _vp],
     "tmf_conv1_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp],
     "tmf_conv1_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv1_bwd_fused": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _f, _vp, C.c_size_t, _vp],
     "tmf_conv3d_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "tmf_conv3d_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_bn_finalize": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i64, _f, _f, _i, _vp],
@@ -45,7 +46,8 @@ SIGNATURES = {
 }
 PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
-         "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9)}
+         "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
+         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6)}
 
 _lib = None
 _device_checked = False

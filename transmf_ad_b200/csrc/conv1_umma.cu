@@ -92,53 +92,78 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 
   if (warp < 8) {
     // ======================================= im2col producers =======================================
+    // Software-pipelined: the 27 loads of a thread's NEXT tile are in flight while the current row is split into
+    // bf16 hi / lo and written, so one producer group alone already overlaps global latency with ALU work; the two
+    // groups (alternating tiles) then overlap each other's barrier waits.  Voxel coordinates advance incrementally
+    // (no div / mod in the loop).
     const int grp = warp >> 2;                       // producer group: handles every other tile of this CTA
     const int r = threadIdx.x & 127;                 // row of the tile
     const float* xg = p.x[g];
     const unsigned W = (unsigned)p.W, H = (unsigned)p.H, D = (unsigned)p.D;
     const unsigned M32 = (unsigned)p.M;              // host guarantees M < 2^31
+    const int sH = (int)(W * H), sW = (int)W;
+    const unsigned stride = 256u * (unsigned)ncta;   // voxels between consecutive tiles of this group
+    const unsigned st_w = stride % W, st_t = stride / W, st_h = st_t % H, st_d = (st_t / H) % D;
+    unsigned m = (unsigned)(cta + grp * ncta) * 128u + (unsigned)r;
+    unsigned wq = m % W, hq = (m / W) % H, dq = (m / (W * H)) % D;
+    float nxt[28];
+    auto load_row = [&](float (&v)[28]) {
+      const bool in_range = m < M32;
+      v[27] = in_range ? 1.f : 0.f;                   // bias column; rows past the end stay all-zero
+      const bool dok[3] = {in_range && dq > 0, in_range, in_range && dq + 1 < D};
+      const bool hok[3] = {hq > 0, true, hq + 1 < H};
+      const bool wok[3] = {wq > 0, true, wq + 1 < W};
+      const float* xp = xg + m;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = dok[kd] && hok[kh] && wok[kw];
+            v[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
+          }
+    };
+    auto advance = [&]() {
+      m += stride;
+      wq += st_w;
+      unsigned c = wq >= W ? 1u : 0u;
+      wq -= c * W;
+      hq += st_h + c;
+      c = hq >= H ? 1u : 0u;
+      hq -= c * H;
+      dq += st_d + c;
+      if (dq >= D) dq -= D;
+    };
     int it = grp;
-    for (int tile = cta + grp * ncta; tile < p.ntiles; tile += 2 * ncta, it += 2) {
+    int tile = cta + grp * ncta;
+    if (tile < p.ntiles) load_row(nxt);
+    for (; tile < p.ntiles; tile += 2 * ncta, it += 2) {
       const int s = it % C1U_STAGES;
       const uint32_t ph = (uint32_t)(it / C1U_STAGES) & 1u;
-      const unsigned m = (unsigned)tile * 128u + (unsigned)r;
-      float in[32];
+      float in[28];
 #pragma unroll
-      for (int t = 28; t < 32; ++t) in[t] = 0.f;
-      in[27] = (m < M32) ? 1.f : 0.f;                 // bias column; rows past the end stay all-zero
-      if (m < M32) {
-        const unsigned wq = m % W, t1 = m / W;
-        const unsigned hq = t1 % H, t2 = t1 / H;
-        const unsigned dq = t2 % D;
-        const bool dok[3] = {dq > 0, true, dq + 1 < D};
-        const bool hok[3] = {hq > 0, true, hq + 1 < H};
-        const bool wok[3] = {wq > 0, true, wq + 1 < W};
-        const float* xp = xg + m;
-        const int sH = (int)(W * H), sW = (int)W;
+      for (int t = 0; t < 28; ++t) in[t] = nxt[t];
+      advance();
+      if (tile + 2 * ncta < p.ntiles) load_row(nxt);
+      // bf16 hi / lo split, two elements per cvt.rn.bf16x2:  hi = bf16(v), lo = bf16(v - hi)
+      uint32_t phi[16], plo[16];
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const bool ok = dok[kd] && hok[kh] && wok[kw];
-              in[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
-            }
-      } else {
-#pragma unroll
-        for (int t = 0; t < 27; ++t) in[t] = 0.f;
+      for (int j = 0; j < 14; ++j) {
+        const float a = in[2 * j], b = in[2 * j + 1];
+        const uint32_t h2 = pack_bf16(a, b);
+        phi[j] = h2;
+        plo[j] = pack_bf16(a - bf16_lo(h2), b - bf16_hi(h2));
       }
+      phi[14] = phi[15] = plo[14] = plo[15] = 0u;
       mbar_wait(empty + 8 * s, ph ^ 1u);
       uint8_t* a_hi = gen + (smA - smem_base) + (size_t)s * 2 * C1U_TILE_BYTES;
       uint8_t* a_lo = a_hi + C1U_TILE_BYTES;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(in[j * 8 + e], hi[e], lo[e]);
         const uint32_t off = sw64_off(r, j);
-        *reinterpret_cast<uint4*>(a_hi + off) = pack8(hi);
-        *reinterpret_cast<uint4*>(a_lo + off) = pack8(lo);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
       }
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
       mbar_arrive(full + 8 * s);

@@ -148,10 +148,23 @@ class SNetFunction(torch.autograd.Function):
             bcoef = [torch.empty(2 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(dgamma), L.ptrs(dbeta),
                    L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
+            dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
+            fused_ws = 0
+            if l == 0 and pool == L.POOL_MAX and not dout_fp32 and ctx.impl != L.CONV_DIRECT:
+                fused_ws = int(L.load().tmf_conv1_bwd_fused_workspace_bytes(ng, B, Dl, Hl, Wl, cout))
+            if fused_ws > 0:
+                # block 1: BN/LeakyReLU/MaxPool backward "apply" + conv1.0 weight gradient in one pass; dy stays on chip
+                ws = torch.empty(fused_ws, dtype=torch.uint8, device=dev)
+                L.call("tmf_conv1_bwd_fused", ng, L.ptrs(dout), L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef), L.ptrs(act),
+                       L.ptrs(dw), B, Dl, Hl, Wl, cout, LRELU_SLOPE, L.ptr(ws), fused_ws)
+                for t in range(ng):
+                    base = (t * 7 + l) * 4
+                    pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
+                saved[l] = None
+                continue
             dy = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
             L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef),
                    L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_apply@L{l}")
-            dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
             if l == 0:
                 L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout, ctx.impl)
             else:
