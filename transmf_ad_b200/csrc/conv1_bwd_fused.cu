@@ -160,22 +160,40 @@ __global__ void __launch_bounds__(C1B_THREADS, 1) conv1_bwd_fused_kernel(const _
     __syncwarp();
   } else {
     // =========================================== dy builders ============================================
+    // ALU diet (this pass is instruction-bound if written element by element):
+    //  * the window arg-max runs on PACKED bf16 pairs: key = (y & and) ^ xor puts sign(scale) into the sign bit
+    //    (and = 0 for scale == 0: every key equal, the first voxel wins like in torch), HMNMX2 for the maximum,
+    //    HSET2 equality masks + a 16-bit unsigned min over voxel numbers for "first maximum in (d,h,w) order";
+    //  * the dense part is one FFMA per element, dy = A + Bc*y, with no dependence on the arg-max;
+    //  * the single arg-max voxel of each (window, channel) is then patched with a 2-byte store of
+    //    bf16(A + Bc*ybest + scale*dz) -- same value, same single rounding as the two-step kernels.
+    // Bank conflicts: rows 2wo and 2wo+1 of a segment are 128 contiguous bytes, but rows of equal parity share banks;
+    // odd windows therefore load / store their two rows in swapped order, so the 8 lanes of a quarter-warp (two
+    // windows x four chunks) always cover all 32 banks.
     const int bt = threadIdx.x - 64;
     const int grp = bt / C1B_GROUP_THREADS, tb = bt % C1B_GROUP_THREADS;
     const int cq = tb & 3;                               // this thread's 8-channel chunk (loop-invariant)
+    const int b = (tb >> 2) & 1;                         // window parity (loop-invariant: the task stride is 48 windows)
     const int c0 = cq * 8;
-    float sc[8], sh[8], cA[8], cB[8], sg[8];
+    float sc[8], sh[8], cA[8], cB[8];
+    uint32_t kand[4], kxor[4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float scale = p.coef[g][c0 + j], mean = p.coef[g][64 + c0 + j], invstd = p.coef[g][96 + c0 + j];
       const float m1 = p.bcoef[g][c0 + j], m2 = p.bcoef[g][32 + c0 + j];
       sc[j] = scale;
       sh[j] = p.coef[g][32 + c0 + j];
-      sg[j] = scale > 0.f ? 1.f : (scale < 0.f ? -1.f : 0.f);
       cB[j] = -scale * m2 * invstd;
       cA[j] = -scale * m1 - cB[j] * mean;
+      const uint32_t ka = scale != 0.f ? 0xFFFFu : 0u, kx = scale < 0.f ? 0x8000u : 0u;
+      if (j & 1) { kand[j >> 1] |= ka << 16; kxor[j >> 1] |= kx << 16; }
+      else { kand[j >> 1] = ka; kxor[j >> 1] = kx; }
     }
+    uint32_t qc[8];                                       // voxel number (d,h,w scan order) held by load slot i, both halves
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qc[i] = (uint32_t)((i & 6) | ((i & 1) ^ b)) * 0x00010001u;
     const uint32_t seg_bytes = (uint32_t)p.P * 64u;
+    const uint32_t eoff[2] = {(uint32_t)b * 64u, (uint32_t)(1 - b) * 64u};     // row offset of load slot parity 0 / 1
     const int ntask = p.WC * 4;
     int it = grp;
     for (int u = cta + grp * ncta; u < p.units; u += C1B_GROUPS * ncta, it += C1B_GROUPS) {
@@ -184,59 +202,69 @@ __global__ void __launch_bounds__(C1B_THREADS, 1) conv1_bwd_fused_kernel(const _
       int t = u;
       const int hp = t % p.HP; t /= p.HP;
       const int dp = t % p.DP;
-      const bool dok[2] = {true, 2 * dp + 1 < p.D};
-      const bool hok[2] = {true, 2 * hp + 1 < p.H};
+      const bool d1 = 2 * dp + 1 < p.D, h1 = 2 * hp + 1 < p.H;
       uint8_t* stage = gen + (size_t)s * p.stage_bytes;
       mbar_wait(tma_full + 8 * s, ph);
       for (int task = tb; task < ntask; task += C1B_GROUP_THREADS) {
         const int wo = task >> 2;
-        const bool wok[2] = {true, 2 * wo + 1 < p.W};
-        const bool win_ok = dok[1] && hok[1] && wok[1];
-        float go[8];
-        unpack8(*reinterpret_cast<const uint4*>(stage + p.g_off + (uint32_t)wo * 64u + (uint32_t)cq * 16u), go);
-        const uint32_t pos = (uint32_t)((cq ^ (wo & 3)) << 4);          // 64B-swizzled chunk position (row>>1 = wo)
-        uint4 raw[8];
-        bool ex[8];
-        uint32_t off[8];
+        const bool w1 = 2 * wo + 1 < p.W;
+        const bool win_ok = d1 && h1 && w1;
+        // 64B-swizzled chunk position (row >> 1 = wo for both rows of the window)
+        uint8_t* base = stage + (uint32_t)(2 * wo) * 64u + (uint32_t)((cq ^ (wo & 3)) << 4);
+        const uint4 gov = *reinterpret_cast<const uint4*>(stage + p.g_off + (uint32_t)wo * 64u + (uint32_t)cq * 16u);
+        uint4 X[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int ds = q >> 2, hs = (q >> 1) & 1, e = q & 1;
-          ex[q] = dok[ds] && hok[hs] && wok[e];
-          off[q] = (uint32_t)(ds * 2 + hs) * seg_bytes + (uint32_t)(2 * wo + e) * 64u + pos;
-          raw[q] = ex[q] ? *reinterpret_cast<const uint4*>(stage + off[q]) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        // arg-max per channel on sign(scale)*y (first maximum in (d,h,w) scan order); dz only at the arg-max
-        float best[8], ybest[8];
-        int amax[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; ybest[j] = 0.f; amax[j] = 0; }
+        for (int i = 0; i < 8; ++i)
+          X[i] = *reinterpret_cast<const uint4*>(base + (uint32_t)(i >> 1) * seg_bytes + eoff[i & 1]);
+        uint32_t mx[4], idx[4];
         if (win_ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float f[8];
-            unpack8(raw[q], f);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t key[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float key = f[j] * sg[j];
-              if (key > best[j]) { best[j] = key; ybest[j] = f[j]; amax[j] = q; }
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t v = c == 0 ? X[i].x : (c == 1 ? X[i].y : (c == 2 ? X[i].z : X[i].w));
+              key[i] = (v & kand[c]) ^ kxor[c];
             }
+            __nv_bfloat162 m = *reinterpret_cast<__nv_bfloat162*>(&key[0]);
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&key[i]));
+            uint32_t first = 0x000F000Fu;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t eq = __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&key[i]), m);
+              first = __vminu2(first, (qc[i] & eq) | (0x000F000Fu & ~eq));
+            }
+            mx[c] = *reinterpret_cast<uint32_t*>(&m);
+            idx[c] = first;
           }
         }
-        float dzs[8];
+        // dense part: dy = A + Bc*y for every existing voxel of the window
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(ybest[j], sc[j], sh[j]);
-          const float dz = win_ok ? (z > 0.f ? go[j] : go[j] * p.slope) : 0.f;
-          dzs[j] = sc[j] * dz;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (!ex[q]) continue;
+        for (int i = 0; i < 8; ++i) {
+          const bool ex = ((i >> 2) == 0 || d1) && (((i >> 1) & 1) == 0 || h1) && ((((i & 1) ^ b) == 0) || w1);
+          if (!ex) continue;
           float f[8], o[8];
-          unpack8(raw[q], f);
+          unpack8(X[i], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(cB[j], f[j], cA[j]) + ((win_ok && amax[j] == q) ? dzs[j] : 0.f);
-          *reinterpret_cast<uint4*>(stage + off[q]) = pack8(o);
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(cB[j], f[j], cA[j]);
+          *reinterpret_cast<uint4*>(base + (uint32_t)(i >> 1) * seg_bytes + eoff[i & 1]) = pack8(o);
+        }
+        // arg-max voxel of each channel: + scale*dz  (2-byte patch, program order after the dense store)
+        if (win_ok) {
+          float go[8];
+          unpack8(gov, go);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = j >> 1, sft = (j & 1) * 16;
+            const uint32_t a = (idx[c] >> sft) & 7u;
+            const uint32_t ybits = ((mx[c] ^ kxor[c]) >> sft) & 0xFFFFu;
+            const float ybest = __uint_as_float(ybits << 16);
+            const float z = fmaf(ybest, sc[j], sh[j]);
+            const float dz = z > 0.f ? go[j] : go[j] * p.slope;
+            const float o = fmaf(cB[j], ybest, cA[j]) + sc[j] * dz;
+            *reinterpret_cast<__nv_bfloat16*>(base + (a >> 1) * seg_bytes + (a & 1u) * 64u + 2u * j) = __float2bfloat16_rn(o);
+          }
         }
       }
       fence_proxy_async();                               // generic-proxy smem writes -> visible to the tensor core
