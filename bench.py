@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cnn_ad", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="subjects per GPU per step")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the step replayed as CUDA graphs (transmf_ad_b200.train.GraphedTrainStep); "
+                         "eager: the reference's Python loop, one launch at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -224,9 +227,13 @@ def main():
     model = getattr(M, kind)(**kwargs)
     model.load_state_dict(procedural_state(model.state_dict(), seed=0))     # identical replicas on every rank
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0)   # utils/utils.py:38-41 (Adam branch)
+    graph_mode = args.mode == "graph"
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0,   # utils/utils.py:38-41 (Adam branch)
+                           capturable=graph_mode)
     reducer = GradBucketReducer(model.parameters())
     ce_fn = torch.nn.CrossEntropyLoss()
+    ones = torch.ones(B, dtype=torch.int64, device=dev)
+    zeros = torch.zeros(B, dtype=torch.int64, device=dev)
 
     # synthetic batches: a small pool, distinct per rank (seed offsets as in SURVEY.md section 8d)
     npool = 2
@@ -241,14 +248,12 @@ def main():
     def losses(outs, label):
         if len(outs) == 3:                                    # kfold_train_adversarial.py:119-131
             ce = ce_fn(outs[0], label)
-            ones = torch.ones(outs[1].shape[0], dtype=torch.int64, device=dev)
-            zeros = torch.zeros(outs[2].shape[0], dtype=torch.int64, device=dev)
             ad = (ce_fn(outs[1], ones) + ce_fn(outs[2], zeros)) / 2
             return ce, ad, ad + ce
         ce = ce_fn(outs[0], label)                           # kfold_train_single.py:105
         return ce, None, ce
 
-    def train_step(batch, read_losses):
+    def train_step(batch, read_losses):                      # the reference's eager loop
         mri, pet, label = batch
         opt.zero_grad()
         outs = model(mri) if towers == 1 else model(mri, pet)
@@ -280,28 +285,76 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    def inputs_of(batch):
+        return batch[:1] if towers == 1 else batch[:2]
+
+    graphed = None
+    if graph_mode:
+        from transmf_ad_b200.train import DevicePrefetcher, GraphedTrainStep
+
+        def graph_loss(outs, label):                         # (total, ce, ad): total.backward() is captured
+            ce, ad, total = losses(outs, label)
+            return (total, ce) if ad is None else (total, ce, ad)
+
+        for i in range(args.warmup):                         # eager warm-up (lazy inits, allocator, attribute calls)
+            train_step(pool_d[i % npool], False)
+        barrier()
+        graphed = GraphedTrainStep(model, opt, graph_loss, inputs_of(pool_d[0]), pool_d[0][2], reducer=reducer,
+                                   warmup=args.warmup)
+
+        def dev_step(i):
+            b = pool_d[i % npool]
+            graphed(inputs_of(b), b[2])
+    else:
+        def dev_step(i):
+            train_step(pool_d[i % npool], False)
+
     # ---- warm-up, then the device-resident timed region ---------------------------------------------------------
     for i in range(args.warmup):
-        train_step(pool_d[i % npool], False)
+        dev_step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
-    total_ms = timed(lambda i: train_step(pool_d[i % npool], False), args.steps)
-    launches = _lib.launch_count() - n0
+    total_ms = timed(dev_step, args.steps)
+    launches = (graphed.launches_per_step * args.steps) if graph_mode else (_lib.launch_count() - n0)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- end-to-end: pinned host buffers, H2D inside the timed region, loss .item() reads ----------------------------
-    def e2e_step(i):
-        hb = pool_h[i % npool]
-        db = tuple(t.to(dev, non_blocking=True) for t in hb)
-        train_step(db, True)
+    if graph_mode:
+        # batch i+1 is copied from pinned host memory on a side stream while step i runs (DevicePrefetcher); every
+        # step's inputs cross PCIe inside the timed region and both loss values are read back each step.
+        def e2e_run(steps):
+            def host_batches():
+                for i in range(steps):
+                    hb = pool_h[i % npool]
+                    yield (hb[0], hb[2]) if towers == 1 else hb
+            for db in DevicePrefetcher(host_batches(), dev):
+                out = graphed(db[:-1], db[-1])
+                _ = (out[1].item(), out[2].item() if len(out) > 2 else 0.0)
 
-    for i in range(2):
-        e2e_step(i)
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
+        e2e_run(2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(args.steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(ms) / args.steps
+    else:
+        def e2e_step(i):
+            hb = pool_h[i % npool]
+            db = tuple(t.to(dev, non_blocking=True) for t in hb)
+            train_step(db, True)
+
+        for i in range(2):
+            e2e_step(i)
+        e2e_ms = timed(e2e_step, args.steps) / args.steps
     h2d = sum(t.numel() * t.element_size() for t in pool_h[0][: (1 if towers == 1 else 2)]) + pool_h[0][2].numel() * 8
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "subjects/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 if towers > 1 else 4}
@@ -342,6 +395,8 @@ def main():
             "config": {"workload": f"{desc}, batch {B}/GPU, volumes 91x109x91 fp32, Adam lr 1e-4",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "conv_impl": os.environ.get("TMF_CONV_IMPL", "auto"),
+                       "mode": ("CUDA-graph replay of the whole step (transmf_ad_b200.train.GraphedTrainStep); e2e adds "
+                                "DevicePrefetcher (H2D of batch i+1 on a side stream)") if graph_mode else "eager launches",
                        "l2": "per-step working set (~0.2 GB/subject of activations) >> 126 MB L2; inputs rotate over a pool"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "breakdown": breakdown,

@@ -91,7 +91,14 @@ def _require_device():
         _device_checked = True
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream (raw C accessors: this sits on the launch path of every kernel)."""
+    if _raw_stream is not None and _cur_device is not None:
+        return C.c_void_p(_raw_stream(_cur_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -100,12 +107,20 @@ def ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+_PA = {1: C.c_void_p * 1, 2: C.c_void_p * 2}
+_NULL_PP = C.cast(None, _pp)
+
+
 def ptrs(ts):
-    """host array of device pointers, one per group; ``None`` -> NULL array."""
+    """host array of device pointers, one per group; ``None`` -> NULL array.  (A ctypes array instance is accepted
+    where the prototype says POINTER(c_void_p); no cast needed.)"""
     if ts is None:
-        return C.cast(None, _pp)
-    arr = (C.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
-    return C.cast(arr, _pp)
+        return _NULL_PP
+    if len(ts) == 2:
+        a, b = ts
+        return _PA[2](0 if a is None else a.data_ptr(), 0 if b is None else b.data_ptr())
+    a = ts[0]
+    return _PA[1](0 if a is None else a.data_ptr())
 
 
 class KernelTimer:

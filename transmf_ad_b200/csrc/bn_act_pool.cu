@@ -391,7 +391,7 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
       !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(sums[g], 0, sizeof(double) * 2 * C, st));
+  TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
   const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
   dim3 grid(pick_grid(total, C / 8, 148 * 4), 1, ng);
   launch_bwd<false>(p, grid, 2 * C * sizeof(float), st);

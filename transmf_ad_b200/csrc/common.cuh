@@ -69,6 +69,21 @@ static inline bool load_group(GroupPtr<T>& g, T* const* host, int ng, bool requi
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Zero one `bytes`-sized buffer per group; adjacent buffers (callers that carve the towers' buffers out of one
+// allocation) are cleared by a single memset node.
+static inline cudaError_t zero_group_buffers(void* const* bufs, int ng, size_t bytes, cudaStream_t st) {
+  int g = 0;
+  while (g < ng) {
+    if (bufs[g] == nullptr) { ++g; continue; }
+    int e = g + 1;
+    while (e < ng && bufs[e] == (char*)bufs[g] + (size_t)(e - g) * bytes) ++e;
+    cudaError_t err = cudaMemsetAsync(bufs[g], 0, bytes * (size_t)(e - g), st);
+    if (err != cudaSuccess) return err;
+    g = e;
+  }
+  return cudaSuccess;
+}
+
 // ---- device helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }

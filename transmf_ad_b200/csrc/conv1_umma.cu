@@ -495,8 +495,8 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
     p.bias[g] = bias ? bias[g] : nullptr;
     p.y[g] = (__nv_bfloat16*)y[g];
     p.stats[g] = stats ? stats[g] : nullptr;
-    if (stats && stats[g]) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
   }
+  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
   const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 512 + 64;
   static bool attr_done = false;
   if (!attr_done) {

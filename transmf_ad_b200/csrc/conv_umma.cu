@@ -432,8 +432,8 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_umma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
-    if (stats && stats[g]) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
   }
+  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

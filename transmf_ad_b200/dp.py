@@ -109,6 +109,33 @@ class GradBucketReducer:
                 torch._foreach_copy_(dst, src)
             b["pending"], b["work"], b["launched"] = len(b["params"]), None, False
 
+    # ---- hook-free form for CUDA-graphed steps (train.GraphedTrainStep) ---------------------------------------
+    def bind_static_grads(self):
+        """After the backward pass has been captured into a CUDA graph the ``.grad`` tensors are static: remember them
+        (graph replays do not run autograd hooks, so the hooks are dropped) and reduce with ``reduce_now()``."""
+        self.remove()
+        for b in self.buckets:
+            self._ensure_flat(b)
+            b["grads"] = [p.grad for p in b["params"]]
+            if any(g is None for g in b["grads"]):
+                raise RuntimeError("bind_static_grads: every parameter must have received a gradient in the captured step")
+
+    def reduce_now(self):
+        """Pack -> all-reduce(AVG) -> unpack for every bucket, on the current stream (world size 1: no-op)."""
+        if self.world == 1:
+            return
+        op = dist.ReduceOp.AVG if self._native_avg else dist.ReduceOp.SUM
+        for b in self.buckets:
+            self._ensure_flat(b)
+            grads = b.get("grads") or [p.grad for p in b["params"]]
+            torch._foreach_copy_(b["views"], grads)
+            dist.all_reduce(b["flat"], op=op, group=self.group)
+            if not self._native_avg:
+                b["flat"].div_(self.world)
+            torch._foreach_copy_(grads, b["views"])
+            self.allreduce_launches += 1
+            b["pending"], b["work"], b["launched"] = len(b["params"]), None, False
+
     def remove(self):
         for h in self._hooks:
             h.remove()

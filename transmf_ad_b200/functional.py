@@ -83,7 +83,8 @@ class SNetFunction(torch.autograd.Function):
             Dl, Hl, Wl = dims
             count = B * Dl * Hl * Wl
             y = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
-            stats = [torch.empty(2 * cout, dtype=torch.float64, device=dev) for _ in range(ng)] if training else None
+            # one allocation for both towers: the library clears adjacent buffers with a single memset node
+            stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0)) if training else None
             w = [P(t, l, 0) for t in range(ng)]
             b = [P(t, l, 1) for t in range(ng)]
             wd = None
@@ -98,7 +99,7 @@ class SNetFunction(torch.autograd.Function):
                 L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs(wf), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
                        B, Dl, Hl, Wl, cin, cout, ks, impl, tag=f"tmf_conv3d_fwd@L{l}")
-            coef = [torch.empty(4 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            coef = list(torch.empty((ng, 4 * cout), dtype=torch.float32, device=dev).unbind(0))
             L.call("tmf_bn_finalize", ng, L.ptrs(stats), L.ptrs([P(t, l, 2) for t in range(ng)]),
                    L.ptrs([P(t, l, 3) for t in range(ng)]), L.ptrs([buffers[t][l][0] for t in range(ng)]),
                    L.ptrs([buffers[t][l][1] for t in range(ng)]), L.ptrs([buffers[t][l][2] for t in range(ng)]),
@@ -139,13 +140,13 @@ class SNetFunction(torch.autograd.Function):
             cin, cout, ks, pool = spec.layers[l]
             act, y, coef, wd, (Dl, Hl, Wl) = saved[l]
             count = B * Dl * Hl * Wl
-            sums = [torch.empty(2 * cout, dtype=torch.float64, device=dev) for _ in range(ng)]
+            sums = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0))
             L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
                    B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
             dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
-            bcoef = [torch.empty(2 * cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            bcoef = list(torch.empty((ng, 2 * cout), dtype=torch.float32, device=dev).unbind(0))
             L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(dgamma), L.ptrs(dbeta),
                    L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
             dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]

@@ -1,0 +1,155 @@
+"""CUDA-graphed train step and host->device prefetch for the TransMF_AD hot path.
+
+The reference's train step (kfold_train_adversarial.py:101-136 / kfold_train_single.py:95-112) is
+
+    optimizer.zero_grad(); outs = net_model(mri, pet); loss = criterion(...); loss.backward(); optimizer.step()
+
+i.e. ~500 kernel launches of a few microseconds each from Python.  On a B200 the kernels of one step take about as
+long as the host needs to enqueue them, so the eager loop is launch-bound.  ``GraphedTrainStep`` captures the same
+sequence -- the unchanged ``nn.Module`` forward, the caller's loss function, autograd backward and the optimizer
+step -- once into CUDA graphs with static input buffers and replays them; nothing in the model code changes, and the
+eager path stays available (it is what the parity tests drive).
+
+``DevicePrefetcher`` is the matching input side: batch i+1 is copied from pinned host memory on a side stream while
+batch i computes (the reference loads synchronously with ``num_workers=0``, datasets/ADNI.py).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def _as_tuple(x):
+    return x if isinstance(x, (tuple, list)) else (x,)
+
+
+class GraphedTrainStep:
+    """One train step as CUDA graph replays.
+
+    ``loss_fn(outputs, *targets) -> (total_loss, *extras)`` must be made of capturable torch ops (no host syncs);
+    ``total_loss.backward()`` is captured with the forward.  ``inputs`` / ``targets`` passed to ``__call__`` are
+    copied device-to-device into the static buffers (tens of microseconds at HBM speed) and must keep the shapes and
+    dtypes of the examples.  Returns the static ``(total_loss, *extras)`` tensors of the captured step: read them
+    (``.item()``) before the next call.
+
+    world size 1 : zero_grad + forward + loss + backward + optimizer.step in ONE graph.
+    world size N : graph A = zero_grad + forward + loss + backward; then the bucketed NCCL all-reduce of ``reducer``
+                   on the (static) gradient tensors, eagerly; then graph B = optimizer.step.
+
+    The optimizer must be graph-capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).
+    """
+
+    def __init__(self, model, optimizer, loss_fn, example_inputs, example_targets, reducer=None, warmup=3):
+        self.model, self.optimizer, self.loss_fn, self.reducer = model, optimizer, loss_fn, reducer
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1 and reducer is None:
+            raise ValueError("world size > 1 needs a GradBucketReducer")
+        if reducer is not None:
+            reducer.remove()                               # graph replays do not run autograd hooks: reduce_now() instead
+        self.launches_per_step = 0                         # libtmf kernel launches captured per step
+        self.static_inputs = [t.clone() for t in _as_tuple(example_inputs)]
+        self.static_targets = [t.clone() for t in _as_tuple(example_targets)]
+        self.graph_fb, self.graph_opt = torch.cuda.CUDAGraph(), None
+        self.outputs, self.losses = None, None
+        self._capture(warmup)
+
+    # ---- the step, in eager form (used for warm-up and as the thing that is captured) ---------------------------
+    def _fwd_bwd(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        outs = self.model(*self.static_inputs)
+        losses = _as_tuple(self.loss_fn(_as_tuple(outs), *self.static_targets))
+        losses[0].backward()
+        return outs, losses
+
+    def _reduce(self):
+        if self.world > 1:
+            self.reducer.reduce_now()
+
+    def _capture(self, warmup):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                      # warm-up on a side stream (allocator + lazy inits + autotune)
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+                self._reduce()
+                self.optimizer.step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        n0 = _lib.launch_count()
+        if self.world == 1:
+            with torch.cuda.graph(self.graph_fb):
+                self.outputs, self.losses = self._fwd_bwd()
+                self.optimizer.step()
+        else:
+            with torch.cuda.graph(self.graph_fb):
+                self.outputs, self.losses = self._fwd_bwd()
+            self.reducer.bind_static_grads()               # the captured backward's .grad tensors are static from here on
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+                self.optimizer.step()
+        self.launches_per_step = _lib.launch_count() - n0
+        torch.cuda.synchronize()
+
+    def __call__(self, inputs, targets):
+        for dst, src in zip(self.static_inputs, _as_tuple(inputs)):
+            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(self.static_targets, _as_tuple(targets)):
+            dst.copy_(src, non_blocking=True)
+        self.graph_fb.replay()
+        if self.world > 1:
+            self.reducer.reduce_now()
+            self.graph_opt.replay()
+        return self.losses
+
+
+class DevicePrefetcher:
+    """Iterates over host batches (tuples of pinned CPU tensors) and yields device batches; the copy of batch i+1 runs
+    on a side stream while the caller works on batch i.  Two device buffer sets are recycled: a yielded batch stays
+    valid until the next ``next()`` call has returned, and everything that reads it must have been enqueued on the
+    current stream by then (single-threaded use)."""
+
+    def __init__(self, host_batches, device):
+        self.it = iter(host_batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self._last = None
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            hb = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        k = self.k
+        self.k ^= 1
+        with torch.cuda.stream(self.stream):
+            if self.slots[k] is None:
+                self.slots[k] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in hb)
+            self.stream.wait_event(self.consumed[k])        # no-op until the slot has been handed out once
+            for d, h in zip(self.slots[k], hb):
+                d.copy_(h, non_blocking=True)
+            ready = self.stream.record_event()
+        self._next = (k, ready)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self._last is not None:                          # all readers of the previous batch are enqueued by now
+            self.consumed[self._last].record(cur)
+        if self._next is None:
+            raise StopIteration
+        k, ready = self._next
+        cur.wait_event(ready)
+        self._last = k
+        batch = self.slots[k]
+        self._preload()                                     # batch i+1: H2D overlaps with the caller's work on batch i
+        return batch
