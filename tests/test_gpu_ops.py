@@ -65,7 +65,10 @@ def test_conv1_fwd_and_stats(impl, shape, cout):
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("shape,cin,cout,ks", [
     ((2, 9, 11, 10), 32, 32, 3), ((1, 12, 13, 11), 32, 64, 3), ((2, 6, 7, 5), 64, 128, 3), ((1, 5, 6, 5), 128, 256, 3),
-    ((2, 5, 6, 5), 256, 128, 1), ((1, 22, 27, 22), 64, 64, 3), ((1, 8, 8, 8), 16, 16, 3)])
+    ((2, 5, 6, 5), 256, 128, 1), ((1, 22, 27, 22), 64, 64, 3), ((1, 8, 8, 8), 16, 16, 3),
+    # block-2 sized planes: several columns per plane, CTA ranges that roll along d and cross column boundaries
+    ((1, 45, 54, 45), 32, 32, 3), ((2, 21, 54, 45), 32, 64, 3), ((1, 3, 40, 128), 64, 64, 3), ((3, 1, 9, 7), 32, 32, 3),
+    ((2, 22, 27, 22), 64, 128, 3), ((1, 5, 9, 200), 32, 96, 3)])
 def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
     B, D, H, W = shape
     lib = L.load()
@@ -108,18 +111,19 @@ def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
     assert rel_l2(dw.cpu(), w_ref.grad) < 2e-3, "wgrad"
 
 
-def test_conv_grouped_towers_match_single_launches():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_conv_grouped_towers_match_single_launches(impl):
     B, D, H, W, cin, cout = 1, 7, 8, 9, 32, 32
     outs = []
     a = [to_ndhwc_bf16(g_randn(B, cin, D, H, W, seed=s)) for s in (1, 2)]
     w = [g_randn(27, cout, cin, seed=s, scale=0.05).to(torch.bfloat16).to(DEV) for s in (3, 4)]
     y2 = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV) for _ in range(2)]
     L.call("tmf_conv3d_fwd", 2, L.ptrs(a), L.ptrs(w), L.ptrs(None), L.ptrs(y2), L.ptrs(None), B, D, H, W, cin, cout, 3,
-           L.CONV_DIRECT)
+           impl)
     for t in range(2):
         y1 = torch.empty_like(y2[t])
         L.call("tmf_conv3d_fwd", 1, L.ptrs([a[t]]), L.ptrs([w[t]]), L.ptrs(None), L.ptrs([y1]), L.ptrs(None), B, D, H, W,
-               cin, cout, 3, L.CONV_DIRECT)
+               cin, cout, 3, impl)
         assert torch.equal(y1, y2[t])
 
 

@@ -467,6 +467,11 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
                         int ksize, void* stream);
 bool tmf_conv3d_fwd_umma_supported(int D, int H, int W, int cin, int cout, int ksize);
+// conv_umma_col.cu: input-stationary rolling-plane, kw-stacked variant (Cin in {32, 64}, Cout a multiple of 32)
+int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, const float* const* bias,
+                       void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize,
+                       void* stream);
+bool tmf_conv3d_fwd_col_supported(int ng, int D, int H, int W, int cin, int cout, int ksize);
 int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H,
                           int W, int cin, int cout, int ksize, void* ws, size_t ws_bytes, void* stream);
 size_t tmf_conv3d_wgrad_umma_workspace(int ng, int B, int D, int H, int W, int cin, int cout, int ksize);
@@ -573,6 +578,8 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
     TMF_REQUIRE(tmf_conv3d_fwd_umma_supported(D, H, W, cin, cout, ksize),
                 "conv3d_fwd: tcgen05 path does not support D,H,W=%d,%d,%d Cin=%d Cout=%d k=%d", D, H, W, cin, cout,
                 ksize);
+    if (tmf_conv3d_fwd_col_supported(ng, D, H, W, cin, cout, ksize))
+      return tmf_conv3d_fwd_col(ng, a, wf, bias, y, stats, B, D, H, W, cin, cout, ksize, stream);
     return tmf_conv3d_fwd_umma(ng, a, wf, bias, y, stats, B, D, H, W, cin, cout, ksize, stream);
   }
   ConvDirectArgs p;

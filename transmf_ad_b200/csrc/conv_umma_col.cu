@@ -1,0 +1,525 @@
+// conv_umma_col.cu -- second-generation implicit-GEMM Conv3d 3x3x3 (pad 1) forward / dgrad for the layers with
+// Cin in {32, 64} and Cout a multiple of 32 (<= 128): blocks 2 and 3 of sNet (reference models/networks.py:28-41) and
+// their input gradients.  Everything below was sized from measurements on B200 (scripts/ubench/*.cu, TMF_COL_DEBUG):
+//
+//   * ISSUE-BOUND MMAs.  A 128 x N x 16 tcgen05.mma with small N is not limited by the tensor pipe but by the thread
+//     that issues it (~100 cycles of descriptor moves per instruction) and by shared-memory operand reads (the A tile
+//     costs the same bytes whatever N is).  Two remedies:
+//       - kw-STACKING IN N.  The three kw taps of one (kd, kh) are neighbouring blocks of wf[tap][Cout][Cin], i.e. ONE
+//         K-major B operand with N = 96 rows (3 taps x 32 output channels).  One MMA per (kd, kh, k-step), with the A
+//         window shifted by kh rows only, fills three column blocks D_kw[r] = sum X[r + kh*Wp] W[kd,kh,kw]; the
+//         convolution is y[r] = D_0[r] + D_1[r+1] + D_2[r+2], a two-lane shift done in the epilogue with warp shuffles
+//         (rows 32q+32, 32q+33 come from the next TMEM lane quarter through shared memory).  An M tile of 128 rows
+//         therefore yields 126 outputs.  3x fewer MMAs.
+//       - THREE ISSUER WARPS, one elected thread each running its whole role (no per-tap elect/reconverge).
+//   * INPUT-STATIONARY ROLLING PLANES.  A CTA walks a column (sample, 126 positions) along d.  An input plane slab is
+//     used the moment it lands: it adds tap plane kd=2 to output d-1 (completing it), kd=1 to output d, kd=0 to output
+//     d+1, and its shared-memory slot is released at once -- every slot of the ring is prefetch depth, the three open
+//     outputs live in TMEM (4 accumulator buffers x 96 columns).  Output io belongs to issuer io % 3: a plane feeds
+//     exactly one output per issuer, and an output's 27 taps are issued by one thread, in order.
+//   * TMA: one thread keeps only ~2 tensor loads in flight (~600 cycles per box whatever its size, more from DRAM), so
+//     four lanes of the producer warp issue the plane loads round-robin; weights (27 taps x 32 channels) are resident.
+//   * Cout > 32 is split into 32-channel slices handled by different CTAs ("virtual groups"): the slice's weights
+//     (55-110 KB) stay resident, the input is re-read from L2.
+//   * Padded row pitch W+1 (the right halo of row h is the left halo of row h+1: one zero column, TMA OOB fill).
+//   * mbarrier parity waits are only sound for a thread that has observed every earlier phase of that barrier, so every
+//     issuer waits on every accumulator hand-over and every TMA lane on every slot hand-over, owner or not.
+//   * Epilogue: 2 groups x 4 warps alternate outputs; BatchNorm statistics accumulate per thread in registers over the
+//     CTA's whole range; 256-bit stores (whole sectors per thread).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace tmf {
+using namespace umma;
+
+constexpr int CC_TMA_LANES = 4;
+constexpr int CC_MMA_WARPS = 3;
+constexpr int CC_FIRST_EPI = 1 + CC_MMA_WARPS;
+constexpr int CC_EPI_WARPS = 8;
+constexpr int CC_THREADS = 32 * (CC_FIRST_EPI + CC_EPI_WARPS);
+constexpr int CC_TILE_OUT = 126;                // outputs per 128-row M tile (2 rows feed the kw shift)
+constexpr int CC_MAX_SLOTS = 10;
+constexpr int CC_CO = 32;                       // output channels per CTA (slice of Cout)
+constexpr int CC_NSTACK = 3 * CC_CO;            // MMA N
+constexpr int CC_NBUF = 4;                      // accumulator buffers
+constexpr int CC_MAX_VG = 8;                    // towers x Cout slices
+constexpr uint32_t CC_SMEM_BUDGET = 227 * 1024;
+constexpr uint32_t CC_XCHG_BYTES = 2 * 2 * 4 * 3 * 32 * 4;   // [parity][group][quarter][D1_0, D2_0, D2_1][32 ch] floats
+constexpr uint32_t CC_FIXED_SMEM = 1024 /*align*/ + 8 * (2 * CC_MAX_SLOTS) + 8 + 8 * 2 * CC_NBUF + 24 + CC_XCHG_BYTES + 256 /*stats*/ +
+                                   128 /*bias*/ + 64;
+
+struct alignas(64) ColConvParams {
+  CUtensorMap tmA[TMF_MAX_GROUPS];
+  CUtensorMap tmB[TMF_MAX_GROUPS];
+  const float* bias[TMF_MAX_GROUPS];
+  __nv_bfloat16* y[TMF_MAX_GROUPS];
+  double* stats[TMF_MAX_GROUPS];
+  int ng, nsplit, cout, B, D, H, W;
+  int Wp, NH, NC, S;              // padded pitch (W+1), slab rows (in h), columns per plane, ring slots
+  int qneed;                      // positions of a plane that hold outputs: (H-1)*Wp + W
+  int steps_per_group;            // B * NC * D
+  uint32_t layout, slot_bytes, a_tx_bytes, b_bytes, idesc;
+  int debug;                      // bring-up switches (TMF_COL_DEBUG): 1 no shift, 2 no stores/stats, 8 no MMAs, 32 role timing
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// bring-up instrumentation (debug & 32): cycles a role spends blocked on one kind of barrier
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+// KSTEPS = Cin / 16 (2 or 4)
+template <int KSTEPS>
+__global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __grid_constant__ ColConvParams p) {
+  constexpr uint32_t PITCH = KSTEPS * 32u;          // bytes per smem row (= Cin * 2)
+  constexpr uint32_t ROW_UNITS = PITCH >> 4;
+  constexpr uint32_t SBO = 8u * PITCH;
+  constexpr uint32_t TAP_UNITS = (uint32_t)CC_CO * ROW_UNITS;   // one tap of the slice's weights, in 16-byte units
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smB = smem_base;
+  const uint32_t smA = smB + ((p.b_bytes + 1023u) & ~1023u);
+  const uint32_t bars = smA + (uint32_t)p.S * p.slot_bytes;
+  const uint32_t a_full = bars, a_empty = a_full + 8 * CC_MAX_SLOTS;
+  const uint32_t b_full = a_empty + 8 * CC_MAX_SLOTS;
+  const uint32_t acc_full = b_full + 8, acc_empty = acc_full + 8 * CC_NBUF;
+  const uint32_t tmem_slot = acc_empty + 8 * CC_NBUF;
+  const uint32_t xchg_sm = tmem_slot + 24;                               // 16-byte aligned (bars is 1024-aligned)
+  const uint32_t stats_sm = xchg_sm + CC_XCHG_BYTES;                     // float [2][32]
+  const uint32_t bias_sm = stats_sm + 256;                               // float [32]
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  float* xchg_ptr = reinterpret_cast<float*>(gen_base + (xchg_sm - smem_base));
+  float* stats_ptr = reinterpret_cast<float*>(gen_base + (stats_sm - smem_base));
+  float* bias_ptr = reinterpret_cast<float*>(gen_base + (bias_sm - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool prof = (p.debug & 32) != 0;
+  const int ngv = p.ng * p.nsplit;
+  const int gv = blockIdx.x % ngv;                  // virtual group = (tower, Cout slice)
+  const int g = gv / p.nsplit;
+  const int co_off = (gv % p.nsplit) * CC_CO;
+  const int cta = blockIdx.x / ngv, ncta = gridDim.x / ngv;
+  const int s_begin = (int)(((int64_t)cta * p.steps_per_group) / ncta);
+  const int s_end = (int)(((int64_t)(cta + 1) * p.steps_per_group) / ncta);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.S; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, CC_MMA_WARPS); }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < CC_NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, CC_EPI_WARPS / 2); }
+    fence_barrier_init();
+    prefetch_tmap(&p.tmA[g]);
+    prefetch_tmap(&p.tmB[g]);
+  }
+  if (threadIdx.x < 64) stats_ptr[threadIdx.x] = 0.f;
+  if (threadIdx.x < CC_CO) bias_ptr[threadIdx.x] = (p.bias[g] != nullptr) ? p.bias[g][co_off + threadIdx.x] : 0.f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================================== TMA producer ===========================================
+    if (lane < CC_TMA_LANES && s_begin < s_end) {
+      if (lane == 0) {
+        mbar_expect_tx(b_full, p.b_bytes);
+        tma_load_3d(smB, &p.tmB[g], b_full, 0, co_off, 0);             // all 27 taps of this Cout slice at once
+      }
+      int slot = 0, jw = 0;
+      uint32_t ph = 0;
+      long long t_wait = 0;
+      const long long t_start = clock64();
+      for (int s = s_begin; s < s_end;) {
+        const int d = s % p.D, col = s / p.D;
+        const int c = col % p.NC, n = col / p.NC;
+        const int len = min(p.D - d, s_end - s);
+        const int pa = max(d - 1, 0), pb = min(d + len, p.D - 1);
+        const int h0 = (c * CC_TILE_OUT) / p.Wp;
+        for (int pl = pa; pl <= pb; ++pl, ++jw) {
+          mbar_wait_t(a_empty + 8 * slot, ph ^ 1u, t_wait, prof);      // every lane sees every phase (see header)
+          if ((jw % CC_TMA_LANES) == lane) {
+            mbar_expect_tx(a_full + 8 * slot, p.a_tx_bytes);
+            tma_load_5d(smA + (uint32_t)slot * p.slot_bytes, &p.tmA[g], a_full + 8 * slot, 0, -1, h0 - 1, pl, n);
+          }
+          if (++slot == p.S) { slot = 0; ph ^= 1u; }
+        }
+        s += len;
+      }
+      if (prof && blockIdx.x == 0 && lane == 0)
+        printf("col prof: producer lane 0: total %lld cyc, waiting for a free slot %lld\n", clock64() - t_start, t_wait);
+    }
+  } else if (warp < CC_FIRST_EPI) {
+    // =========================================== MMA issuers ============================================
+    const int issuer = warp - 1;
+    if (s_begin < s_end && elect_one()) {
+      const uint64_t desc_hi = make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo_const = (uint32_t)(make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFF0000ull);
+      const uint32_t a0_lo = desc_lo_const | ((smA & 0x3FFFFu) >> 4);
+      const uint32_t b0_lo = desc_lo_const | ((smB & 0x3FFFFu) >> 4);
+      const uint32_t slot_units = p.slot_bytes >> 4;
+      const uint32_t wp_units = (uint32_t)p.Wp * ROW_UNITS;
+      const uint32_t idesc = p.idesc;
+      const bool no_mma = (p.debug & 8) != 0;
+      int it = 0;                        // outputs finished by earlier segments
+      int slot = 0;
+      uint32_t ph = 0;
+      long long t_full = 0, t_acc = 0;
+      const long long t_start = clock64();
+      mbar_wait(b_full, 0u);
+      tc_fence_after();
+      for (int s = s_begin; s < s_end;) {
+        const int d0 = s % p.D, col = s / p.D;
+        const int c = col % p.NC;
+        const int len = min(p.D - d0, s_end - s);
+        const int da = d0, db = d0 + len - 1;
+        const int pa = max(da - 1, 0), pb = min(db + 1, p.D - 1);
+        const uint32_t qoff_units = (uint32_t)((c * CC_TILE_OUT) % p.Wp) * ROW_UNITS;
+        for (int pl = pa; pl <= pb; ++pl) {
+          mbar_wait_t(a_full + 8 * slot, ph, t_full, prof);
+          tc_fence_after();
+          const uint32_t a_slab = a0_lo + (uint32_t)slot * slot_units + qoff_units;
+#pragma unroll
+          for (int kd = 2; kd >= 0; --kd) {          // output o = pl + 1 - kd: the one this plane completes goes first
+            const int o = pl + 1 - kd;
+            if (o < da || o > db) continue;
+            const int io = it + (o - da);            // index of output o in this CTA's sequence
+            const int as = io & (CC_NBUF - 1);
+            const bool first = (pl == max(o - 1, 0));
+            if (first) {                             // every issuer, owner or not (parity soundness)
+              mbar_wait_t(acc_empty + 8 * as, ((uint32_t)(io / CC_NBUF) & 1u) ^ 1u, t_acc, prof);
+              tc_fence_after();
+            }
+            if ((io % CC_MMA_WARPS) != issuer) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * CC_NSTACK);
+            if (!no_mma) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint32_t b_lo = b0_lo + (uint32_t)((kd * 3 + kh) * 3) * TAP_UNITS;
+                const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                              (!first || kh != 0 || k != 0) ? 1u : 0u);
+              }
+            }
+            if (pl == min(o + 1, p.D - 1)) mma_commit(acc_full + 8 * as);   // last contribution: output o is complete
+          }
+          mma_commit(a_empty + 8 * slot);            // (count 3: the slot is free once every issuer is done with it)
+          if (++slot == p.S) { slot = 0; ph ^= 1u; }
+        }
+        it += len;
+        s += len;
+      }
+      if (prof && blockIdx.x == 0)
+        printf("col prof: issuer %d: total %lld cyc, waiting for input planes %lld, for a free accumulator %lld (%d outputs)\n",
+               issuer, clock64() - t_start, t_full, t_acc, s_end - s_begin);
+    }
+  } else {
+    // =========================================== epilogue ================================================
+    // Two groups of 4 warps (one per TMEM lane quarter); outputs alternate between the groups, so two accumulators are
+    // drained concurrently.  A thread owns one output row and all 32 channels of the slice, processed 16 at a time.
+    const int ew = warp - CC_FIRST_EPI;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int eg = ew >> 2;                       // epilogue group
+    const int row = quarter * 32 + lane;
+    __nv_bfloat16* yg = p.y[g];
+    const bool want_stats = p.stats[g] != nullptr;
+    const bool no_shift = (p.debug & 1) != 0, no_store = (p.debug & 2) != 0;
+    float acc_s[CC_CO], acc_q[CC_CO];
+#pragma unroll
+    for (int j = 0; j < CC_CO; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_ptr);
+    long long t_epi = 0;
+    const long long t_epi0 = clock64();
+    uint32_t xb = 0;                              // exchange buffer parity
+    int it = eg;
+    for (int s = s_begin + eg; s < s_end; s += 2, it += 2) {
+      const int d = s % p.D, col = s / p.D;
+      const int c = col % p.NC, n = col / p.NC;
+      const int as = it & (CC_NBUF - 1);
+      mbar_wait_t(acc_full + 8 * as, (uint32_t)(it / CC_NBUF) & 1u, t_epi, prof);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * CC_NSTACK);
+      // ---- phase A: publish the rows the previous lane quarter needs (D1 of row 0; D2 of rows 0 and 1)
+      float4* xw = reinterpret_cast<float4*>(xchg_ptr + (((xb * 2 + eg) * 4 + quarter) * 3) * 32);
+      const float4* xr = reinterpret_cast<const float4*>(xchg_ptr + (((xb * 2 + eg) * 4 + ((quarter + 1) & 3)) * 3) * 32);
+      xb ^= 1u;
+      if (!no_shift) {
+        uint32_t b1[32], b2[32];
+        tmem_ld32(taddr + CC_CO, b1);
+        tmem_ld32(taddr + 2 * CC_CO, b2);
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xw[j] = make_float4(__uint_as_float(b1[4 * j]), __uint_as_float(b1[4 * j + 1]), __uint_as_float(b1[4 * j + 2]),
+                                __uint_as_float(b1[4 * j + 3]));
+            xw[8 + j] = make_float4(__uint_as_float(b2[4 * j]), __uint_as_float(b2[4 * j + 1]), __uint_as_float(b2[4 * j + 2]),
+                                    __uint_as_float(b2[4 * j + 3]));
+          }
+        } else if (lane == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            xw[16 + j] = make_float4(__uint_as_float(b2[4 * j]), __uint_as_float(b2[4 * j + 1]), __uint_as_float(b2[4 * j + 2]),
+                                     __uint_as_float(b2[4 * j + 3]));
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+      }
+      // ---- phase B: 16 channels at a time
+      const int q = c * CC_TILE_OUT + row;
+      const int h = q / p.Wp, w = q - h * p.Wp;
+      const bool valid = (row < CC_TILE_OUT) && (h < p.H) && (w < p.W) && !no_store;
+      __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout + co_off;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r0[16], r1[16], r2[16];
+        tmem_ld16(taddr + hf * 16, r0);
+        tmem_ld16(taddr + CC_CO + hf * 16, r1);
+        tmem_ld16(taddr + 2 * CC_CO + hf * 16, r2);
+        tmem_ld_wait();
+        if (hf == 1) {                               // last TMEM read of this accumulator buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+        }
+        float v[16];
+        if (no_shift) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) + __uint_as_float(r2[j]);
+        } else {
+          // T[r] = D1[r] + D2[r+1];  y[r] = D0[r] + T[r+1]
+          float tt[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            tt[j] = __uint_as_float(r1[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
+          if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 n2 = xr[8 + hf * 4 + j];           // D2 of the next quarter's row 0
+              tt[4 * j] = __uint_as_float(r1[4 * j]) + n2.x;
+              tt[4 * j + 1] = __uint_as_float(r1[4 * j + 1]) + n2.y;
+              tt[4 * j + 2] = __uint_as_float(r1[4 * j + 2]) + n2.z;
+              tt[4 * j + 3] = __uint_as_float(r1[4 * j + 3]) + n2.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __shfl_down_sync(0xffffffffu, tt[j], 1);
+          if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 n1 = xr[hf * 4 + j];               // D1 of the next quarter's row 0
+              const float4 n2 = xr[16 + hf * 4 + j];          // D2 of the next quarter's row 1
+              v[4 * j] = __uint_as_float(r0[4 * j]) + (n1.x + n2.x);
+              v[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + (n1.y + n2.y);
+              v[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + (n1.z + n2.z);
+              v[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + (n1.w + n2.w);
+            }
+          }
+        }
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = bias4[hf * 4 + j];                 // shared-memory broadcast
+            pk[2 * j] = pack_bf16(v[4 * j] + b4.x, v[4 * j + 1] + b4.y);
+            pk[2 * j + 1] = pack_bf16(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float f0 = bf16_lo(pk[j]), f1 = bf16_hi(pk[j]);
+            acc_s[hf * 16 + 2 * j] += f0;
+            acc_q[hf * 16 + 2 * j] = fmaf(f0, f0, acc_q[hf * 16 + 2 * j]);
+            acc_s[hf * 16 + 2 * j + 1] += f1;
+            acc_q[hf * 16 + 2 * j + 1] = fmaf(f1, f1, acc_q[hf * 16 + 2 * j + 1]);
+          }
+          // one 256-bit store: a thread writes whole 32-byte sectors
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + hf * 16), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        }
+      }
+    }
+    if (prof && blockIdx.x == 0 && ew == 0 && lane == 0)
+      printf("col prof: epilogue warp 0: total %lld cyc, waiting for a finished accumulator %lld\n", clock64() - t_epi0, t_epi);
+    if (want_stats) {
+#pragma unroll
+      for (int j = 0; j < CC_CO; ++j) {
+        const float ssum = warp_sum(acc_s[j]);
+        const float qsum = warp_sum(acc_q[j]);
+        if (lane == 0) {
+          atomicAdd(&stats_ptr[j], ssum);
+          atomicAdd(&stats_ptr[32 + j], qsum);
+        }
+      }
+      asm volatile("bar.sync 3, %0;" ::"r"(32 * CC_EPI_WARPS) : "memory");
+      const int i = threadIdx.x - 32 * CC_FIRST_EPI;
+      if (i < CC_CO) {
+        atomicAdd(&p.stats[g][co_off + i], (double)stats_ptr[i]);
+        atomicAdd(&p.stats[g][p.cout + co_off + i], (double)stats_ptr[32 + i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn col_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct ColPlan {
+  bool ok;
+  int Wp, NH, NC, S, nsplit, qneed;
+  uint32_t slot_bytes, a_tx, b_bytes, smem_bytes, layout;
+  CUtensorMapSwizzle swz;
+};
+
+static ColPlan make_col_plan(int ng, int D, int H, int W, int cin, int cout, int ks) {
+  ColPlan pl{};
+  pl.ok = false;
+  if (ks != 3) return pl;
+  if (!(cin == 32 || cin == 64) || cout % CC_CO != 0 || cout < CC_CO) return pl;
+  pl.nsplit = cout / CC_CO;
+  if (ng * pl.nsplit > CC_MAX_VG) return pl;
+  if (D < 1 || H < 1 || W < 2) return pl;
+  const uint32_t pitch = (uint32_t)cin * 2;
+  pl.layout = (cin == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+  pl.swz = (cin == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  pl.Wp = W + 1;
+  if (pl.Wp > 256) return pl;
+  pl.qneed = (H - 1) * pl.Wp + W;
+  pl.b_bytes = 27u * (uint32_t)CC_CO * pitch;
+  const uint32_t wbytes = (pl.b_bytes + 1023u) & ~1023u;
+  const int rmax = (pl.Wp - 1) + 127 + 2 * pl.Wp;
+  pl.NH = rmax / pl.Wp + 1;
+  if (pl.NH > 256) return pl;
+  pl.a_tx = (uint32_t)pl.NH * pl.Wp * pitch;
+  pl.slot_bytes = (pl.a_tx + 1023u) & ~1023u;
+  for (int S = CC_MAX_SLOTS; S >= 2; --S) {
+    const uint32_t total = CC_FIXED_SMEM + wbytes + (uint32_t)S * pl.slot_bytes;
+    if (total <= CC_SMEM_BUDGET) {
+      pl.ok = true; pl.S = S; pl.smem_bytes = total;
+      break;
+    }
+  }
+  if (!pl.ok) return pl;
+  pl.NC = (pl.qneed + CC_TILE_OUT - 1) / CC_TILE_OUT;
+  return pl;
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+bool tmf_conv3d_fwd_col_supported(int ng, int D, int H, int W, int cin, int cout, int ksize) {
+  if (getenv("TMF_DISABLE_UMMA") != nullptr || getenv("TMF_DISABLE_COL") != nullptr) return false;
+  return make_col_plan(ng, D, H, W, cin, cout, ksize).ok;
+}
+
+int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, const float* const* bias, void* const* y,
+                       double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize, void* stream) {
+  TMF_CHECK_NG(ng);
+  const ColPlan pl = make_col_plan(ng, D, H, W, cin, cout, ksize);
+  TMF_REQUIRE(pl.ok, "conv3d_fwd_col: unsupported problem");
+  EncodeTiledFn encode = col_encode_fn();
+  TMF_REQUIRE(encode != nullptr, "conv3d_fwd_col: cuTensorMapEncodeTiled entry point not available");
+  TMF_REQUIRE((int64_t)B * pl.NC * D < (int64_t)1 << 30, "conv3d_fwd_col: problem too large");
+  ColConvParams p{};
+  p.ng = ng; p.nsplit = pl.nsplit; p.cout = cout; p.B = B; p.D = D; p.H = H; p.W = W;
+  p.Wp = pl.Wp; p.NH = pl.NH; p.NC = pl.NC; p.S = pl.S; p.qneed = pl.qneed;
+  p.steps_per_group = B * pl.NC * D;
+  p.layout = pl.layout; p.slot_bytes = pl.slot_bytes; p.a_tx_bytes = pl.a_tx; p.b_bytes = pl.b_bytes;
+  p.idesc = make_idesc_bf16(128, CC_NSTACK, 0, 0);
+  p.debug = getenv("TMF_COL_DEBUG") ? atoi(getenv("TMF_COL_DEBUG")) : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int g = 0; g < ng; ++g) {
+    TMF_REQUIRE(a[g] && wf[g] && y[g], "conv3d_fwd_col: NULL device pointer");
+    TMF_REQUIRE(((uintptr_t)a[g] & 15) == 0 && ((uintptr_t)wf[g] & 15) == 0 && ((uintptr_t)y[g] & 31) == 0,
+                "conv3d_fwd_col: tensors must be 16-byte (output: 32-byte) aligned");
+    p.bias[g] = bias ? bias[g] : nullptr;
+    p.y[g] = (__nv_bfloat16*)y[g];
+    p.stats[g] = stats ? stats[g] : nullptr;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+      cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2,
+                               (cuuint64_t)D * H * W * cin * 2};
+      cuuint32_t box[5] = {(cuuint32_t)cin, (cuuint32_t)pl.Wp, (cuuint32_t)pl.NH, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&p.tmA[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a[g]), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_col: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 27};
+      cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+      cuuint32_t box[3] = {(cuuint32_t)cin, (cuuint32_t)CC_CO, 27};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&p.tmB[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wf[g]), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_col: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+  }
+  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ngv = ng * pl.nsplit;
+  int per_group = sms / ngv;
+  if (per_group > p.steps_per_group) per_group = p.steps_per_group;
+  if (per_group < 1) per_group = 1;
+  dim3 grid(per_group * ngv, 1, 1);
+#define TMF_LAUNCH_COL(KST)                                                                                              \
+  do {                                                                                                                  \
+    static bool attr_done = false;                                                                                      \
+    if (!attr_done) {                                                                                                   \
+      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_col_kernel<KST>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                    (int)CC_SMEM_BUDGET));                                                              \
+      attr_done = true;                                                                                                 \
+    }                                                                                                                   \
+    conv3d_umma_col_kernel<KST><<<grid, CC_THREADS, pl.smem_bytes, st>>>(p);                                            \
+  } while (0)
+  if (cin == 32) TMF_LAUNCH_COL(2);
+  else TMF_LAUNCH_COL(4);
+#undef TMF_LAUNCH_COL
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
