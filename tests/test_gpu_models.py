@@ -2,7 +2,9 @@
 and (b) the CPU oracle with bf16 rounding emulated at the CUDA path's rounding points ("Oracle-A").
 
 Tolerances (the network is ill-conditioned under train-mode BatchNorm with tiny batches):
-  vs Oracle-A : sNet features <= 2e-2 rel-L2, logits <= 3e-2 abs, losses <= 2e-2, whole-model gradient cosine >= min(0.95, cos(A, fp32) - 0.03),
+  vs Oracle-A : sNet features <= 2e-2 rel-L2, logits <= 5e-2 abs (train mode: a different fp32 summation order flips single
+                bf16 ulps of the stored conv outputs, which the BatchNorm1d heads amplify exactly as they amplify Oracle-A's
+                own rounding -- Oracle-A sits up to 5.2e-2 from the fp32 reference; eval-mode logits agree to 1e-3), losses <= 2e-2, whole-model gradient cosine >= min(0.95, cos(A, fp32) - 0.03),
                 per-tensor gradient cosine >= 0.8 (run-to-run atomics + BatchNorm conditioning move single small tensors)
   vs fp32 golden (Oracle-B): logits <= 8e-2 abs, losses <= 4e-2, per-tensor gradient cosine >= min(0.75, cos(A,B) - 0.1),
     eval argmax identical wherever the reference margin exceeds twice the logit tolerance.
@@ -20,7 +22,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 # features: kernel exactness upstream of the BatchNorm1d heads; logits / losses / gradients: end to end
-FEAT_A, LOGIT_A, LOSS_A, LOGIT_B, LOSS_B = 2e-2, 3e-2, 2e-2, 8e-2, 4e-2
+FEAT_A, LOGIT_A, LOSS_A, LOGIT_B, LOSS_B = 2e-2, 5e-2, 2e-2, 8e-2, 4e-2
+EVAL_A = 1e-2                      # eval mode (running statistics): no batch-statistics amplification
 GRAD_COS_A, GRAD_COS_A_GLOBAL, GRAD_COS_B = 0.8, 0.95, 0.75
 
 
@@ -68,8 +71,8 @@ def test_train_step_against_reference_golden_and_oracle_a(name):
         assert e["cos_B"] >= min(GRAD_COS_B, e["cos_A_vs_B"] - 0.1), f"{k}: cos {e['cos_B']:.3f} vs fp32 reference sample"
     for k, v in r["buffers"].items():
         assert v is True or v <= 5e-2, k
-    assert max(r["eval_err_A"]) <= LOGIT_A
-    assert r["eval_argmax_equal_sure"](LOGIT_A)
+    assert max(r["eval_err_A"]) <= EVAL_A
+    assert r["eval_argmax_equal_sure"](EVAL_A)
 
 
 def test_ragged_and_single_sample_eval_batches():

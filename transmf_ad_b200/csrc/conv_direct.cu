@@ -472,6 +472,11 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
                        void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize,
                        void* stream);
 bool tmf_conv3d_fwd_col_supported(int ng, int D, int H, int W, int cin, int cout, int ksize);
+// wgrad_umma_col.cu: rolling-plane weight gradient, 9 taps per MMA (Cin, Cout multiples of 32)
+bool tmf_conv3d_wgrad_col_supported(int ng, int D, int H, int W, int cin, int cout, int ksize);
+size_t tmf_conv3d_wgrad_col_workspace(int ng, int D, int H, int W, int cin, int cout, int ksize);
+int tmf_conv3d_wgrad_col(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H, int W,
+                         int cin, int cout, int ksize, void* ws, size_t ws_bytes, void* stream);
 int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H,
                           int W, int cin, int cout, int ksize, void* ws, size_t ws_bytes, void* stream);
 size_t tmf_conv3d_wgrad_umma_workspace(int ng, int B, int D, int H, int W, int cin, int cout, int ksize);
@@ -602,7 +607,9 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
 int64_t tmf_conv3d_wgrad_workspace_bytes(int ng, int impl, int B, int D, int H, int W, int cin, int cout, int ksize) {
   if (impl == TMF_CONV_DIRECT) return 0;
   if (!tmf_conv3d_wgrad_umma_supported(D, H, W, cin, cout, ksize)) return 0;
-  return (int64_t)tmf_conv3d_wgrad_umma_workspace(ng, B, D, H, W, cin, cout, ksize);
+  const size_t a = tmf_conv3d_wgrad_umma_workspace(ng, B, D, H, W, cin, cout, ksize);
+  const size_t b = tmf_conv3d_wgrad_col_workspace(ng, D, H, W, cin, cout, ksize);
+  return (int64_t)(a > b ? a : b);
 }
 
 int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float* const* dw, int B, int D, int H,
@@ -617,6 +624,8 @@ int tmf_conv3d_wgrad(int ng, const void* const* dy, const void* const* a, float*
     TMF_REQUIRE(tmf_conv3d_wgrad_umma_supported(D, H, W, cin, cout, ksize),
                 "conv3d_wgrad: tcgen05 path does not support D,H,W=%d,%d,%d Cin=%d Cout=%d k=%d", D, H, W, cin, cout,
                 ksize);
+    if (tmf_conv3d_wgrad_col_supported(ng, D, H, W, cin, cout, ksize))
+      return tmf_conv3d_wgrad_col(ng, dy, a, dw, B, D, H, W, cin, cout, ksize, ws, ws_bytes, stream);
     return tmf_conv3d_wgrad_umma(ng, dy, a, dw, B, D, H, W, cin, cout, ksize, ws, ws_bytes, stream);
   }
   WgradDirectArgs p;

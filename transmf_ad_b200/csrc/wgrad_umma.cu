@@ -372,6 +372,19 @@ static int device_sms() {
 
 using namespace tmf;
 
+// fixed-order sum of split-K partials ws[split][tap][ci][co] -> dw (Cout,Cin,k,k,k); shared with wgrad_umma_col.cu
+int tmf_wgrad_reduce(int ng, float* const* ws, float* const* dw, int nsplit, int taps, int cin, int cout, void* stream) {
+  GroupPtr<const float> gws;
+  GroupPtr<float> gdw;
+  for (int g = 0; g < TMF_MAX_GROUPS; ++g) { gws.p[g] = nullptr; gdw.p[g] = nullptr; }
+  for (int g = 0; g < ng; ++g) { gws.p[g] = ws[g]; gdw.p[g] = dw[g]; }
+  const int64_t total = (int64_t)taps * cin * cout;
+  dim3 rgrid(min(ceil_div(total, 256), 148 * 4), 1, ng);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(gws, gdw, nsplit, taps, cin, cout);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
 bool tmf_conv3d_wgrad_umma_supported(int D, int H, int W, int cin, int cout, int ksize) {
   if (getenv("TMF_DISABLE_UMMA") != nullptr || getenv("TMF_DISABLE_UMMA_WGRAD") != nullptr) return false;
   WgradParams p{};
