@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: the step replayed as CUDA graphs (transmf_ad_b200.train.GraphedTrainStep); "
                          "eager: the reference's Python loop, one launch at a time")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: transmf_ad_b200.optim.FusedAdam (one launch); torch: torch.optim.Adam as the reference builds it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -228,8 +230,11 @@ def main():
     model.load_state_dict(procedural_state(model.state_dict(), seed=0))     # identical replicas on every rank
     model = model.to(dev).train()
     graph_mode = args.mode == "graph"
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0,   # utils/utils.py:38-41 (Adam branch)
-                           capturable=graph_mode)
+    if args.optimizer == "fused":                                            # utils/utils.py:38-41 (Adam branch), one launch
+        from transmf_ad_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0, capturable=graph_mode)
     reducer = GradBucketReducer(model.parameters())
     ce_fn = torch.nn.CrossEntropyLoss()
     ones = torch.ones(B, dtype=torch.int64, device=dev)
@@ -395,6 +400,7 @@ def main():
             "config": {"workload": f"{desc}, batch {B}/GPU, volumes 91x109x91 fp32, Adam lr 1e-4",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "conv_impl": os.environ.get("TMF_CONV_IMPL", "auto"),
+                       "optimizer": "FusedAdam (tmf_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam",
                        "mode": ("CUDA-graph replay of the whole step (transmf_ad_b200.train.GraphedTrainStep); e2e adds "
                                 "DevicePrefetcher (H2D of batch i+1 on a side stream)") if graph_mode else "eager launches",
                        "l2": "per-step working set (~0.2 GB/subject of activations) >> 126 MB L2; inputs rotate over a pool"},

@@ -170,6 +170,16 @@ int tmf_token_pool_bwd(const float* dmean, const float* dmax, const int32_t* arg
  * models/gradient_reversal/functional.py:11-16 */
 int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int64_t n, void* stream);
 
+/* ---- optimizer -------------------------------------------------------------------------
+ * Fused multi-tensor Adam with torch.optim.Adam arithmetic (amsgrad off): replaces the per-parameter launches of the
+ * optimizer the reference builds in utils/utils.py:38-41.  `chunks` is a device array of `nchunks` records
+ * {float* p; const float* g; float* m; float* v; int32 n; int32 pad} (tmf_adam_chunk_bytes() each, n <= 2^31-1), one block
+ * per record.  `lr_dev` (1 float) and `step_dev` (1 float, the number of steps taken so far; advanced by the kernel) live
+ * on the device so that CUDA-graph replays see their current values; `ticket_dev` is a zero-initialised uint32 scratch. */
+int tmf_adam_chunk_bytes(void);
+int tmf_adam_step(const void* chunks, int nchunks, const float* lr_dev, float beta1, float beta2, float eps,
+                  float weight_decay, float* step_dev, void* ticket_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

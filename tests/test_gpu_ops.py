@@ -381,3 +381,28 @@ def test_conv1_bwd_fused_matches_two_step_path_and_torch(shape, ng, training):
            B, D, H, W, cout, 0.01, L.ptr(ws), nws)
     for t in range(ng):
         assert torch.equal(dw_again[t], dw_f[t])
+
+
+def test_fused_adam_matches_torch_adam():
+    """transmf_ad_b200.optim.FusedAdam against torch.optim.Adam (the optimizer utils/utils.py:38-41 builds): same
+    parameters after several steps, with weight decay, odd sizes (scalar tail path) and a learning-rate change."""
+    from transmf_ad_b200.optim import FusedAdam
+    shapes = [(64, 32, 3, 3, 3), (32,), (7,), (129, 5), (1,), (20000,)]
+    ref = [torch.nn.Parameter(g_randn(*s, seed=i).to(DEV)) for i, s in enumerate(shapes)]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=0.01)
+    o_ours = FusedAdam(ours, lr=1e-3, weight_decay=0.01)
+    for step in range(5):
+        for i, (a, b) in enumerate(zip(ref, ours)):
+            g = g_randn(*a.shape, seed=100 * step + i).to(DEV)
+            a.grad = g.clone()
+            b.grad = g.clone()
+        if step == 3:
+            for grp in o_ref.param_groups + o_ours.param_groups:
+                grp["lr"] = 3e-4
+        o_ref.step()
+        o_ours.step()
+    for a, b in zip(ref, ours):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
+    st = o_ours.state[ours[0]]
+    assert float(st["step"]) == 5.0 and st["exp_avg"].shape == ours[0].shape

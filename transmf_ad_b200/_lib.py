@@ -43,11 +43,12 @@ SIGNATURES = {
     "tmf_token_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tmf_token_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
+    "tmf_adam_step": [_vp, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp],
 }
 PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
-         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6)}
+         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_adam_chunk_bytes": (_i, [])}
 
 _lib = None
 _device_checked = False

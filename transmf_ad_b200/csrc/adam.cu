@@ -1,0 +1,89 @@
+// adam.cu -- fused multi-tensor Adam step (replaces the ~200 small launches of
+// torch.optim.Adam(capturable=True) that the reference's getOptimizer (utils/utils.py:38-41) issues per step).
+// One launch updates every parameter: the host builds, once, a device table of chunks {p, g, m, v, n}; the step count
+// and the learning rate live on the device (CUDA-graph replays must not bake them in), and the step counter is advanced
+// by the last block to finish.  Arithmetic follows torch.optim.Adam exactly (amsgrad = False, maximize = False):
+//   g' = g + wd * p;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+#include "common.cuh"
+
+namespace tmf {
+
+struct AdamChunk {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int32_t n;
+  int32_t pad;
+};
+static_assert(sizeof(AdamChunk) == 40, "host code packs 40-byte chunk records");
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __restrict__ chunks, const float* __restrict__ lr_dev,
+                                                         float b1, float b2, float eps, float wd, float* step_dev,
+                                                         unsigned* ticket) {
+  const AdamChunk c = chunks[blockIdx.x];
+  const float t = step_dev[0] + 1.f;              // step_dev is only advanced after every block has read it (ticket below)
+  const float lr = lr_dev[0];
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const bool vec = ((((uintptr_t)c.p | (uintptr_t)c.g | (uintptr_t)c.m | (uintptr_t)c.v) & 15) == 0);
+  const int n4 = vec ? (c.n >> 2) : 0;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    float4 p4 = reinterpret_cast<float4*>(c.p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(c.g)[i];
+    float4 m4 = reinterpret_cast<float4*>(c.m)[i];
+    float4 v4 = reinterpret_cast<float4*>(c.v)[i];
+    float* pp = &p4.x; const float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = fmaf(wd, pp[j], gp[j]);
+      mp[j] = fmaf(b1, mp[j], (1.f - b1) * g);
+      vp[j] = fmaf(b2, vp[j], (1.f - b2) * g * g);
+      pp[j] -= step_size * (mp[j] / (sqrtf(vp[j]) * inv_sqrt_bc2 + eps));
+    }
+    reinterpret_cast<float4*>(c.p)[i] = p4;
+    reinterpret_cast<float4*>(c.m)[i] = m4;
+    reinterpret_cast<float4*>(c.v)[i] = v4;
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < c.n; i += 256) {
+    const float g = fmaf(wd, c.p[i], c.g[i]);
+    const float m = fmaf(b1, c.m[i], (1.f - b1) * g);
+    const float v = fmaf(b2, c.v[i], (1.f - b2) * g * g);
+    c.m[i] = m;
+    c.v[i] = v;
+    c.p[i] -= step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(ticket, 1u);
+    if (done == gridDim.x - 1) {
+      step_dev[0] = t;
+      *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+extern "C" {
+
+int tmf_adam_chunk_bytes(void) { return (int)sizeof(AdamChunk); }
+
+int tmf_adam_step(const void* chunks, int nchunks, const float* lr_dev, float beta1, float beta2, float eps,
+                  float weight_decay, float* step_dev, void* ticket_dev, void* stream) {
+  TMF_REQUIRE(chunks != nullptr && lr_dev != nullptr && step_dev != nullptr && ticket_dev != nullptr,
+              "adam_step: NULL device pointer");
+  TMF_REQUIRE(nchunks > 0, "adam_step: empty chunk table");
+  TMF_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_step: bad hyper-parameters");
+  adam_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, lr_dev, beta1, beta2, eps,
+                                                               weight_decay, step_dev, (unsigned*)ticket_dev);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

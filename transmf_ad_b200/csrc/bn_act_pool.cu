@@ -74,6 +74,7 @@ struct ActPoolArgs {
   int B, D, H, W, C, pool, fp32io;
   int Do, Ho, Wo;                     // forward output dims (floor)
   int Dc, Hc, Wc;                     // ceil dims (windows that touch any input voxel)
+  int nch, hcr, nch_c, hcr_c;         // row chunks per output plane / rows per chunk (floor dims; ceil dims)
   float slope;
 };
 
@@ -96,23 +97,29 @@ __device__ __forceinline__ void store8f(void* base, int64_t elem_off, int fp32, 
   }
 }
 
-__global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
+__global__ void __launch_bounds__(256, 4) bn_act_pool_fwd_kernel(ActPoolArgs p) {
   const int g = blockIdx.z;
   const int CQ = p.C >> 3;
-  const int64_t total = (int64_t)p.B * p.Do * p.Ho * p.Wo * CQ;
   const __nv_bfloat16* yg = p.y.p[g];
-  // 32-bit index arithmetic (host checks total < 2^31): 64-bit div/mod would cost more than the useful work
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % (unsigned)CQ);
-    unsigned r = idx / (unsigned)CQ;
-    const int wo = (int)(r % p.Wo); r /= p.Wo;
-    const int ho = (int)(r % p.Ho); r /= p.Ho;
-    const int dd = (int)(r % p.Do);
-    const int n = (int)(r / p.Do);
-    const int c0 = cq * 8;
-    float sc[8], sh[8];
+  // Work = units (sample, output plane, chunk of output rows); a thread keeps ONE 8-channel chunk for the whole kernel
+  // (threads beyond the largest multiple of CQ idle), so the coefficients live in registers and a position costs one
+  // integer division.
+  const int cq = threadIdx.x % CQ, pstep = 256 / CQ;
+  if ((int)threadIdx.x >= pstep * CQ) return;
+  const int c0 = cq * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = p.coef.p[g][c0 + j]; sh[j] = p.coef.p[g][p.C + c0 + j]; }
+  for (int j = 0; j < 8; ++j) { sc[j] = p.coef.p[g][c0 + j]; sh[j] = p.coef.p[g][p.C + c0 + j]; }
+  const int nunits = p.B * p.Do * p.nch;
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int hc = unit % p.nch;
+    const int rr = unit / p.nch;
+    const int dd = rr % p.Do, n = rr / p.Do;
+    const int hb = hc * p.hcr, he = min(hb + p.hcr, p.Ho);
+    const int items = (he - hb) * p.Wo;
+   for (int pos = threadIdx.x / CQ; pos < items; pos += pstep) {
+    const int hh = pos / p.Wo;
+    const int wo = pos - hh * p.Wo, ho = hb + hh;
     float o[8];
     if (p.pool == TMF_POOL_NONE) {
       float f[8];
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
       }
     }
     store8f(p.out.p[g], ((((int64_t)n * p.Do + dd) * p.Ho + ho) * p.Wo + wo) * p.C + c0, p.fp32io, o);
+   }
   }
 }
 
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(ActPoolArgs p) {
 //  * APPLY folds the constant part into one FMA per element:  dy = A + Bc*y (+ scale*dz at the arg-max),
 //    A = scale*(m2*invstd*mean - m1),  Bc = -scale*m2*invstd.
 template <bool APPLY, int POOL>
-__global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
+__global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_pool_bwd_kernel(ActPoolArgs p) {
   const int g = blockIdx.z;
   extern __shared__ float red[];  // [2][C] (REDUCE only)
   const int CQ = p.C >> 3;
@@ -165,47 +173,41 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
     __syncthreads();
   }
   const int Dw = APPLY ? p.Dc : p.Do, Hw = APPLY ? p.Hc : p.Ho, Ww = APPLY ? p.Wc : p.Wo;
-  const int64_t total = (int64_t)p.B * Dw * Hw * Ww * CQ;
   const __nv_bfloat16* yg = p.y.p[g];
   constexpr int NPOS = (POOL == TMF_POOL_NONE) ? 1 : 8;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  int last_cq = -1;
+  // a thread keeps ONE 8-channel chunk for the whole kernel (threads beyond the largest multiple of CQ idle):
+  // coefficients in registers, one integer division per position (see the forward kernel)
+  const int cq = threadIdx.x % CQ, pstep = 256 / CQ;
+  const bool active = (int)threadIdx.x < pstep * CQ;
+  const int c0 = cq * 8;
   float sc[8], sh[8], mu[8], is[8], cA[8], cB[8], sg[8];
-  // 32-bit index arithmetic (host checks total < 2^31): 64-bit div/mod would cost more than the useful work
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * blockDim.x) {
-    const int cq = (int)(idx % (unsigned)CQ);
-    unsigned r = idx / (unsigned)CQ;
-    const int ww = (int)(r % Ww); r /= Ww;
-    const int hw = (int)(r % Hw); r /= Hw;
-    const int dw = (int)(r % Dw);
-    const int n = (int)(r / Dw);
-    const int c0 = cq * 8;
-    if (cq != last_cq) {                       // (host keeps a thread's channel chunk loop-invariant)
-      if (!APPLY && last_cq >= 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&red[last_cq * 8 + j], s1[j]);
-          atomicAdd(&red[p.C + last_cq * 8 + j], s2[j]);
-          s1[j] = 0.f; s2[j] = 0.f;
-        }
-      }
-      last_cq = cq;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[j] = p.coef.p[g][c0 + j];
-        sh[j] = p.coef.p[g][p.C + c0 + j];
-        mu[j] = p.coef.p[g][2 * p.C + c0 + j];
-        is[j] = p.coef.p[g][3 * p.C + c0 + j];
-        sg[j] = sc[j] > 0.f ? 1.f : (sc[j] < 0.f ? -1.f : 0.f);
-        if (APPLY) {
-          const float m1 = p.bcoef.p[g][c0 + j], m2 = p.bcoef.p[g][p.C + c0 + j];
-          cB[j] = -sc[j] * m2 * is[j];
-          cA[j] = -sc[j] * m1 - cB[j] * mu[j];
-        }
-      }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = p.coef.p[g][c0 + j];
+    sh[j] = p.coef.p[g][p.C + c0 + j];
+    mu[j] = p.coef.p[g][2 * p.C + c0 + j];
+    is[j] = p.coef.p[g][3 * p.C + c0 + j];
+    sg[j] = sc[j] > 0.f ? 1.f : (sc[j] < 0.f ? -1.f : 0.f);
+    if (APPLY) {
+      const float m1 = p.bcoef.p[g][c0 + j], m2 = p.bcoef.p[g][p.C + c0 + j];
+      cB[j] = -sc[j] * m2 * is[j];
+      cA[j] = -sc[j] * m1 - cB[j] * mu[j];
     }
+  }
+  const int nch = APPLY ? p.nch_c : p.nch, hcr = APPLY ? p.hcr_c : p.hcr;
+  const int nunits = p.B * Dw * nch;
+  for (int unit = blockIdx.x; unit < nunits && active; unit += gridDim.x) {
+    const int hc = unit % nch;
+    const int rr = unit / nch;
+    const int dw = rr % Dw, n = rr / Dw;
+    const int hb = hc * hcr, he = min(hb + hcr, Hw);
+    const int items = (he - hb) * Ww;
+   for (int pos = threadIdx.x / CQ; pos < items; pos += pstep) {
+    const int hh = pos / Ww;
+    const int ww = pos - hh * Ww, hw = hb + hh;
     const bool win_ok = (POOL == TMF_POOL_NONE) || (dw < p.Do && hw < p.Ho && ww < p.Wo);
     float go[8];
 #pragma unroll
@@ -291,13 +293,14 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(ActPoolArgs p) {
         if (APPLY) *reinterpret_cast<uint4*>(p.dy.p[g] + off[q]) = pack8(o);
       }
     }
+   }
   }
   if (!APPLY) {
-    if (last_cq >= 0) {
+    if (active) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[last_cq * 8 + j], s1[j]);
-        atomicAdd(&red[p.C + last_cq * 8 + j], s2[j]);
+        atomicAdd(&red[c0 + j], s1[j]);
+        atomicAdd(&red[p.C + c0 + j], s2[j]);
       }
     }
     __syncthreads();
@@ -326,6 +329,18 @@ static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool
     TMF_REQUIRE(p.Do > 0 && p.Ho > 0 && p.Wo > 0, "bn_act_pool: volume %dx%dx%d too small to pool", D, H, W);
   }
   return 0;
+}
+
+// Units = (sample, plane, chunk of rows): enough of them to fill `waves` x 148 blocks evenly; returns the grid size.
+static int plan_units(int B, int Dw, int Hw, int waves_x148, int* nch, int* hcr) {
+  const int planes = B * Dw;
+  int n = (waves_x148 + planes - 1) / planes;
+  if (n < 1) n = 1;
+  if (n > Hw) n = Hw;
+  *hcr = (Hw + n - 1) / n;
+  *nch = (Hw + *hcr - 1) / *hcr;
+  const int units = planes * *nch;
+  return units < waves_x148 ? units : waves_x148;
 }
 
 static int pick_grid(int64_t total_threads, int CQ, int64_t cap = 148 * 16) {
@@ -374,8 +389,7 @@ int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, 
   if (!load_group(p.y, (const __nv_bfloat16* const*)y, ng, true, "y") || !load_group(p.coef, coef, ng, true, "coef") ||
       !load_group(p.out, (void* const*)out, ng, true, "out"))
     return 1;
-  const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
-  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 8, &p.nch, &p.hcr), 1, ng);
   bn_act_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -392,8 +406,7 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
   TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
-  const int64_t total = (int64_t)B * p.Do * p.Ho * p.Wo * (C / 8);
-  dim3 grid(pick_grid(total, C / 8, 148 * 4), 1, ng);
+  dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 3, &p.nch, &p.hcr), 1, ng);
   launch_bwd<false>(p, grid, 2 * C * sizeof(float), st);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -428,8 +441,7 @@ int tmf_bn_act_pool_bwd_apply(int ng, const void* const* dout, int dout_fp32, co
       !load_group(p.dout, (const void* const*)dout, ng, true, "dout") ||
       !load_group(p.dy, (__nv_bfloat16* const*)dy, ng, true, "dy"))
     return 1;
-  const int64_t total = (int64_t)B * p.Dc * p.Hc * p.Wc * (C / 8);
-  dim3 grid(pick_grid(total, C / 8), 1, ng);
+  dim3 grid(plan_units(B, p.Dc, p.Hc, 148 * 6, &p.nch_c, &p.hcr_c), 1, ng);
   launch_bwd<true>(p, grid, 0, (cudaStream_t)stream);
   TMF_LAUNCH_CHECK();
   return 0;

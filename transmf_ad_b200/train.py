@@ -97,6 +97,9 @@ class GraphedTrainStep:
             dst.copy_(src, non_blocking=True)
         for dst, src in zip(self.static_targets, _as_tuple(targets)):
             dst.copy_(src, non_blocking=True)
+        refresh = getattr(self.optimizer, "refresh_hyperparams", None)
+        if refresh is not None:
+            refresh()                                      # e.g. FusedAdam: a scheduler-changed lr reaches the device scalar
         self.graph_fb.replay()
         if self.world > 1:
             self.reducer.reduce_now()
