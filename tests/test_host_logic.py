@@ -94,3 +94,21 @@ def test_snet_spec_matches_reference_layer_table():
     assert [(a, b, k) for a, b, k, _ in spec.layers] == [(1, 32, 3), (32, 32, 3), (32, 64, 3), (64, 64, 3), (64, 128, 3),
                                                          (128, 256, 3), (256, 128, 1)]
     assert [p for *_, p in spec.layers] == [1, 0, 1, 0, 1, 0, 2]
+
+
+def test_fused_adam_host_logic():
+    """FusedAdam mirrors torch.optim.Adam's constructor / param_groups and refuses anything it cannot run on the GPU
+    (there is no CPU fallback)."""
+    import pytest
+    import torch
+    from transmf_ad_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdam([p], lr=1e-4, weight_decay=0.0)
+    g = opt.param_groups[0]
+    assert g["lr"] == 1e-4 and g["betas"] == (0.9, 0.999) and g["eps"] == 1e-8 and g["weight_decay"] == 0.0
+    opt.step()                                   # no gradients yet: nothing to do, like torch.optim.Adam
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        opt.step()                               # CPU parameter: must fail loudly
+    with pytest.raises(ValueError):
+        FusedAdam([p], amsgrad=True)

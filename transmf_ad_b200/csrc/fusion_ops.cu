@@ -11,6 +11,7 @@ namespace tmf {
 // C[M,N] (+)= epilogue( sum_k A(m,k) * B(k,n) ),  A(m,k) = A[m*sAm + k*sAk],  B(k,n) = B[k*sBk + n*sBn]
 // ------------------------------------------------------------------------------------------------------------
 constexpr int G_TM = 64, G_TN = 64, G_TK = 16, G_PAD = 4;
+constexpr int G_SPLIT_K = 64;          // K elements per CTA when a GEMM is split along K (weight gradients: K = B*tokens)
 
 struct GemmArgs {
   const float* A; const float* B; float* C;
@@ -18,15 +19,20 @@ struct GemmArgs {
   int M, N, K;
   int64_t sAm, sAk, sBk, sBn;
   int act, accumulate;
+  int kchunk;                          // 0: whole K in one CTA; else K range per blockIdx.z, results added atomically to a zeroed C
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
+// These GEMMs are tiny (M = B*150 rows, K, N <= 512): what matters is latency, so the global loads of tile k+1 are
+// issued before the FMAs of tile k (register double buffering), and long-K problems are split over blockIdx.z.
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
   __shared__ __align__(16) float As[G_TK][G_TM + G_PAD];
   __shared__ __align__(16) float Bs[G_TK][G_TN + G_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * G_TM, n0 = blockIdx.x * G_TN;
+  const int kb = p.kchunk ? blockIdx.z * p.kchunk : 0;
+  const int ke = p.kchunk ? min(p.K, kb + p.kchunk) : p.K;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -34,19 +40,22 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (p.sAk == 1);
   const bool b_kfast = (p.sBk == 1);
-  for (int k0 = 0; k0 < p.K; k0 += G_TK) {
-    float ra[4], rb[4];
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int mm, kk;
       if (a_kfast) { kk = tid & 15; mm = (tid >> 4) + 16 * i; } else { mm = tid & 63; kk = (tid >> 6) + 4 * i; }
       const int m = m0 + mm, k = k0 + kk;
-      ra[i] = (m < p.M && k < p.K) ? __ldg(p.A + m * p.sAm + k * p.sAk) : 0.f;
-      int nn, kb;
-      if (b_kfast) { kb = tid & 15; nn = (tid >> 4) + 16 * i; } else { nn = tid & 63; kb = (tid >> 6) + 4 * i; }
-      const int n = n0 + nn, k2 = k0 + kb;
-      rb[i] = (n < p.N && k2 < p.K) ? __ldg(p.B + k2 * p.sBk + n * p.sBn) : 0.f;
+      ra[i] = (m < p.M && k < ke) ? __ldg(p.A + m * p.sAm + k * p.sAk) : 0.f;
+      int nn, kb2;
+      if (b_kfast) { kb2 = tid & 15; nn = (tid >> 4) + 16 * i; } else { nn = tid & 63; kb2 = (tid >> 6) + 4 * i; }
+      const int n = n0 + nn, k2 = k0 + kb2;
+      rb[i] = (n < p.N && k2 < ke) ? __ldg(p.B + k2 * p.sBk + n * p.sBn) : 0.f;
     }
+  };
+  load_tile(kb);
+  for (int k0 = kb; k0 < ke; k0 += G_TK) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -54,6 +63,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
       if (b_kfast) Bs[tid & 15][(tid >> 4) + 16 * i] = rb[i]; else Bs[(tid >> 6) + 4 * i][tid & 63] = rb[i];
     }
     __syncthreads();
+    if (k0 + G_TK < ke) load_tile(k0 + G_TK);         // in flight while this tile is multiplied
 #pragma unroll
     for (int k = 0; k < G_TK; ++k) {
       const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -75,8 +85,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
       float v = acc[i][j];
-      if (p.bias) v += p.bias[n];
       const int64_t o = (int64_t)m * p.N + n;
+      if (p.kchunk) { atomicAdd(p.C + o, v); continue; }
+      if (p.bias) v += p.bias[n];
       if (p.pre) p.pre[o] = v;
       if (p.act == 1) v = gelu_exact(v);
       if (p.residual) v += p.residual[o];
@@ -86,21 +97,24 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
   }
 }
 
-// column sums: out[n] = sum_m x[m,n]
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+// column sums: out[n] += sum over this block's rows of x[m,n]   (out zeroed by the caller; grid.y splits the rows)
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int rows_per_block) {
   __shared__ float part[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r = threadIdx.x >> 5;
+  const int mb = blockIdx.y * rows_per_block, me = min(M, mb + rows_per_block);
   float s = 0.f;
-  if (n < N)
-    for (int m = r; m < M; m += 8) s += x[(int64_t)m * N + n];
+  if (n < N) {
+#pragma unroll 4
+    for (int m = mb + r; m < me; m += 8) s += x[(int64_t)m * N + n];
+  }
   part[r][threadIdx.x & 31] = s;
   __syncthreads();
   if (r == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
-    out[n] = t;
+    atomicAdd(out + n, t);
   }
 }
 
@@ -459,7 +473,7 @@ __global__ void token_pool_bwd_kernel(const float* __restrict__ dmean, const flo
 }
 
 static int launch_gemm(GemmArgs& p, cudaStream_t st) {
-  dim3 grid(ceil_div(p.N, G_TN), ceil_div(p.M, G_TM), 1);
+  dim3 grid(ceil_div(p.N, G_TN), ceil_div(p.M, G_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
   gemm_kernel<<<grid, 256, 0, st>>>(p);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -499,9 +513,17 @@ int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, i
   p.A = dy; p.B = x; p.C = dw;
   p.M = N; p.N = K; p.K = M;          // dw[N,K] = dy^T[N,M] . x[M,K]
   p.sAm = 1; p.sAk = N; p.sBk = K; p.sBn = 1;
-  if (launch_gemm(p, (cudaStream_t)stream)) return 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M > 2 * G_SPLIT_K) {             // long reduction over the tokens: split it, partial sums meet in a zeroed dw
+    p.kchunk = G_SPLIT_K;
+    TMF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+  }
+  if (launch_gemm(p, st)) return 3;
   if (dbias) {
-    colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(dy, dbias, M, N);
+    TMF_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)N, st));
+    const int rows = 128;
+    dim3 grid(ceil_div(N, 32), ceil_div(M, rows), 1);
+    colsum_kernel<<<grid, 256, 0, st>>>(dy, dbias, M, N, rows);
     TMF_LAUNCH_CHECK();
   }
   return 0;
