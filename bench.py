@@ -45,17 +45,41 @@ WORKLOADS = {
 }
 
 
-def conv_flops_per_subject(shape, dim=128, towers=2):
-    """Algorithmic conv FLOPs: 2*M*Cout*Cin*k^3 for fwd and wgrad of every layer and dgrad of all but conv1.0."""
+def conv_flops_per_subject(shape, dim=128, towers=2, first_layer=True, other_layers=True):
+    """Algorithmic conv FLOPs: 2*M*Cout*Cin*k^3 for fwd and wgrad of every layer and dgrad of all but conv1.0.
+    ``first_layer`` / ``other_layers`` select conv1.0 (Cin = 1, HBM-bound) and conv2.0 .. conv4.3 (tensor-bound)."""
     from transmf_ad_b200.functional import SNetSpec
     D, H, W = shape
     total = 0.0
     for l, (cin, cout, ks, pool) in enumerate(SNetSpec(dim).layers):
         f = 2.0 * D * H * W * cout * cin * ks ** 3
-        total += f * (3 if l > 0 else 2)
+        if (l == 0 and first_layer) or (l > 0 and other_layers):
+            total += f * (3 if l > 0 else 2)
         if pool:
             D, H, W = D // 2, H // 2, W // 2
     return total * towers
+
+
+def block1_bytes_per_subject(shape, dim=128, towers=2):
+    """Algorithmic HBM bytes of the four block-1 passes: x fp32, y bf16 (dim/4 channels),
+    pooled activation / its gradient bf16."""
+    D, H, W = shape
+    c = dim // 4
+    x = 4.0 * D * H * W
+    y = 2.0 * D * H * W * c
+    pooled = 2.0 * (D // 2) * (H // 2) * (W // 2) * c
+    return {"tmf_conv1_fwd": towers * (x + y), "tmf_bn_act_pool_fwd@L0": towers * (y + pooled),
+            "tmf_bn_act_pool_bwd_reduce@L0": towers * (y + pooled), "tmf_conv1_bwd_fused": towers * (y + pooled + x)}
+
+
+def committed_traffic():
+    """DRAM bytes per step of the tensor-bound conv launches from the committed `ncu --set full` capture
+    (profiles/conv_traffic.json, written by scripts/ncu_traffic.py); None when absent."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
 
 
 def measured_peaks():
@@ -361,8 +385,22 @@ def main():
             e2e_step(i)
         e2e_ms = timed(e2e_step, args.steps) / args.steps
     h2d = sum(t.numel() * t.element_size() for t in pool_h[0][: (1 if towers == 1 else 2)]) + pool_h[0][2].numel() * 8
+    # the PCIe leg on its own (pinned host -> device, nothing else running): when e2e ~= this, the step is link-bound
+    probe_dst = [torch.empty_like(t, device=dev) for t in pool_h[0][: (1 if towers == 1 else 2)]]
+    h2d_ms_alone = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for d, hsrc in zip(probe_dst, pool_h[0]):
+            d.copy_(hsrc, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        h2d_ms_alone.append(e0.elapsed_time(e1))
+    del probe_dst
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "subjects/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 if towers > 1 else 4}
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 if towers > 1 else 4,
+           "h2d_ms_alone": round(min(h2d_ms_alone), 4), "h2d_gbs_alone": round(h2d / min(h2d_ms_alone) / 1e6, 2)}
 
     # ---- roofline leg: CUDA events around every C-ABI launch (separate pass; not part of `value`) --------------------
     roofline, breakdown = None, None
@@ -373,15 +411,42 @@ def main():
         for i in range(nprof):
             train_step(pool_d[i % npool], False)
         rec = _lib.TIMER.stop()
-        conv_tags = ("tmf_conv3d_fwd", "tmf_conv3d_dgrad", "tmf_conv3d_wgrad", "tmf_conv1_fwd", "tmf_conv1_wgrad")
-        conv_ms = sum(v[0] for t, v in rec.items() if t.split("@")[0] in conv_tags) / nprof
-        flops = conv_flops_per_subject(SHAPE, kwargs["dim"], towers) * B
-        achieved = flops / (conv_ms * 1e-3) / 1e12
+        # dominant kernel family: the tcgen05 implicit-GEMM convolutions conv2.0 .. conv4.3 (fwd, dgrad, wgrad), the
+        # layers SURVEY.md section 8d puts under the tensor roofline.  conv1.0 (Cin = 1, 26 FLOP/B) is HBM-bound and
+        # is reported against the copy bandwidth below, together with the other block-1 passes.
+        gemm_tags = ("tmf_conv3d_fwd", "tmf_conv3d_dgrad", "tmf_conv3d_wgrad")
+        conv1_tags = ("tmf_conv1_fwd", "tmf_conv1_wgrad", "tmf_conv1_bwd_fused")
+        gemm_ms = sum(v[0] for t, v in rec.items() if t.split("@")[0] in gemm_tags) / nprof
+        conv1_ms = sum(v[0] for t, v in rec.items() if t.split("@")[0] in conv1_tags) / nprof
+        flops = conv_flops_per_subject(SHAPE, kwargs["dim"], towers, first_layer=False) * B
+        flops_all = conv_flops_per_subject(SHAPE, kwargs["dim"], towers) * B
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        achieved_all = flops_all / ((gemm_ms + conv1_ms) * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": "conv3d fwd+dgrad+wgrad (all 7 layers, both towers)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        traffic = committed_traffic()
+        hbm = {}
+        for tag, nbytes in block1_bytes_per_subject(SHAPE, kwargs["dim"], towers).items():
+            if tag in rec:
+                ms = rec[tag][0] / nprof
+                gbs = nbytes * B / (ms * 1e-3) / 1e9
+                hbm[tag] = {"ms": round(ms, 4), "algorithmic_mb": round(nbytes * B / 1e6, 1), "achieved_gbs": round(gbs, 1),
+                            "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3)}
+        roofline = {"bound": "tensor",
+                    "kernel": "conv3d implicit GEMM on tcgen05: fwd + dgrad + wgrad of conv2.0 .. conv4.3, both towers "
+                              "(18 launches per step)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic["dram_bytes_per_step"] if traffic else None,
+                    "traffic_source": traffic["source"] if traffic else None,
                     "peak_source": f"{peaks['source']} bf16 sustained (kernels timed inside the step)",
-                    "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": conv_ms}
+                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+                    "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": gemm_ms,
+                    "all_conv_incl_conv1": {"achieved": achieved_all, "frac": achieved_all / peak,
+                                            "algorithmic_gflop_per_step": flops_all / 1e9,
+                                            "ms_per_step": gemm_ms + conv1_ms,
+                                            "note": "conv1.0 fwd and the fused block-1 backward (BN/LeakyReLU/MaxPool "
+                                                    "backward + conv1.0 wgrad) are HBM-bound passes; their whole time is "
+                                                    "counted here"},
+                    "hbm_bound_block1": {"peak_gbs": peaks["hbm_gbs"], "kernels": hbm}}
         breakdown = {t: round(rec[t][0] / nprof, 4) for t in sorted(rec)}          # ms per step per entry point (@L = layer)
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------

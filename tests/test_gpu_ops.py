@@ -228,7 +228,10 @@ def test_maxpool_backward_routes_ties_to_first_maximum():
 
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,K,N,gelu,res", [(300, 128, 128, False, True), (300, 128, 512, True, False),
-                                            (2, 512, 512, False, False), (77, 64, 2, False, False), (150, 512, 128, False, True)])
+                                            (2, 512, 512, False, False), (77, 64, 2, False, False), (150, 512, 128, False, True),
+                                            (1200, 128, 256, False, False), (1200, 512, 128, False, True),   # B=8 x 150 tokens
+                                            (8, 512, 128, False, False), (8, 128, 2, False, False),           # heads
+                                            (45, 100, 36, True, True), (33, 30, 20, False, False)])           # K % 4 != 0 -> generic kernel
 def test_linear_function(M, K, N, gelu, res):
     x, w, b = g_randn(M, K, seed=1), g_randn(N, K, seed=2, scale=K ** -0.5), g_randn(N, seed=3, scale=0.1)
     r = g_randn(M, N, seed=4) if res else None

@@ -19,10 +19,11 @@
 namespace tmf {
 using namespace umma;
 
-constexpr int UC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+// threads: warp 0 = TMA producer, warp 1 (and 2 in the two-issuer variant) = MMA issuer (warp 1 owns TMEM), then 4 epilogue warps
 constexpr int UC_TILE_M = 128;
 constexpr int UC_MAX_BSTAGES = 27 * 4;
 constexpr int UC_MAX_ASTAGES = 4;
+constexpr int UC_TMA_LANES = 4;  // producer lanes issuing TMA boxes round-robin (TMF_UMMA_TMA_LANES=1..8: bring-up switch)
 constexpr uint32_t UC_SMEM_BUDGET = 227 * 1024;
 
 struct alignas(64) UmmaConvParams {
@@ -41,6 +42,7 @@ struct alignas(64) UmmaConvParams {
   uint32_t idesc;
   uint32_t tmem_cols;
   int bo_mode;                    // how the descriptor base-offset field is derived (bring-up switch)
+  int tma_lanes;                  // producer lanes that issue TMA boxes round-robin
 };
 
 __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
@@ -49,8 +51,14 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
   return 0u;
 }
 
-template <int KSTEPS, int KS, bool RES>
-__global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+// NISS = 2 (streamed weights, 4*Cout <= 512 TMEM columns): a narrow-N tcgen05.mma (N = 64: ~54 tensor-pipe cycles) is
+// bound by the ~100 cycles its issuing thread needs, so two issuer warps take alternate taps of the weight ring (ring
+// stage s always belongs to issuer s % 2: SB is even), each into its own TMEM accumulator; the epilogue adds the two.
+template <int KSTEPS, int KS, bool RES, int NISS>
+__global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+  static_assert(NISS == 1 || !RES, "two issuers only with the streamed weight ring");
+  constexpr int NTHREADS = 32 * (5 + NISS);
+  constexpr int EPI0 = 32 * (1 + NISS);             // first epilogue thread
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smA = smem_base;
@@ -71,14 +79,14 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
   const int taps2 = p.ks * p.ks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, NISS); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, NISS); mbar_init(acc_empty + 8 * i, 128); }
     fence_barrier_init();
     prefetch_tmap(&p.tmA[g]);
     prefetch_tmap(&p.tmB[g]);
   }
-  for (int i = threadIdx.x; i < 512; i += UC_THREADS) stats_ptr[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += NTHREADS) stats_ptr[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
@@ -90,8 +98,14 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
 
   if (warp == 0) {
     // =========================================== TMA producer ===========================================
-    if (lane == 0) {
-      int sa = 0, sb = 0;
+    // One thread keeps only ~2 tensor loads in flight (measured: ~600 cycles per box whatever its size,
+    // scripts/ubench/tma_bw.cu), which starves the narrow-N layers whose weights stream through the ring (conv3.3
+    // dgrad: 60 boxes per 128-row tile).  UC_TMA_LANES lanes therefore walk the same load sequence and issue the
+    // boxes round-robin.  Every lane waits on EVERY ring hand-over, owner or not: an mbarrier parity wait is only
+    // sound for a thread that has observed each earlier phase of that barrier.
+    if (lane < p.tma_lanes) {
+      const int nl = p.tma_lanes;
+      int sa = 0, sb = 0, jw = 0;
       uint32_t pa = 0, pb = 0;
       uint32_t kd_loaded = 0;                                  // resident weights: planes already requested
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta) {
@@ -106,7 +120,8 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
           if (p.b_resident && !((kd_loaded >> kd) & 1u)) {     // all (tap, chunk) boxes of this plane, once per CTA
             kd_loaded |= 1u << kd;
             for (int t = 0; t < taps2; ++t)
-              for (int c = 0; c < p.nchunk; ++c) {
+              for (int c = 0; c < p.nchunk; ++c, ++jw) {
+                if ((jw % nl) != lane) continue;
                 const int tap = kd * taps2 + t, idx = tap * p.nchunk + c;
                 mbar_expect_tx(b_full + 8 * idx, p.b_tx_bytes);
                 tma_load_3d(smB + (uint32_t)idx * p.b_stage_bytes, &p.tmB[g], b_full + 8 * idx, c * p.chunk, 0, tap);
@@ -114,16 +129,21 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
           }
           for (int c = 0; c < p.nchunk; ++c) {
             mbar_wait(a_empty + 8 * sa, pa ^ 1u);
-            mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
-            tma_load_5d(smA + (uint32_t)sa * p.a_stage_bytes, &p.tmA[g], a_full + 8 * sa, c * p.chunk, -p.hw,
-                        h0 - p.hw, dd, n);
+            if ((jw % nl) == lane) {
+              mbar_expect_tx(a_full + 8 * sa, p.a_tx_bytes);
+              tma_load_5d(smA + (uint32_t)sa * p.a_stage_bytes, &p.tmA[g], a_full + 8 * sa, c * p.chunk, -p.hw,
+                          h0 - p.hw, dd, n);
+            }
+            ++jw;
             if (++sa == p.SA) { sa = 0; pa ^= 1u; }
             if (!p.b_resident) {
-              for (int t = 0; t < taps2; ++t) {
+              for (int t = 0; t < taps2; ++t, ++jw) {
                 const int tap = kd * taps2 + t;
                 mbar_wait(b_empty + 8 * sb, pb ^ 1u);
-                mbar_expect_tx(b_full + 8 * sb, p.b_tx_bytes);
-                tma_load_3d(smB + (uint32_t)sb * p.b_stage_bytes, &p.tmB[g], b_full + 8 * sb, c * p.chunk, 0, tap);
+                if ((jw % nl) == lane) {
+                  mbar_expect_tx(b_full + 8 * sb, p.b_tx_bytes);
+                  tma_load_3d(smB + (uint32_t)sb * p.b_stage_bytes, &p.tmB[g], b_full + 8 * sb, c * p.chunk, 0, tap);
+                }
                 if (++sb == p.SB) { sb = 0; pb ^= 1u; }
               }
             }
@@ -131,7 +151,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= NISS) {
     // =========================================== MMA issuer =============================================
     // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
     // one elected lane issues tcgen05.mma / tcgen05.commit.  KSTEPS (16-element K steps per smem row), the kernel
@@ -140,6 +160,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
       constexpr uint32_t ROW_UNITS = KSTEPS * 2;                 // row bytes / 16
       constexpr uint32_t SBO = 8u * KSTEPS * 32u;
       constexpr int TAPS2 = KS * KS;
+      const int iss = warp - 1;                                  // which issuer this warp is (0 when NISS == 1)
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint64_t desc_hi = make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFFFFFF00000000ull;
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((as * NISS + iss) * p.cout);
         uint32_t accumulate = 0;
 #pragma unroll 1
         for (int kd = 0; kd < KS; ++kd) {
@@ -187,6 +208,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
                   b_lo = b_res;
                   b_res += b_res_step;
                 } else {
+                  if (NISS > 1 && (sb & (NISS - 1)) != iss) {    // the other issuer's tap
+                    if (++sb == p.SB) { sb = 0; pb ^= 1u; }
+                    continue;
+                  }
                   mbar_wait(b_full + 8 * sb, pb);
                   tc_fence_after();
                   b_lo = b0_lo + (uint32_t)sb * b_units;
@@ -236,12 +261,19 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(acc_full + 8 * as, acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NISS * p.cout);
       __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout;
       for (int c0 = 0; c0 < p.cout; c0 += 32) {
         uint32_t raw[32];
         tmem_ld32(taddr + (uint32_t)c0, raw);
         tmem_ld_wait();
+        if (NISS > 1) {                                        // second issuer's partial sums
+          uint32_t raw2[32];
+          tmem_ld32(taddr + (uint32_t)(p.cout + c0), raw2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -280,7 +312,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) conv3d_umma_kernel(const __grid
     }
     if (want_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < p.cout; i += 128) {
+      for (int i = threadIdx.x - EPI0; i < p.cout; i += 128) {
         atomicAdd(&p.stats[g][i], (double)stats_ptr[i]);
         atomicAdd(&p.stats[g][p.cout + i], (double)stats_ptr[256 + i]);
       }
@@ -313,9 +345,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int umma_issuers() {
+  static int n = -1;
+  if (n < 0) {
+    const char* e = getenv("TMF_UMMA_ISSUERS");      // bring-up switch: 1 = single issuer warp everywhere
+    n = e ? atoi(e) : 2;
+  }
+  return n;
+}
+
 struct UmmaPlan {
   bool ok;
-  int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident;
+  int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident, niss;
   uint32_t layout, a_stage_bytes, b_stage_bytes, a_tx, b_tx, tmem_cols, smem_bytes;
   CUtensorMapSwizzle swz;
 };
@@ -357,8 +398,11 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
     pl.SB = (int)((budget - (uint32_t)pl.SA * pl.a_stage_bytes) / pl.b_stage_bytes);
     if (pl.SB > 8) pl.SB = 8;
   }
+  // two issuer warps (alternate taps, separate accumulators) where the streamed ring and 512 TMEM columns allow it
+  pl.niss = (ks == 3 && !pl.b_resident && 4 * cout <= 512 && pl.SB >= 4 && umma_issuers() >= 2) ? 2 : 1;
+  if (pl.niss == 2) pl.SB &= ~1;                 // ring stage s is always issuer s % 2's
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * cout)) cols <<= 1;
+  while (cols < (uint32_t)(2 * pl.niss * cout)) cols <<= 1;
   if (cols > 512) return pl;
   pl.tmem_cols = cols;
   pl.smem_bytes = fixed + (uint32_t)pl.SA * pl.a_stage_bytes + (uint32_t)pl.SB * pl.b_stage_bytes;
@@ -373,6 +417,17 @@ static int umma_bo_mode() {
     mode = e ? atoi(e) : 0;   // hardware swizzles on absolute smem address bits: verified on B200 (scripts/umma_bringup.py)
   }
   return mode;
+}
+
+static int umma_tma_lanes() {
+  static int lanes = -1;
+  if (lanes < 0) {
+    const char* e = getenv("TMF_UMMA_TMA_LANES");
+    lanes = e ? atoi(e) : UC_TMA_LANES;
+    if (lanes < 1) lanes = 1;
+    if (lanes > 8) lanes = 8;
+  }
+  return lanes;
 }
 
 }  // namespace tmf
@@ -402,6 +457,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   p.idesc = make_idesc_bf16(UC_TILE_M, cout, 0, 0);
   p.tmem_cols = pl.tmem_cols;
   p.bo_mode = umma_bo_mode();
+  p.tma_lanes = umma_tma_lanes();
   const int taps = ksize * ksize * ksize;
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) {
@@ -442,24 +498,29 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   if (per_group < 1) per_group = 1;
   dim3 grid(per_group * ng, 1, 1);
   const int ksteps = pl.chunk / 16;
-#define TMF_LAUNCH_CONV(KST, KSZ, RES)                                                                              \
+#define TMF_LAUNCH_CONV(KST, KSZ, RES, NI)                                                                          \
   do {                                                                                                             \
     static bool attr_done = false;                                                                                 \
     if (!attr_done) {                                                                                              \
-      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<KST, KSZ, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)UC_SMEM_BUDGET));                                                         \
+      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<KST, KSZ, RES, NI>,                                          \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UC_SMEM_BUDGET));            \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    conv3d_umma_kernel<KST, KSZ, RES><<<grid, UC_THREADS, pl.smem_bytes, st>>>(p);                                 \
+    conv3d_umma_kernel<KST, KSZ, RES, NI><<<grid, 32 * (5 + NI), pl.smem_bytes, st>>>(p);                          \
   } while (0)
-  if (ksteps == 4 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(4, 3, true);
-  else if (ksteps == 4 && ksize == 3) TMF_LAUNCH_CONV(4, 3, false);
-  else if (ksteps == 2 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(2, 3, true);
-  else if (ksteps == 2 && ksize == 3) TMF_LAUNCH_CONV(2, 3, false);
-  else if (ksteps == 4 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(4, 1, true);
-  else if (ksteps == 4 && ksize == 1) TMF_LAUNCH_CONV(4, 1, false);
-  else if (ksteps == 2 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(2, 1, true);
-  else TMF_LAUNCH_CONV(2, 1, false);
+  if (ksteps == 4 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(4, 3, true, 1);
+  else if (ksteps == 4 && ksize == 3 && pl.niss == 2) TMF_LAUNCH_CONV(4, 3, false, 2);
+  else if (ksteps == 4 && ksize == 3) TMF_LAUNCH_CONV(4, 3, false, 1);
+  else if (ksteps == 2 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(2, 3, true, 1);
+  else if (ksteps == 2 && ksize == 3 && pl.niss == 2) TMF_LAUNCH_CONV(2, 3, false, 2);
+  else if (ksteps == 2 && ksize == 3) TMF_LAUNCH_CONV(2, 3, false, 1);
+  else if (ksteps == 4 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(4, 1, true, 1);
+  else if (ksteps == 2 && ksize == 1 && pl.b_resident) TMF_LAUNCH_CONV(2, 1, true, 1);
+  else {
+    TMF_REQUIRE(pl.niss == 1, "conv3d_fwd_umma: internal: two-issuer plan without a kernel variant");
+    if (ksteps == 4) TMF_LAUNCH_CONV(4, 1, false, 1);
+    else TMF_LAUNCH_CONV(2, 1, false, 1);
+  }
 #undef TMF_LAUNCH_CONV
   TMF_LAUNCH_CHECK();
   return 0;

@@ -3,6 +3,8 @@
 //   LayerNorm fwd/bwd (warp per row, float4), GELU backward, short-sequence multi-head cross attention fwd/bwd
 //   (K/V resident in shared memory, warp-level softmax reductions), token pooling (GAP + GMP) and the
 //   gradient-reversal scale.  Reference: models/networks.py:114-175, 215-281; models/gradient_reversal/functional.py.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tmf {
@@ -472,7 +474,198 @@ __global__ void token_pool_bwd_kernel(const float* __restrict__ dmean, const flo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Pipelined variant for the shapes the fusion transformer actually runs (every extent a multiple of 4, 16-byte
+// aligned rows): 32 x 64 output tile, 128 threads (4 x 4 outputs each), K in 32-wide slices moved global -> shared
+// with 16-byte cp.async through a 3-deep ring, so the loads of two slices are in flight while one is multiplied
+// (gemm_kernel exposes one global-load latency per 16-wide slice: ~1 us x K/16, i.e. 8-30 us for these GEMMs whose
+// arithmetic is ~1 us).  Smaller tiles also put M = B*150 = 1200 rows on 76-304 CTAs instead of 38-152.
+//   AKF / BKF: the operand is contiguous along k in global memory (x and w of the forward pass; dy of dgrad).  It is
+//   kept as [row][k] in shared memory and read four k at a time; rows are interleaved over the threads (row = t +
+//   8*i or t + 16*j) so that the 144-byte row pitch spreads a quarter-warp over all 32 banks.  Otherwise the operand
+//   is contiguous along m / n (w of dgrad, dy and x of wgrad), kept as [k][m|n] and read as one float4 per k.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int F_TM = 32, F_TN = 64, F_TK = 32, F_STAGES = 3, F_THREADS = 128;
+constexpr int F_KPITCH = F_TK + 4;                 // [row][k] tiles
+constexpr int F_A_FLOATS = (F_TM * F_KPITCH > F_TK * (F_TM + 4)) ? F_TM * F_KPITCH : F_TK * (F_TM + 4);
+constexpr int F_B_FLOATS = (F_TN * F_KPITCH > F_TK * (F_TN + 4)) ? F_TN * F_KPITCH : F_TK * (F_TN + 4);
+constexpr int F_STAGE_FLOATS = F_A_FLOATS + F_B_FLOATS;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;                    // src-size 0: the 16 bytes are zero-filled, gsrc is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool AKF, bool BKF>
+__global__ void __launch_bounds__(F_THREADS) gemm_pipe_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) float fsm[];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * F_TM, n0 = blockIdx.x * F_TN;
+  const int kb = p.kchunk ? blockIdx.z * p.kchunk : 0;
+  const int ke = p.kchunk ? min(p.K, kb + p.kchunk) : p.K;
+  const int nkt = (ke - kb + F_TK - 1) / F_TK;
+  const int64_t lda = AKF ? p.sAm : p.sAk, ldb = BKF ? p.sBn : p.sBk;
+
+  auto load_stage = [&](int kt) {
+    float* As = fsm + (kt % F_STAGES) * F_STAGE_FLOATS;
+    float* Bs = As + F_A_FLOATS;
+    const int k0 = kb + kt * F_TK;
+    if (AKF) {                                     // [m][k]: 32 rows x 8 chunks
+#pragma unroll
+      for (int c = tid; c < F_TM * (F_TK / 4); c += F_THREADS) {
+        const int r = c >> 3, q = c & 7;
+        const int m = m0 + r, k = k0 + 4 * q;
+        const bool ok = m < p.M && k < ke;
+        cp_async16(As + r * F_KPITCH + 4 * q, p.A + (ok ? (int64_t)m * lda + k : 0), ok);
+      }
+    } else {                                       // [k][m]: 32 rows x 8 chunks
+#pragma unroll
+      for (int c = tid; c < F_TK * (F_TM / 4); c += F_THREADS) {
+        const int r = c >> 3, q = c & 7;
+        const int k = k0 + r, m = m0 + 4 * q;
+        const bool ok = m < p.M && k < ke;
+        cp_async16(As + r * (F_TM + 4) + 4 * q, p.A + (ok ? (int64_t)k * lda + m : 0), ok);
+      }
+    }
+    if (BKF) {                                     // [n][k]: 64 rows x 8 chunks
+#pragma unroll
+      for (int c = tid; c < F_TN * (F_TK / 4); c += F_THREADS) {
+        const int r = c >> 3, q = c & 7;
+        const int n = n0 + r, k = k0 + 4 * q;
+        const bool ok = n < p.N && k < ke;
+        cp_async16(Bs + r * F_KPITCH + 4 * q, p.B + (ok ? (int64_t)n * ldb + k : 0), ok);
+      }
+    } else {                                       // [k][n]: 32 rows x 16 chunks
+#pragma unroll
+      for (int c = tid; c < F_TK * (F_TN / 4); c += F_THREADS) {
+        const int r = c >> 4, q = c & 15;
+        const int k = k0 + r, n = n0 + 4 * q;
+        const bool ok = n < p.N && k < ke;
+        cp_async16(Bs + r * (F_TN + 4) + 4 * q, p.B + (ok ? (int64_t)k * ldb + n : 0), ok);
+      }
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < F_STAGES - 1; ++s) {
+    if (s < nkt) load_stage(s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nkt; ++kt) {
+    cp_async_wait<F_STAGES - 2>();                 // slice kt has landed (for this thread's copies)
+    __syncthreads();                               // ... and everybody's; slice kt-1's buffer is free again
+    if (kt + F_STAGES - 1 < nkt) load_stage(kt + F_STAGES - 1);
+    cp_async_commit();
+    const float* As = fsm + (kt % F_STAGES) * F_STAGE_FLOATS;
+    const float* Bs = As + F_A_FLOATS;
+#pragma unroll
+    for (int k4 = 0; k4 < F_TK; k4 += 4) {
+      float a[4][4], b[4][4];                      // [k][i], [k][j]
+      if (AKF) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (ty + 8 * i) * F_KPITCH + k4);
+          a[0][i] = v.x; a[1][i] = v.y; a[2][i] = v.z; a[3][i] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (k4 + k) * (F_TM + 4) + ty * 4);
+          a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+        }
+      }
+      if (BKF) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (tx + 16 * j) * F_KPITCH + k4);
+          b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (k4 + k) * (F_TN + 4) + tx * 4);
+          b[k][0] = v.x; b[k][1] = v.y; b[k][2] = v.z; b[k][3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[k][i], b[k][j], acc[i][j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + (AKF ? ty + 8 * i : ty * 4 + i);
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + (BKF ? tx + 16 * j : tx * 4 + j);
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      const int64_t o = (int64_t)m * p.N + n;
+      if (p.kchunk) { atomicAdd(p.C + o, v); continue; }
+      if (p.bias) v += __ldg(p.bias + n);
+      if (p.pre) p.pre[o] = v;
+      if (p.act == 1) v = gelu_exact(v);
+      if (p.residual) v += __ldg(p.residual + o);
+      if (p.accumulate) v += p.C[o];
+      p.C[o] = v;
+    }
+  }
+}
+
+static bool gemm_pipe_eligible(const GemmArgs& p) {
+  static int off = -1;
+  if (off < 0) off = getenv("TMF_GEMM_IMPL") != nullptr && atoi(getenv("TMF_GEMM_IMPL")) == 0;   // 0: always gemm_kernel
+  if (off) return false;
+  const bool akf = p.sAk == 1, bkf = p.sBk == 1;
+  if (!akf && p.sAm != 1) return false;
+  if (!bkf && p.sBn != 1) return false;
+  const int64_t lda = akf ? p.sAm : p.sAk, ldb = bkf ? p.sBn : p.sBk;
+  if ((lda & 3) || (ldb & 3) || ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15)) return false;
+  if ((akf || bkf) && (p.K & 3)) return false;       // 16-byte chunks along k
+  if (!akf && (p.M & 3)) return false;               // ... along m
+  if (!bkf && (p.N & 3)) return false;               // ... along n
+  return true;
+}
+
 static int launch_gemm(GemmArgs& p, cudaStream_t st) {
+  if (gemm_pipe_eligible(p)) {
+    dim3 grid(ceil_div(p.N, F_TN), ceil_div(p.M, F_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
+    const size_t smem = sizeof(float) * F_STAGES * F_STAGE_FLOATS;
+    const bool akf = p.sAk == 1, bkf = p.sBk == 1;
+#define TMF_LAUNCH_PIPE(AK, BK)                                                                                      \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      TMF_CUDA(cudaFuncSetAttribute(gemm_pipe_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    gemm_pipe_kernel<AK, BK><<<grid, F_THREADS, smem, st>>>(p);                                                     \
+  } while (0)
+    if (akf && bkf) TMF_LAUNCH_PIPE(true, true);
+    else if (akf) TMF_LAUNCH_PIPE(true, false);
+    else if (bkf) TMF_LAUNCH_PIPE(false, true);
+    else TMF_LAUNCH_PIPE(false, false);
+#undef TMF_LAUNCH_PIPE
+    TMF_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(ceil_div(p.N, G_TN), ceil_div(p.M, G_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
   gemm_kernel<<<grid, 256, 0, st>>>(p);
   TMF_LAUNCH_CHECK();
@@ -516,6 +709,12 @@ int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, i
   cudaStream_t st = (cudaStream_t)stream;
   if (M > 2 * G_SPLIT_K) {             // long reduction over the tokens: split it, partial sums meet in a zeroed dw
     p.kchunk = G_SPLIT_K;
+    if (gemm_pipe_eligible(p)) {       // enough K slices to put ~one CTA on every SM, in whole 32-wide slices
+      const int tiles = ceil_div(N, F_TM) * ceil_div(K, F_TN);
+      int splits = ceil_div(148, tiles);
+      if (splits > ceil_div(M, F_TK)) splits = ceil_div(M, F_TK);
+      p.kchunk = ceil_div(ceil_div(M, splits), F_TK) * F_TK;
+    }
     TMF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
   }
   if (launch_gemm(p, st)) return 3;
