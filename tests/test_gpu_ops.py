@@ -1,5 +1,6 @@
 """Op-level parity (GPU): every C-ABI kernel against the matching torch fp32 CPU op on identical (bf16-rounded)
 inputs.  bf16 outputs: <= 1 bf16 ulp (2^-8 relative) plus accumulation-order noise; fp32 outputs: <= 1e-4."""
+import ctypes as C
 import os
 
 import pytest
@@ -409,3 +410,53 @@ def test_fused_adam_matches_torch_adam():
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
     st = o_ours.state[ours[0]]
     assert float(st["step"]) == 5.0 and st["exp_avg"].shape == ours[0].shape
+
+
+def test_loss_reader_returns_each_steps_scalars_one_call_late():
+    from transmf_ad_b200.train import LossReader
+    reader = LossReader(2, DEV)
+    got = []
+    for i in range(5):
+        a = torch.full((), float(i), device=DEV)
+        b = torch.full((), 10.0 + i, device=DEV)
+        got.append(reader.push((a, b)))
+    got.append(reader.flush())
+    assert got[0] is None
+    assert got[1:] == [(float(i), 10.0 + i) for i in range(5)]
+    assert reader.flush() is None
+
+
+@pytest.mark.parametrize("shape,cin,cout", [((2, 22, 27, 22), 128, 64), ((2, 11, 13, 11), 128, 256),
+                                            ((2, 11, 13, 11), 256, 128), ((1, 19, 23, 19), 128, 64)])
+@pytest.mark.parametrize("max_ctas", ["0", "3"])
+def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_ctas, monkeypatch):
+    """The generic tcgen05 kernel with streamed weights (conv3.3 dgrad, conv4.0 fwd/dgrad): several 128-row tiles per
+    weight pass, one or two issuer warps, single- or double-buffered accumulators -- also with only 3 CTAs per tower,
+    so that every CTA walks many super-tiles (barrier phases wrap).  Checked against the CUDA-core kernel."""
+    B, D, H, W = shape
+    lib = L.load()
+    info = (C.c_int * 8)()
+    assert lib.tmf_conv3d_umma_plan_info(D, H, W, cin, cout, 3, info) == 0 and info[7] == 0   # streamed weights
+    monkeypatch.setenv("TMF_UMMA_MAX_CTAS", max_ctas)
+    ng = 2
+    a = [to_ndhwc_bf16(bf16r(g_randn(B, cin, D, H, W, seed=11 + t))) for t in range(ng)]
+    w = [g_randn(cout, cin, 3, 3, 3, seed=21 + t, scale=(2.0 / (cin * 27)) ** 0.5).to(DEV) for t in range(ng)]
+    bias = [g_randn(cout, seed=31 + t, scale=0.1).to(DEV) for t in range(ng)]
+    wf = [torch.empty((27, cout, cin), dtype=torch.bfloat16, device=DEV) for _ in range(ng)]
+    L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(None), cout, cin, 3)
+    res = {}
+    for impl in (L.CONV_DIRECT, L.CONV_UMMA):
+        y = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV) for _ in range(ng)]
+        stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=DEV).unbind(0))
+        L.call("tmf_conv3d_fwd", ng, L.ptrs(a), L.ptrs(wf), L.ptrs(bias), L.ptrs(y), L.ptrs(stats), B, D, H, W, cin, cout,
+               3, impl)
+        torch.cuda.synchronize()
+        res[impl] = (y, stats)
+    for t in range(ng):
+        yd, yu = res[L.CONV_DIRECT][0][t].float(), res[L.CONV_UMMA][0][t].float()
+        assert float((yd - yu).abs().max() / yd.abs().max()) < 6e-3, f"tower {t}: plan {list(info)}"
+        sd, su = res[L.CONV_DIRECT][1][t], res[L.CONV_UMMA][1][t]
+        yu64 = res[L.CONV_UMMA][0][t].double()
+        want = torch.cat([yu64.sum(dim=(0, 1, 2, 3)), (yu64 * yu64).sum(dim=(0, 1, 2, 3))])
+        assert torch.allclose(su, want, rtol=1e-5, atol=1e-4)          # statistics of the STORED values
+        assert torch.allclose(sd, su, rtol=2e-2, atol=0.5)

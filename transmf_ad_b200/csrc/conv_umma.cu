@@ -43,6 +43,8 @@ struct alignas(64) UmmaConvParams {
   uint32_t tmem_cols;
   int bo_mode;                    // how the descriptor base-offset field is derived (bring-up switch)
   int tma_lanes;                  // producer lanes that issue TMA boxes round-robin
+  int mt;                         // 128-row M tiles per weight pass ("super-tile" = 128*mt consecutive positions)
+  int nbuf;                       // accumulator sets in TMEM: 2 = epilogue overlaps the next super-tile, 1 = it does not
 };
 
 __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
         const int qt = r % p.QT; r /= p.QT;
         const int d = r % p.D;
         const int n = r / p.D;
-        const int h0 = (qt * UC_TILE_M) / p.Wp;
+        const int h0 = (qt * UC_TILE_M * p.mt) / p.Wp;
         for (int kd = 0; kd < p.ks; ++kd) {
           const int dd = d + kd - p.hw;
           if (dd < 0 || dd >= p.D) continue;
@@ -176,12 +178,13 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
         const int d = r % p.D;
-        const uint32_t qoff_units = (uint32_t)((qt * UC_TILE_M) % p.Wp) * ROW_UNITS;
-        const int as = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        const uint32_t qoff_units = (uint32_t)((qt * UC_TILE_M * p.mt) % p.Wp) * ROW_UNITS;
+        const int as = (p.nbuf == 2) ? (it & 1) : 0;
+        const uint32_t acc_ph = (uint32_t)((p.nbuf == 2) ? (it >> 1) : it) & 1u;
         mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)((as * NISS + iss) * p.cout);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((as * NISS + iss) * p.mt * p.cout);
+        const uint32_t mt_a_units = (uint32_t)UC_TILE_M * ROW_UNITS;      // next 128 rows of the slab
         uint32_t accumulate = 0;
 #pragma unroll 1
         for (int kd = 0; kd < KS; ++kd) {
@@ -217,11 +220,14 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
                   b_lo = b0_lo + (uint32_t)sb * b_units;
                 }
                 if (elect_one()) {
+                  // the tap's weights multiply every 128-row tile of the super-tile before the ring stage is released
+                  for (int mt = 0; mt < p.mt; ++mt) {
+                    const uint32_t a_mt = a_lo + (uint32_t)mt * mt_a_units;
+                    const uint32_t d_mt = d_tmem + (uint32_t)(mt * p.cout);
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) {
-                    mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
-                                accumulate);
-                    accumulate = 1;
+                    for (int k = 0; k < KSTEPS; ++k)
+                      mma_bf16_ss(d_mt, desc_hi | (uint64_t)(a_mt + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
+                                  k ? 1u : accumulate);
                   }
                   if (!RES) mma_commit(b_empty + 8 * sb);
                 }
@@ -254,14 +260,15 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
       const int qt = r % p.QT; r /= p.QT;
       const int d = r % p.D;
       const int n = r / p.D;
-      const int q = qt * UC_TILE_M + row;
-      const int h = q / p.Wp, w = q - h * p.Wp;
-      const bool valid = (h < p.H) && (w < p.W);
-      const int as = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const int as = (p.nbuf == 2) ? (it & 1) : 0;
+      const uint32_t acc_ph = (uint32_t)((p.nbuf == 2) ? (it >> 1) : it) & 1u;
       mbar_wait(acc_full + 8 * as, acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NISS * p.cout);
+      for (int mt = 0; mt < p.mt; ++mt) {
+      const int q = (qt * p.mt + mt) * UC_TILE_M + row;
+      const int h = q / p.Wp, w = q - h * p.Wp;
+      const bool valid = (h < p.H) && (w < p.W);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * NISS * p.mt + mt) * p.cout);
       __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout;
       for (int c0 = 0; c0 < p.cout; c0 += 32) {
         uint32_t raw[32];
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
         tmem_ld_wait();
         if (NISS > 1) {                                        // second issuer's partial sums
           uint32_t raw2[32];
-          tmem_ld32(taddr + (uint32_t)(p.cout + c0), raw2);
+          tmem_ld32(taddr + (uint32_t)(p.mt * p.cout + c0), raw2);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
           atomicAdd(&stats_ptr[c0 + lane], v[0]);
           atomicAdd(&stats_ptr[256 + c0 + lane], sq[0]);
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(acc_empty + 8 * as);
@@ -356,10 +364,25 @@ static int umma_issuers() {
 
 struct UmmaPlan {
   bool ok;
-  int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident, niss;
+  int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident, niss, mt, nbuf;
   uint32_t layout, a_stage_bytes, b_stage_bytes, a_tx, b_tx, tmem_cols, smem_bytes;
   CUtensorMapSwizzle swz;
 };
+
+static int umma_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// geometry of a super-tile of mt 128-row tiles: slab rows, tiles per plane, TMA bytes
+static void plan_geometry(UmmaPlan& pl, int H, int ks, int mt) {
+  const int rmax = (pl.Wp - 1) + (ks - 1) * pl.Wp + (ks - 1) + (UC_TILE_M * mt - 1);
+  pl.NH = rmax / pl.Wp + 1;
+  pl.QT = (H * pl.Wp + UC_TILE_M * mt - 1) / (UC_TILE_M * mt);
+  pl.a_tx = (uint32_t)pl.NH * pl.Wp * pl.row_bytes;
+  pl.a_stage_bytes = (pl.a_tx + 1023u) & ~1023u;
+  pl.mt = mt;
+}
 
 static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
   UmmaPlan pl{};
@@ -373,12 +396,10 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
   pl.layout = (pl.chunk == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
   pl.swz = (pl.chunk == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   pl.Wp = W + 2 * hw;
-  const int rmax = (pl.Wp - 1) + (ks - 1) * pl.Wp + (ks - 1) + (UC_TILE_M - 1);
-  pl.NH = rmax / pl.Wp + 1;
+  pl.niss = 1;
+  pl.nbuf = 2;
+  plan_geometry(pl, H, ks, 1);
   if (pl.Wp > 256 || pl.NH > 256) return pl;
-  pl.QT = (H * pl.Wp + UC_TILE_M - 1) / UC_TILE_M;
-  pl.a_tx = (uint32_t)pl.NH * pl.Wp * pl.row_bytes;
-  pl.a_stage_bytes = (pl.a_tx + 1023u) & ~1023u;
   pl.b_tx = (uint32_t)cout * pl.row_bytes;
   pl.b_stage_bytes = (pl.b_tx + 1023u) & ~1023u;
   const int taps = ks * ks * ks;
@@ -391,18 +412,52 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
     pl.SA = (int)((budget - total_b) / pl.a_stage_bytes);
     if (pl.SA > UC_MAX_ASTAGES) pl.SA = UC_MAX_ASTAGES;
   } else {
+    // Streamed weights.  Measured on B200 (profiles/r1d_conv_microbench.md): the kernel is bound by the NUMBER of TMA
+    // boxes -- ~500 cycles per box plus ~1.5 cycles per 128-byte row, whatever issues them -- and every 128-row tile
+    // re-streams all 27 x nchunk weight boxes.  So the weights of a tap are applied to `mt` consecutive 128-row tiles
+    // (one bigger input slab per (kd, chunk), mt accumulators in TMEM), and two issuer warps share the taps where the
+    // MMAs are narrow.  The plan with the smallest modelled cost per plane wins:
+    //   tma = QT * 3 * nchunk * [(500 + 1.5 * slab rows) + 9 * (500 + 1.5 * Cout)]          (128-byte rows)
+    //   mma = QT * mt * (27 * nchunk * ksteps) * max(0.75 * Cout, 100 / issuers)            (pipe vs issue cycles)
+    //   cost = max(tma, mma) * (1.05 if the accumulators are single-buffered)
     pl.b_resident = 0;
-    pl.SA = 3;
-    if (3 * pl.a_stage_bytes + 2 * pl.b_stage_bytes > budget) pl.SA = 2;
-    if ((uint32_t)pl.SA * pl.a_stage_bytes + 2 * pl.b_stage_bytes > budget) return pl;
-    pl.SB = (int)((budget - (uint32_t)pl.SA * pl.a_stage_bytes) / pl.b_stage_bytes);
-    if (pl.SB > 8) pl.SB = 8;
+    const int force_mt = umma_env_int("TMF_UMMA_MT", 0);             // bring-up switches
+    const int max_iss = (ks == 3) ? umma_issuers() : 1;
+    double best = 1e30;
+    UmmaPlan bp = pl;
+    bool found = false;
+    for (int mt = 1; mt <= 4; ++mt) {
+      if (force_mt > 0 && mt != force_mt) continue;
+      if (ks != 3 && mt > 1) break;
+      for (int niss = 1; niss <= (max_iss >= 2 ? 2 : 1); ++niss)
+        for (int nbuf = 2; nbuf >= 1; --nbuf) {
+          if (nbuf * niss * mt * cout > 512) continue;
+          UmmaPlan c = pl;
+          plan_geometry(c, H, ks, mt);
+          if (c.NH > 256) continue;
+          c.niss = niss;
+          c.nbuf = nbuf;
+          c.SA = 3;
+          if (3 * c.a_stage_bytes + 4 * c.b_stage_bytes > budget) c.SA = 2;
+          const int min_sb = (niss == 2) ? 4 : 2;
+          if ((uint32_t)c.SA * c.a_stage_bytes + (uint32_t)min_sb * c.b_stage_bytes > budget) continue;
+          c.SB = (int)((budget - (uint32_t)c.SA * c.a_stage_bytes) / c.b_stage_bytes);
+          if (c.SB > 8) c.SB = 8;
+          if (niss == 2) c.SB &= ~1;               // ring stage s is always issuer s % 2's
+          const double rows128 = c.row_bytes / 128.0;
+          const double tma = (double)c.QT * ks * c.nchunk *
+                             ((500.0 + 1.5 * c.NH * c.Wp * rows128) + ks * ks * (500.0 + 1.5 * cout * rows128));
+          const double per_mma = (0.75 * cout > 100.0 / niss) ? 0.75 * cout : 100.0 / niss;
+          const double mma = (double)c.QT * mt * (taps * c.nchunk * (c.chunk / 16)) * per_mma;
+          const double cost = (tma > mma ? tma : mma) * (nbuf == 1 ? 1.05 : 1.0);
+          if (cost < best * 0.999) { best = cost; bp = c; found = true; }
+        }
+    }
+    if (!found) return pl;
+    pl = bp;
   }
-  // two issuer warps (alternate taps, separate accumulators) where the streamed ring and 512 TMEM columns allow it
-  pl.niss = (ks == 3 && !pl.b_resident && 4 * cout <= 512 && pl.SB >= 4 && umma_issuers() >= 2) ? 2 : 1;
-  if (pl.niss == 2) pl.SB &= ~1;                 // ring stage s is always issuer s % 2's
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * pl.niss * cout)) cols <<= 1;
+  while (cols < (uint32_t)(pl.nbuf * pl.niss * pl.mt * cout)) cols <<= 1;
   if (cols > 512) return pl;
   pl.tmem_cols = cols;
   pl.smem_bytes = fixed + (uint32_t)pl.SA * pl.a_stage_bytes + (uint32_t)pl.SB * pl.b_stage_bytes;
@@ -434,6 +489,15 @@ static int umma_tma_lanes() {
 
 using namespace tmf;
 
+extern "C" int tmf_conv3d_umma_plan_info(int D, int H, int W, int cin, int cout, int ksize, int* out8) {
+  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize);
+  if (out8 != nullptr) {
+    out8[0] = pl.ok ? 1 : 0; out8[1] = pl.mt; out8[2] = pl.niss; out8[3] = pl.nbuf;
+    out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident;
+  }
+  return pl.ok ? 0 : 1;
+}
+
 bool tmf_conv3d_fwd_umma_supported(int D, int H, int W, int cin, int cout, int ksize) {
   if (getenv("TMF_DISABLE_UMMA") != nullptr) return false;
   return make_plan(D, H, W, cin, cout, ksize).ok;
@@ -458,6 +522,8 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   p.tmem_cols = pl.tmem_cols;
   p.bo_mode = umma_bo_mode();
   p.tma_lanes = umma_tma_lanes();
+  p.mt = pl.mt;
+  p.nbuf = pl.nbuf;
   const int taps = ksize * ksize * ksize;
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) {
@@ -495,6 +561,10 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_group = sms / ng;
   if (per_group > p.tiles_per_group) per_group = p.tiles_per_group;
+  {
+    const char* e = getenv("TMF_UMMA_MAX_CTAS");     // test switch: few CTAs per tower -> many super-tiles per CTA
+    if (e != nullptr && atoi(e) > 0 && per_group > atoi(e)) per_group = atoi(e);
+  }
   if (per_group < 1) per_group = 1;
   dim3 grid(per_group * ng, 1, 1);
   const int ksteps = pl.chunk / 16;

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "attn_args.cuh"
 
 namespace tmf {
 
@@ -268,13 +269,6 @@ __global__ void scale_kernel(const float* __restrict__ x, float* __restrict__ y,
 // ------------------------------------------------------------------------------------------------------------
 constexpr int AT_WARPS = 8;
 constexpr int AT_ROWS = 32;  // rows per block
-
-struct AttnArgs {
-  const float* q; const float* kv; const float* out; const float* lse_in; const float* dout;
-  float* o; float* lse; float* dq; float* dkv;
-  int B, Nq, Nk, heads, dh;
-  float scale;
-};
 
 // smem: Ks[Nk][dh+1], Vs[Nk][dh+1], sc[AT_WARPS][Nk], qs[AT_WARPS][dh]
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(AttnArgs p) {
@@ -776,6 +770,10 @@ int tmf_attn_fwd(const float* q, const float* kv, float* out, float* lse, int B,
   AttnArgs p{};
   p.q = q; p.kv = kv; p.o = out; p.lse = lse;
   p.B = B; p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.dh = dh; p.scale = scale;
+  {
+    const int rc = attn_tiled_fwd(p, (cudaStream_t)stream);      // register-tiled kernels (attention.cu) when the shape fits
+    if (rc >= 0) return rc;
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)AT_WARPS * dh);
   if (attn_smem_check(smem, (const void*)attn_fwd_kernel)) return 2;
   dim3 grid(B * heads, ceil_div(Nq, AT_ROWS), 1);
@@ -789,6 +787,10 @@ int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float
   AttnArgs p{};
   p.q = q; p.kv = kv; p.out = out; p.lse_in = lse; p.dout = dout; p.dq = dq; p.dkv = dkv;
   p.B = B; p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.dh = dh; p.scale = scale;
+  {
+    const int rc = attn_tiled_bwd(p, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   const size_t smem1 =
       sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)2 * AT_WARPS * dh);
   if (attn_smem_check(smem1, (const void*)attn_bwd_dq_kernel)) return 2;

@@ -156,3 +156,40 @@ class DevicePrefetcher:
         batch = self.slots[k]
         self._preload()                                     # batch i+1: H2D overlaps with the caller's work on batch i
         return batch
+
+
+class LossReader:
+    """Host-side reads of per-step scalars (the reference's ``loss.item()`` pair, kfold_train_adversarial.py:127-128)
+    without stalling the launch queue: ``push(tensors)`` enqueues a device->pinned-host copy of this step's scalars and
+    returns the PREVIOUS step's values (``None`` on the first call); ``flush()`` returns the last step's.  One step of
+    lag keeps the next graph launch and H2D copy in flight while the current step computes."""
+
+    def __init__(self, n, device):
+        self.n = n
+        self.host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.stage = [torch.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self.pending = None
+
+    def _wait(self):
+        if self.pending is None:
+            return None
+        self.done[self.pending].synchronize()
+        return tuple(float(v) for v in self.host[self.pending])
+
+    def push(self, tensors):
+        k = self.k
+        self.k ^= 1
+        for i, t in enumerate(tensors[: self.n]):
+            self.stage[k][i:i + 1].copy_(t.detach().reshape(1), non_blocking=True)
+        self.host[k].copy_(self.stage[k], non_blocking=True)
+        self.done[k].record()
+        prev = self._wait()
+        self.pending = k
+        return prev
+
+    def flush(self):
+        prev = self._wait()
+        self.pending = None
+        return prev
