@@ -99,9 +99,9 @@ int64_t tmf_conv3d_wgrad_workspace_bytes(int ng, int impl, int B, int D, int H, 
 int tmf_conv3d_supported(int op, int impl, int D, int H, int W, int cin, int cout, int ksize);
 
 /* Introspection (host only, no device work): the launch plan of the generic tcgen05 forward/dgrad kernel
- * (conv_umma.cu) for this problem.  out8 = {ok, 128-row tiles per weight pass, issuer warps, accumulator sets,
+ * (conv_umma.cu) for this problem (ng towers of batch B: the plan weighs wave quantisation).  out8 = {ok, 128-row tiles per weight pass, issuer warps, accumulator sets,
  * input stages, weight stages, super-tiles per plane, weights resident}.  Returns 0 if the kernel takes the problem. */
-int tmf_conv3d_umma_plan_info(int D, int H, int W, int cin, int cout, int ksize, int* out8);
+int tmf_conv3d_umma_plan_info(int ng, int B, int D, int H, int W, int cin, int cout, int ksize, int* out8);
 
 /* BatchNorm statistics -> coefficients.  coef[4*C] = {scale = gamma*invstd, shift = beta - mean*scale, mean,
  * invstd}.  training != 0: batch statistics from stats (biased variance), running_mean/var updated with

@@ -436,7 +436,7 @@ def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_
     B, D, H, W = shape
     lib = L.load()
     info = (C.c_int * 8)()
-    assert lib.tmf_conv3d_umma_plan_info(D, H, W, cin, cout, 3, info) == 0 and info[7] == 0   # streamed weights
+    assert lib.tmf_conv3d_umma_plan_info(2, B, D, H, W, cin, cout, 3, info) == 0 and info[7] == 0   # streamed weights
     monkeypatch.setenv("TMF_UMMA_MAX_CTAS", max_ctas)
     ng = 2
     a = [to_ndhwc_bf16(bf16r(g_randn(B, cin, D, H, W, seed=11 + t))) for t in range(ng)]

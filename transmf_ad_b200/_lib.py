@@ -48,7 +48,7 @@ SIGNATURES = {
 PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
-         "tmf_conv3d_umma_plan_info": (_i, [_i] * 6 + [C.POINTER(C.c_int)]),
+         "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),
          "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_adam_chunk_bytes": (_i, [])}
 
 _lib = None

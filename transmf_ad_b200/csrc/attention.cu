@@ -20,19 +20,41 @@ namespace tmf {
 
 constexpr int TA_WARPS = 8, TA_ROWS = 32, TA_THREADS = TA_WARPS * 32;
 
-// stage `rows` rows of a head slice (dh floats at `src + r*row_stride`) as dst[r*ld + d]; rows >= nvalid are zeroed
+// Staging.  Every CTA copies a few tens of KB of head slices (dh contiguous floats per token) into shared memory; what
+// matters is how many loads are in flight, so the copies are 128-bit and issued in batches of four before any is
+// stored (a scalar loop exposes one L2 latency per element: ~10 us per kernel).  Requires dh % 4 == 0.
+// stage `rows` rows (dh floats at `src + r*row_stride`) as dst[r*ld + d]; rows >= nvalid are zeroed
 __device__ __forceinline__ void stage_rows(float* dst, const float* src, int64_t row_stride, int nvalid, int rows,
                                            int dh, int ld) {
-  for (int i = threadIdx.x; i < rows * dh; i += TA_THREADS) {
-    const int r = i / dh, d = i - r * dh;
-    dst[r * ld + d] = (r < nvalid) ? __ldg(src + (int64_t)r * row_stride + d) : 0.f;
+  const int dh4 = dh >> 2, total = rows * dh4;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * TA_THREADS) {
+    float4 v[4];
+    int off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * TA_THREADS;
+      const int r = i / dh4, c = i - r * dh4;
+      off[u] = (i < total) ? r * ld + 4 * c : -1;
+      v[u] = (i < total && r < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * row_stride) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off[u] >= 0) {
+        float* d = dst + off[u];
+        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+      }
   }
 }
-// stage up to 32 rows transposed: dst[d*32 + r]
+// stage up to 32 rows transposed: dst[d*32 + r]  (lane = row: conflict-free stores)
 __device__ __forceinline__ void stage_rows_t(float* dst, const float* src, int64_t row_stride, int nvalid, int dh) {
-  for (int i = threadIdx.x; i < TA_ROWS * dh; i += TA_THREADS) {
-    const int r = i / dh, d = i - r * dh;
-    dst[d * TA_ROWS + r] = (r < nvalid) ? __ldg(src + (int64_t)r * row_stride + d) : 0.f;
+  const int dh4 = dh >> 2;
+  for (int i = threadIdx.x; i < TA_ROWS * dh4; i += TA_THREADS) {
+    const int r = i & (TA_ROWS - 1), c = i >> 5;
+    const float4 v = (r < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * row_stride) + c)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* d = dst + (4 * c) * TA_ROWS + r;
+    d[0] = v.x; d[TA_ROWS] = v.y; d[2 * TA_ROWS] = v.z; d[3 * TA_ROWS] = v.w;
   }
 }
 
@@ -63,6 +85,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_fwd_kernel(AttnArgs p) 
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < NPL; ++j) s[r][j] = 0.f;
+#pragma unroll 4
   for (int d = 0; d < dh; ++d) {
     const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * TA_ROWS + 4 * warp);
     float kk[NPL];
@@ -102,6 +125,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_fwd_kernel(AttnArgs p) 
   __syncwarp();
   for (int d = lane; d < dh; d += 32) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int j = 0; j < p.Nk; ++j) {
       const float4 p4 = *reinterpret_cast<const float4*>(Pw + j * 4);
       const float v = Vs[j * ld + d];
@@ -156,6 +180,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dq_kernel(AttnArgs p) {
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < NPL; ++j) { s[r][j] = 0.f; dp[r][j] = 0.f; }
+#pragma unroll 2
   for (int d = 0; d < dh; ++d) {
     const float4 q4 = *reinterpret_cast<const float4*>(Qt + d * TA_ROWS + 4 * warp);
     const float4 g4 = *reinterpret_cast<const float4*>(dOt + d * TA_ROWS + 4 * warp);
@@ -180,6 +205,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dq_kernel(AttnArgs p) {
   __syncwarp();
   for (int d = lane; d < dh; d += 32) {
     float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int j = 0; j < p.Nk; ++j) {
       const float4 d4 = *reinterpret_cast<const float4*>(dSw + j * 4);
       const float kk = Ks[j * ld + d];
@@ -219,15 +245,15 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dkv_kernel(AttnArgs p) 
   stage_rows(dOs, p.dout + qoff, inner, p.Nq, Np, dh, ld);
   stage_rows_t(Kt, kvb, 2 * inner, p.Nk - j0, dh);
   stage_rows_t(Vt, kvb + inner, 2 * inner, p.Nk - j0, dh);
+  float* Os = Pws;                                       // O rows, only until D_i is known (smem_cols() sizes the area)
+  stage_rows(Os, p.out + qoff, inner, p.Nq, Np, dh, ld);
   for (int i = threadIdx.x; i < Np; i += TA_THREADS)
     lses[i] = (i < p.Nq) ? __ldg(p.lse_in + ((int64_t)b * p.heads + h) * p.Nq + i) : 0.f;
   __syncthreads();
-  for (int i = warp; i < Np; i += TA_WARPS) {            // D_i = dO_i . O_i
+  for (int i = threadIdx.x; i < Np; i += TA_THREADS) {   // D_i = dO_i . O_i   (padding rows are zero)
     float acc = 0.f;
-    if (i < p.Nq)
-      for (int d = lane; d < dh; d += 32) acc = fmaf(dOs[i * ld + d], __ldg(p.out + qoff + (int64_t)i * inner + d), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) Ds[i] = acc;
+    for (int d = 0; d < dh; ++d) acc = fmaf(dOs[i * ld + d], Os[i * ld + d], acc);
+    Ds[i] = acc;
   }
   __syncthreads();
 
@@ -236,6 +262,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dkv_kernel(AttnArgs p) 
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < NPL; ++j) { s[r][j] = 0.f; dp[r][j] = 0.f; }
+#pragma unroll 2
   for (int d = 0; d < dh; ++d) {
     const float4 k4 = *reinterpret_cast<const float4*>(Kt + d * TA_ROWS + 4 * warp);
     const float4 v4 = *reinterpret_cast<const float4*>(Vt + d * TA_ROWS + 4 * warp);
@@ -265,6 +292,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dkv_kernel(AttnArgs p) 
   __syncwarp();
   for (int d = lane; d < dh; d += 32) {
     float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int i = 0; i < p.Nq; ++i) {
       const float4 s4 = *reinterpret_cast<const float4*>(dSw + i * 4);
       const float4 p4 = *reinterpret_cast<const float4*>(Pw + i * 4);
@@ -306,13 +334,14 @@ static size_t smem_rows(int npl, int dh) {   // fwd / dq: Ks, Vs, (Qt | Qt, dOt)
   return sizeof(float) * ((size_t)2 * 32 * npl * (dh + 1) + (size_t)2 * dh * TA_ROWS + (size_t)TA_WARPS * 32 * npl * 4);
 }
 static size_t smem_cols(int npl, int dh) {   // dkv
-  return sizeof(float) * ((size_t)2 * 32 * npl * (dh + 1) + (size_t)2 * 32 * npl + (size_t)2 * dh * TA_ROWS +
-                          (size_t)2 * TA_WARPS * 32 * npl * 4);
+  const size_t np = 32 * (size_t)npl;
+  const size_t pds = 2 * TA_WARPS * np * 4, orows = np * (dh + 1);      // P / dS area, also the temporary home of O
+  return sizeof(float) * (2 * np * (dh + 1) + 2 * np + (size_t)2 * dh * TA_ROWS + (pds > orows ? pds : orows));
 }
 constexpr size_t TA_SMEM_MAX = 200 * 1024;
 
 int attn_tiled_fwd(const AttnArgs& p, cudaStream_t st) {
-  if (!tiled_enabled() || p.dh > 128 || p.Nk > 320) return -1;
+  if (!tiled_enabled() || p.dh > 128 || (p.dh & 3) || p.Nk > 320) return -1;
   const int npl = p.Nk <= 160 ? 5 : 10;
   const size_t smem = smem_rows(npl, p.dh);
   if (smem > TA_SMEM_MAX) return -1;
@@ -322,7 +351,7 @@ int attn_tiled_fwd(const AttnArgs& p, cudaStream_t st) {
 }
 
 int attn_tiled_bwd(const AttnArgs& p, cudaStream_t st) {
-  if (!tiled_enabled() || p.dh > 128 || p.Nk > 320 || p.Nq > 320) return -1;
+  if (!tiled_enabled() || p.dh > 128 || (p.dh & 3) || p.Nk > 320 || p.Nq > 320) return -1;
   const int nk = p.Nk <= 160 ? 5 : 10, nq = p.Nq <= 160 ? 5 : 10;
   const size_t smem1 = smem_rows(nk, p.dh), smem2 = smem_cols(nq, p.dh);
   if (smem1 > TA_SMEM_MAX || smem2 > TA_SMEM_MAX) return -1;

@@ -384,7 +384,7 @@ static void plan_geometry(UmmaPlan& pl, int H, int ks, int mt) {
   pl.mt = mt;
 }
 
-static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
+static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B = 8, int ng = 2) {
   UmmaPlan pl{};
   pl.ok = false;
   if (ks != 1 && ks != 3) return pl;
@@ -419,7 +419,9 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
     // MMAs are narrow.  The plan with the smallest modelled cost per plane wins:
     //   tma = QT * 3 * nchunk * [(500 + 1.5 * slab rows) + 9 * (500 + 1.5 * Cout)]          (128-byte rows)
     //   mma = QT * mt * (27 * nchunk * ksteps) * max(0.75 * Cout, 100 / issuers)            (pipe vs issue cycles)
-    //   cost = max(tma, mma) * (1.05 if the accumulators are single-buffered)
+    //   cost per plane = max(tma, mma) * (1.15 if the accumulators are single-buffered);  the grid is one CTA per SM and
+    //   a CTA walks whole super-tiles, so the total is ceil(B*D*QT / CTAs per tower) rounds of (cost per plane / QT):
+    //   big super-tiles lose to wave quantisation on the small layers (conv4.0 fwd: 88 super-tiles on 74 CTAs).
     pl.b_resident = 0;
     const int force_mt = umma_env_int("TMF_UMMA_MT", 0);             // bring-up switches
     const int max_iss = (ks == 3) ? umma_issuers() : 1;
@@ -449,7 +451,10 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks) {
                              ((500.0 + 1.5 * c.NH * c.Wp * rows128) + ks * ks * (500.0 + 1.5 * cout * rows128));
           const double per_mma = (0.75 * cout > 100.0 / niss) ? 0.75 * cout : 100.0 / niss;
           const double mma = (double)c.QT * mt * (taps * c.nchunk * (c.chunk / 16)) * per_mma;
-          const double cost = (tma > mma ? tma : mma) * (nbuf == 1 ? 1.05 : 1.0);
+          const int ncta = (148 / (ng > 0 ? ng : 1)) > 0 ? 148 / (ng > 0 ? ng : 1) : 1;
+          const int64_t ntiles = (int64_t)B * D * c.QT;
+          const double rounds = (double)((ntiles + ncta - 1) / ncta);
+          const double cost = rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.15 : 1.0) / c.QT;
           if (cost < best * 0.999) { best = cost; bp = c; found = true; }
         }
     }
@@ -489,8 +494,8 @@ static int umma_tma_lanes() {
 
 using namespace tmf;
 
-extern "C" int tmf_conv3d_umma_plan_info(int D, int H, int W, int cin, int cout, int ksize, int* out8) {
-  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize);
+extern "C" int tmf_conv3d_umma_plan_info(int ng, int B, int D, int H, int W, int cin, int cout, int ksize, int* out8) {
+  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize, B, ng);
   if (out8 != nullptr) {
     out8[0] = pl.ok ? 1 : 0; out8[1] = pl.mt; out8[2] = pl.niss; out8[3] = pl.nbuf;
     out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident;
@@ -507,7 +512,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize,
                         void* stream) {
   TMF_CHECK_NG(ng);
-  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize);
+  const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize, B, ng);
   TMF_REQUIRE(pl.ok, "conv3d_fwd_umma: unsupported problem");
   EncodeTiledFn encode = get_encode_fn();
   TMF_REQUIRE(encode != nullptr, "conv3d_fwd_umma: cuTensorMapEncodeTiled entry point not available");
