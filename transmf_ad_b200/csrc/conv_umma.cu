@@ -419,7 +419,7 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
     // MMAs are narrow.  The plan with the smallest modelled cost per plane wins:
     //   tma = QT * 3 * nchunk * [(500 + 1.5 * slab rows) + 9 * (500 + 1.5 * Cout)]          (128-byte rows)
     //   mma = QT * mt * (27 * nchunk * ksteps) * max(0.75 * Cout, 100 / issuers)            (pipe vs issue cycles)
-    //   cost per plane = max(tma, mma) * (1.15 if the accumulators are single-buffered);  the grid is one CTA per SM and
+    //   cost per plane = max(tma, mma) * (1.25 if the accumulators are single-buffered);  the grid is one CTA per SM and
     //   a CTA walks whole super-tiles, so the total is ceil(B*D*QT / CTAs per tower) rounds of (cost per plane / QT):
     //   big super-tiles lose to wave quantisation on the small layers (conv4.0 fwd: 88 super-tiles on 74 CTAs).
     pl.b_resident = 0;
@@ -454,7 +454,7 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
           const int ncta = (148 / (ng > 0 ? ng : 1)) > 0 ? 148 / (ng > 0 ? ng : 1) : 1;
           const int64_t ntiles = (int64_t)B * D * c.QT;
           const double rounds = (double)((ntiles + ncta - 1) / ncta);
-          const double cost = rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.15 : 1.0) / c.QT;
+          const double cost = rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0) / c.QT;
           if (cost < best * 0.999) { best = cost; bp = c; found = true; }
         }
     }
