@@ -406,8 +406,9 @@ def main():
         h2d_ms_alone.append(e0.elapsed_time(e1))
     del probe_dst
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "subjects/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 if towers > 1 else 4,
-           "h2d_ms_alone": round(min(h2d_ms_alone), 4), "h2d_gbs_alone": round(h2d / min(h2d_ms_alone) / 1e6, 2)}
+           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": (8 if towers > 1 else 4) * world,   # whole job
+           "h2d_ms_alone": round(min(h2d_ms_alone), 4), "h2d_gbs_alone": round(h2d / min(h2d_ms_alone) / 1e6, 2),      # one rank's link
+           "h2d_bytes_per_rank": int(h2d)}
 
     # ---- roofline leg: CUDA events around every C-ABI launch (separate pass; not part of `value`) --------------------
     roofline, breakdown = None, None

@@ -623,6 +623,148 @@ __global__ void __launch_bounds__(F_THREADS) gemm_pipe_kernel(GemmArgs p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Second pipelined variant, for latency: 32 x 32 output tile, 256 threads = 4 K-GROUPS of 64 threads.  A "super-slice"
+// is four 32-wide K slices; group g multiplies slice g of every super-slice into its own 4 x 4 register tiles, and
+// the four partial tiles meet in shared memory at the end.  Per thread a K = 128 GEMM is 512 FMAs instead of 2048,
+// and M = 1200, N = 128 is 152 CTAs of 8 warps instead of 76 CTAs of 4 -- these GEMMs are bound by the serial FMA
+// chain of a thread plus one load latency, not by throughput.  Operand layouts as in gemm_pipe_kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int V_TM = 32, V_TN = 32, V_TK = 32, V_GROUPS = 4, V_THREADS = 64 * V_GROUPS, V_BUFS = 2;
+constexpr int V_PITCH = 36;                                        // both [row][k] (32 + 4) and [k][m|n] (32 + 4) tiles
+constexpr int V_SLICE_FLOATS = 2 * 32 * V_PITCH;                   // A tile + B tile of one K slice
+constexpr int V_SUPER_FLOATS = V_GROUPS * V_SLICE_FLOATS;
+constexpr int V_RED_PITCH = 36;
+
+template <bool AKF, bool BKF>
+__global__ void __launch_bounds__(V_THREADS) gemm_ksplit_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) float fsm[];
+  const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63, tx = t & 7, ty = t >> 3;
+  const int m0 = blockIdx.y * V_TM, n0 = blockIdx.x * V_TN;
+  const int kb = p.kchunk ? blockIdx.z * p.kchunk : 0;
+  const int ke = p.kchunk ? min(p.K, kb + p.kchunk) : p.K;
+  const int nss = (ke - kb + V_GROUPS * V_TK - 1) / (V_GROUPS * V_TK);
+  const int64_t lda = AKF ? p.sAm : p.sAk, ldb = BKF ? p.sBn : p.sBk;
+
+  auto load_super = [&](int ss) {                  // 4 slices x (32 x 8 chunks) per operand = 1024 chunks each
+    float* base = fsm + (ss % V_BUFS) * V_SUPER_FLOATS;
+#pragma unroll
+    for (int c = tid; c < V_GROUPS * 32 * 8; c += V_THREADS) {
+      const int sl = c >> 8, r = (c >> 3) & 31, q = c & 7;
+      const int k0 = kb + (ss * V_GROUPS + sl) * V_TK;
+      float* As = base + sl * V_SLICE_FLOATS;
+      float* Bs = As + 32 * V_PITCH;
+      {
+        const int m = m0 + (AKF ? r : 4 * q), k = k0 + (AKF ? 4 * q : r);
+        const bool ok = m < p.M && k < ke;
+        cp_async16(As + r * V_PITCH + 4 * q, p.A + (ok ? (AKF ? (int64_t)m * lda + k : (int64_t)k * lda + m) : 0), ok);
+      }
+      {
+        const int n = n0 + (BKF ? r : 4 * q), k = k0 + (BKF ? 4 * q : r);
+        const bool ok = n < p.N && k < ke;
+        cp_async16(Bs + r * V_PITCH + 4 * q, p.B + (ok ? (BKF ? (int64_t)n * ldb + k : (int64_t)k * ldb + n) : 0), ok);
+      }
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_super(0);
+  cp_async_commit();
+  if (nss > 1) load_super(1);
+  cp_async_commit();
+  for (int ss = 0; ss < nss; ++ss) {
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* As = fsm + (ss % V_BUFS) * V_SUPER_FLOATS + grp * V_SLICE_FLOATS;
+    const float* Bs = As + 32 * V_PITCH;
+#pragma unroll
+    for (int k4 = 0; k4 < V_TK; k4 += 4) {
+      float a[4][4], b[4][4];                      // [k][i], [k][j]
+      if (AKF) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (ty + 8 * i) * V_PITCH + k4);
+          a[0][i] = v.x; a[1][i] = v.y; a[2][i] = v.z; a[3][i] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(As + (k4 + k) * V_PITCH + ty * 4);
+          a[k][0] = v.x; a[k][1] = v.y; a[k][2] = v.z; a[k][3] = v.w;
+        }
+      }
+      if (BKF) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (tx + 8 * j) * V_PITCH + k4);
+          b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(Bs + (k4 + k) * V_PITCH + tx * 4);
+          b[k][0] = v.x; b[k][1] = v.y; b[k][2] = v.z; b[k][3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[k][i], b[k][j], acc[i][j]);
+    }
+    __syncthreads();                               // every group is done with this buffer
+    if (ss + V_BUFS < nss) load_super(ss + V_BUFS);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // the four groups' partial tiles meet in shared memory: red[grp][m][n]
+  float* red = fsm;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ml = AKF ? ty + 8 * i : ty * 4 + i, nl = BKF ? tx + 8 * j : tx * 4 + j;
+      red[(grp * V_TM + ml) * V_RED_PITCH + nl] = acc[i][j];
+    }
+  __syncthreads();
+  {
+    const int ml = tid >> 3, nl = (tid & 7) * 4;   // 256 threads x 4 consecutive columns
+    float4 v = *reinterpret_cast<const float4*>(red + ml * V_RED_PITCH + nl);
+#pragma unroll
+    for (int g = 1; g < V_GROUPS; ++g) {
+      const float4 w = *reinterpret_cast<const float4*>(red + (g * V_TM + ml) * V_RED_PITCH + nl);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    const int m = m0 + ml;
+    if (m < p.M) {
+      const float o4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + nl + e;
+        if (n >= p.N) continue;
+        float val = o4[e];
+        const int64_t o = (int64_t)m * p.N + n;
+        if (p.kchunk) { atomicAdd(p.C + o, val); continue; }
+        if (p.bias) val += __ldg(p.bias + n);
+        if (p.pre) p.pre[o] = val;
+        if (p.act == 1) val = gelu_exact(val);
+        if (p.residual) val += __ldg(p.residual + o);
+        if (p.accumulate) val += p.C[o];
+        p.C[o] = val;
+      }
+    }
+  }
+}
+
 static bool gemm_pipe_eligible(const GemmArgs& p) {
   static int off = -1;
   if (off < 0) off = getenv("TMF_GEMM_IMPL") != nullptr && atoi(getenv("TMF_GEMM_IMPL")) == 0;   // 0: always gemm_kernel
@@ -638,7 +780,37 @@ static bool gemm_pipe_eligible(const GemmArgs& p) {
   return true;
 }
 
+static int gemm_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TMF_GEMM_IMPL");       // 0: gemm_kernel, 1: gemm_pipe_kernel, 2 (default): gemm_ksplit_kernel
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 static int launch_gemm(GemmArgs& p, cudaStream_t st) {
+  if (gemm_pipe_eligible(p) && gemm_variant() >= 2) {
+    dim3 grid(ceil_div(p.N, V_TN), ceil_div(p.M, V_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
+    const size_t smem = sizeof(float) * V_BUFS * V_SUPER_FLOATS;
+    const bool akf = p.sAk == 1, bkf = p.sBk == 1;
+#define TMF_LAUNCH_KS(AK, BK)                                                                                        \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      TMF_CUDA(cudaFuncSetAttribute(gemm_ksplit_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    gemm_ksplit_kernel<AK, BK><<<grid, V_THREADS, smem, st>>>(p);                                                   \
+  } while (0)
+    if (akf && bkf) TMF_LAUNCH_KS(true, true);
+    else if (akf) TMF_LAUNCH_KS(true, false);
+    else if (bkf) TMF_LAUNCH_KS(false, true);
+    else TMF_LAUNCH_KS(false, false);
+#undef TMF_LAUNCH_KS
+    TMF_LAUNCH_CHECK();
+    return 0;
+  }
   if (gemm_pipe_eligible(p)) {
     dim3 grid(ceil_div(p.N, F_TN), ceil_div(p.M, F_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
     const size_t smem = sizeof(float) * F_STAGES * F_STAGE_FLOATS;
@@ -704,10 +876,17 @@ int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, i
   if (M > 2 * G_SPLIT_K) {             // long reduction over the tokens: split it, partial sums meet in a zeroed dw
     p.kchunk = G_SPLIT_K;
     if (gemm_pipe_eligible(p)) {       // enough K slices to put ~one CTA on every SM, in whole 32-wide slices
-      const int tiles = ceil_div(N, F_TM) * ceil_div(K, F_TN);
-      int splits = ceil_div(148, tiles);
-      if (splits > ceil_div(M, F_TK)) splits = ceil_div(M, F_TK);
-      p.kchunk = ceil_div(ceil_div(M, splits), F_TK) * F_TK;
+      if (gemm_variant() >= 2) {       // whole super-slices (4 x 32 tokens) per CTA
+        const int tiles = ceil_div(N, V_TM) * ceil_div(K, V_TN), ss = V_GROUPS * V_TK;
+        int splits = ceil_div(2 * 148, tiles);
+        if (splits > ceil_div(M, ss)) splits = ceil_div(M, ss);
+        p.kchunk = ceil_div(ceil_div(M, splits), ss) * ss;
+      } else {
+        const int tiles = ceil_div(N, F_TM) * ceil_div(K, F_TN);
+        int splits = ceil_div(148, tiles);
+        if (splits > ceil_div(M, F_TK)) splits = ceil_div(M, F_TK);
+        p.kchunk = ceil_div(ceil_div(M, splits), F_TK) * F_TK;
+      }
     }
     TMF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
   }
