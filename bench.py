@@ -68,8 +68,11 @@ def block1_bytes_per_subject(shape, dim=128, towers=2):
     x = 4.0 * D * H * W
     y = 2.0 * D * H * W * c
     pooled = 2.0 * (D // 2) * (H // 2) * (W // 2) * c
-    return {"tmf_conv1_fwd": towers * (x + y), "tmf_bn_act_pool_fwd@L0": towers * (y + pooled),
-            "tmf_bn_act_pool_bwd_reduce@L0": towers * (y + pooled), "tmf_conv1_bwd_fused": towers * (y + pooled + x)}
+    from transmf_ad_b200.functional import keep_ymax
+    keep = keep_ymax()           # forward also writes ymax (pooled extent); the backward reduction reads ymax + dout only
+    return {"tmf_conv1_fwd": towers * (x + y), "tmf_bn_act_pool_fwd@L0": towers * (y + pooled * (2 if keep else 1)),
+            "tmf_bn_act_pool_bwd_reduce@L0": towers * ((2 * pooled) if keep else (y + pooled)),
+            "tmf_conv1_bwd_fused": towers * (y + pooled + x)}
 
 
 def committed_traffic():

@@ -116,6 +116,18 @@ int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamm
 int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, void* const* out, int out_fp32,
                         int B, int D, int H, int W, int C, int pool, float slope, void* stream);
 
+/* tmf_bn_act_pool_fwd for a MAX pool that also keeps ymax[B,D/2,H/2,W/2,C] (bf16): the stored pre-BN value behind each
+ * window's maximum activation (first maximum in (d,h,w) scan order).  The backward reduction of the layer then runs on
+ * ymax + dout at pooled resolution (tmf_bn_maxpool_bwd_reduce_kept) instead of re-reading y.  networks.py:23-25. */
+int tmf_bn_act_pool_fwd_keepmax(int ng, const void* const* y, const float* const* coef, void* const* out,
+                                void* const* ymax, int out_fp32, int B, int D, int H, int W, int C, float slope,
+                                void* stream);
+/* sums[2*C] (double) = {sum dz, sum dz*xhat} of a max-pool layer from ymax and dout (both at pooled extents Do,Ho,Wo):
+ * same result as tmf_bn_act_pool_bwd_reduce(pool = TMF_POOL_MAX) up to summation order. */
+int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp32, const void* const* ymax,
+                                   const float* const* coef, double* const* sums, int B, int Do, int Ho, int Wo, int C,
+                                   float slope, void* stream);
+
 /* backward, pass 1: sums[2*C] (double, zeroed by the call) = {sum dz, sum dz*xhat} with
  * dz = unpool(dout) * leaky_relu'(z) (max-pool routes to the first maximum in (d,h,w) scan order). */
 int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, const void* const* y,

@@ -460,3 +460,55 @@ def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_
         want = torch.cat([yu64.sum(dim=(0, 1, 2, 3)), (yu64 * yu64).sum(dim=(0, 1, 2, 3))])
         assert torch.allclose(su, want, rtol=1e-5, atol=1e-4)          # statistics of the STORED values
         assert torch.allclose(sd, su, rtol=2e-2, atol=0.5)
+
+
+@pytest.mark.parametrize("shape,C,last", [((2, 9, 11, 7), 32, False), ((1, 8, 8, 8), 16, True), ((2, 5, 6, 13), 64, False)])
+def test_maxpool_kept_maximum_and_pooled_resolution_reduction(shape, C, last):
+    """tmf_bn_act_pool_fwd_keepmax stores the pre-BN value behind every window maximum (torch's arg-max, negative BN
+    scales included); tmf_bn_maxpool_bwd_reduce_kept reproduces the full-resolution reduction from it."""
+    B, D, H, W = shape
+    y = bf16r(g_randn(B, C, D, H, W, seed=1, scale=2.0) + 0.5)
+    gamma = 1 + 0.2 * g_randn(C, seed=2)
+    gamma[::3] *= -1.0                                     # negative scale: the maximum activation sits at the minimum y
+    beta = 0.1 * g_randn(C, seed=3)
+    y_d = to_ndhwc_bf16(y)
+    count = B * D * H * W
+    yd64 = y_d.double()
+    stats = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))]).contiguous()
+    g_d, b_d = gamma.to(DEV), beta.to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    coef = torch.empty(4 * C, dtype=torch.float32, device=DEV)
+    L.call("tmf_bn_finalize", 1, L.ptrs([stats]), L.ptrs([g_d]), L.ptrs([b_d]), L.ptrs([rm]), L.ptrs([rv]), L.ptrs([nbt]),
+           L.ptrs([coef]), C, count, 0.1, 1e-5, 1)
+    Do, Ho, Wo = D // 2, H // 2, W // 2
+    odt = torch.float32 if last else torch.bfloat16
+    out0 = torch.empty((B, Do, Ho, Wo, C), dtype=odt, device=DEV)
+    out1 = torch.empty_like(out0)
+    ymax = torch.empty((B, Do, Ho, Wo, C), dtype=torch.bfloat16, device=DEV)
+    L.call("tmf_bn_act_pool_fwd", 1, L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([out0]), int(last), B, D, H, W, C, L.POOL_MAX, 0.01)
+    L.call("tmf_bn_act_pool_fwd_keepmax", 1, L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([out1]), L.ptrs([ymax]), int(last),
+           B, D, H, W, C, 0.01)
+    assert torch.equal(out0, out1)
+    # torch: arg-max of the activation, gathered from y
+    sc, sh = coef[:C].cpu(), coef[C:2 * C].cpu()
+    z = y * sc.view(1, C, 1, 1, 1) + sh.view(1, C, 1, 1, 1)
+    a = F.leaky_relu(z, 0.01)
+    _, idx = F.max_pool3d(a, 2, 2, return_indices=True)
+    want = y.flatten(2).gather(2, idx.flatten(2)).view_as(idx)
+    got = from_ndhwc(ymax)
+    # ties in the activation are resolved to the first maximum on both sides; values must agree exactly
+    assert torch.equal(got, want)
+    dout = g_randn(B, C, Do, Ho, Wo, seed=9)
+    if not last:
+        dout = bf16r(dout)
+    dout_d = dout.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    if not last:
+        dout_d = dout_d.to(torch.bfloat16)
+    s_full = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    s_kept = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    L.call("tmf_bn_act_pool_bwd_reduce", 1, L.ptrs([dout_d]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([s_full]),
+           B, D, H, W, C, L.POOL_MAX, 0.01)
+    L.call("tmf_bn_maxpool_bwd_reduce_kept", 1, L.ptrs([dout_d]), int(last), L.ptrs([ymax]), L.ptrs([coef]), L.ptrs([s_kept]),
+           B, Do, Ho, Wo, C, 0.01)
+    assert torch.allclose(s_full, s_kept, rtol=1e-4, atol=1e-3)

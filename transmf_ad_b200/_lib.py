@@ -30,6 +30,8 @@ SIGNATURES = {
     "tmf_bn_finalize": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i64, _f, _f, _i, _vp],
     "tmf_bn_act_pool_fwd": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_bn_act_pool_bwd_reduce": [_i, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_bn_act_pool_fwd_keepmax": [_i, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "tmf_bn_maxpool_bwd_reduce_kept": [_i, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_bn_bwd_finalize": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i64, _i, _vp],
     "tmf_bn_act_pool_bwd_apply": [_i, _pp, _i, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -71,6 +71,7 @@ struct ActPoolArgs {
   GroupPtr<const void> dout;          // bwd: gradient w.r.t. fwd output (bf16 or fp32)
   GroupPtr<__nv_bfloat16> dy;         // bwd apply output
   GroupPtr<double> sums;              // bwd reduce output
+  GroupPtr<__nv_bfloat16> ymax;       // fwd (max pool, optional): the pre-BN value behind each window's maximum
   int B, D, H, W, C, pool, fp32io;
   int Do, Ho, Wo;                     // forward output dims (floor)
   int Dc, Hc, Wc;                     // ceil dims (windows that touch any input voxel)
@@ -97,7 +98,12 @@ __device__ __forceinline__ void store8f(void* base, int64_t elem_off, int fp32, 
   }
 }
 
-__global__ void __launch_bounds__(256, 4) bn_act_pool_fwd_kernel(ActPoolArgs p) {
+// KEEP (max pool only): also store ymax[B,Do,Ho,Wo,C] = the stored pre-BN value y whose activation is the window's
+// maximum (first maximum in (d,h,w) scan order, torch's rule).  The backward reduction of a max-pool layer needs y
+// only there (dz is zero elsewhere), so it can run on ymax + dout at pooled resolution instead of re-reading all of y:
+// block 1 re-read 925 MB per step for two per-channel sums.
+template <bool KEEP>
+__global__ void __launch_bounds__(256, KEEP ? 3 : 4) bn_act_pool_fwd_kernel(ActPoolArgs p) {
   const int g = blockIdx.z;
   const int CQ = p.C >> 3;
   const __nv_bfloat16* yg = p.y.p[g];
@@ -132,6 +138,11 @@ __global__ void __launch_bounds__(256, 4) bn_act_pool_fwd_kernel(ActPoolArgs p) 
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (p.pool == TMF_POOL_MAX) ? -INFINITY : 0.f;
+      float yb[8];
+      if (KEEP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yb[j] = 0.f;
+      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int di = 2 * dd + (q >> 2), hi = 2 * ho + ((q >> 1) & 1), wi = 2 * wo + (q & 1);
@@ -141,9 +152,15 @@ __global__ void __launch_bounds__(256, 4) bn_act_pool_fwd_kernel(ActPoolArgs p) 
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(f[j], sc[j], sh[j]);
           const float a = z > 0.f ? z : z * p.slope;
-          o[j] = (p.pool == TMF_POOL_MAX) ? fmaxf(o[j], a) : o[j] + a;
+          if (KEEP) {
+            if (a > o[j]) { o[j] = a; yb[j] = f[j]; }          // strict: the first maximum wins
+          } else {
+            o[j] = (p.pool == TMF_POOL_MAX) ? fmaxf(o[j], a) : o[j] + a;
+          }
         }
       }
+      if (KEEP)
+        *reinterpret_cast<uint4*>(p.ymax.p[g] + ((((int64_t)n * p.Do + dd) * p.Ho + ho) * p.Wo + wo) * p.C + c0) = pack8(yb);
       if (p.pool == TMF_POOL_AVG) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] *= 0.125f;
@@ -308,6 +325,52 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
   }
 }
 
+// Max-pool backward reduction from ymax (see bn_act_pool_fwd_kernel<true>): sum dz, sum dz*xhat over the pooled
+// positions;  dz = dout * LeakyReLU'(scale*ymax + shift),  xhat = (ymax - mean) * invstd.
+__global__ void __launch_bounds__(256) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
+  const int g = blockIdx.z;
+  extern __shared__ float red[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int CQ = p.C >> 3;
+  const int cq = threadIdx.x % CQ, pstep = 256 / CQ;
+  const bool active = (int)threadIdx.x < pstep * CQ;
+  const int c0 = cq * 8;
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = p.coef.p[g][c0 + j];
+    sh[j] = p.coef.p[g][p.C + c0 + j];
+    mu[j] = p.coef.p[g][2 * p.C + c0 + j];
+    is[j] = p.coef.p[g][3 * p.C + c0 + j];
+    s1[j] = 0.f; s2[j] = 0.f;
+  }
+  const __nv_bfloat16* ym = p.ymax.p[g];
+  if (active) {
+#pragma unroll 2
+    for (int pos = blockIdx.x * pstep + threadIdx.x / CQ; pos < npos; pos += gridDim.x * pstep) {
+      const int64_t off = (int64_t)pos * p.C + c0;
+      float f[8], go[8];
+      unpack8(*reinterpret_cast<const uint4*>(ym + off), f);
+      load8f(p.dout.p[g], off, p.fp32io, go);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[j], sc[j], sh[j]);
+        const float dz = z > 0.f ? go[j] : go[j] * p.slope;
+        s1[j] += dz;
+        s2[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[p.C + c0 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
+}
+
 template <bool APPLY>
 static void launch_bwd(const ActPoolArgs& p, dim3 grid, size_t smem, cudaStream_t st) {
   if (p.pool == TMF_POOL_MAX) bn_act_pool_bwd_kernel<APPLY, TMF_POOL_MAX><<<grid, 256, smem, st>>>(p);
@@ -390,7 +453,46 @@ int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, 
       !load_group(p.out, (void* const*)out, ng, true, "out"))
     return 1;
   dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 8, &p.nch, &p.hcr), 1, ng);
-  bn_act_pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  bn_act_pool_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_act_pool_fwd_keepmax(int ng, const void* const* y, const float* const* coef, void* const* out,
+                                void* const* ymax, int out_fp32, int B, int D, int H, int W, int C, float slope,
+                                void* stream) {
+  TMF_CHECK_NG(ng);
+  ActPoolArgs p{};
+  if (fill_args(p, B, D, H, W, C, TMF_POOL_MAX, slope, out_fp32)) return 1;
+  if (!load_group(p.y, (const __nv_bfloat16* const*)y, ng, true, "y") || !load_group(p.coef, coef, ng, true, "coef") ||
+      !load_group(p.out, (void* const*)out, ng, true, "out") ||
+      !load_group(p.ymax, (__nv_bfloat16* const*)ymax, ng, true, "ymax"))
+    return 1;
+  dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 8, &p.nch, &p.hcr), 1, ng);
+  bn_act_pool_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp32, const void* const* ymax,
+                                   const float* const* coef, double* const* sums, int B, int Do, int Ho, int Wo, int C,
+                                   float slope, void* stream) {
+  TMF_CHECK_NG(ng);
+  TMF_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "bn_maxpool_bwd_reduce_kept: C must be a multiple of 8 in [8,1024]");
+  const int64_t npos = (int64_t)B * Do * Ho * Wo;
+  TMF_REQUIRE(npos > 0 && npos * (C / 8) < (1ll << 31), "bn_maxpool_bwd_reduce_kept: bad extent");
+  ActPoolArgs p{};
+  p.B = B; p.C = C; p.slope = slope; p.fp32io = dout_fp32; p.pool = TMF_POOL_MAX;
+  if (!load_group(p.ymax, (__nv_bfloat16* const*)ymax, ng, true, "ymax") || !load_group(p.coef, coef, ng, true, "coef") ||
+      !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
+    return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
+  const int pstep = 256 / (C / 8);
+  int blocks = ceil_div(npos, (int64_t)pstep * 4);                 // >= 4 positions per thread
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 2 * C * sizeof(float), st>>>(p, (int)npos);
   TMF_LAUNCH_CHECK();
   return 0;
 }

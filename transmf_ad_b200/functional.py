@@ -20,6 +20,11 @@ def conv_impl():
     return {"auto": L.CONV_AUTO, "direct": L.CONV_DIRECT, "umma": L.CONV_UMMA}[os.environ.get("TMF_CONV_IMPL", "auto")]
 
 
+def keep_ymax():
+    """TMF_KEEP_YMAX=0: max-pool layers re-read y in the backward reduction (cross-check switch; default keeps ymax)."""
+    return os.environ.get("TMF_KEEP_YMAX", "1") != "0"
+
+
 def _f32c(t):
     """fp32, contiguous, plain torch.Tensor (MONAI MetaTensor inputs are unwrapped)."""
     if hasattr(t, "as_tensor"):
@@ -108,10 +113,18 @@ class SNetFunction(torch.autograd.Function):
             Do, Ho, Wo = _pooled(Dl, Hl, Wl, pool)
             out = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if last else torch.bfloat16, device=dev)
                    for _ in range(ng)]
-            L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), int(last), B, Dl, Hl, Wl, cout,
-                   pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
+            ymax = None
+            if need_grad and pool == L.POOL_MAX and keep_ymax():
+                # max-pool layers keep the pre-BN value behind every window maximum: the backward reduction then reads
+                # 1/8 of the voxels instead of all of y
+                ymax = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                L.call("tmf_bn_act_pool_fwd_keepmax", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), L.ptrs(ymax), int(last),
+                       B, Dl, Hl, Wl, cout, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
+            else:
+                L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), int(last), B, Dl, Hl, Wl, cout,
+                       pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
             if need_grad:
-                saved.append((act, y, coef, wd, dims))
+                saved.append((act, y, coef, wd, dims, ymax))
             act = out
             dims = (Do, Ho, Wo)
         ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
@@ -138,11 +151,16 @@ class SNetFunction(torch.autograd.Function):
         pgrads = [None] * (ng * 7 * 4)
         for l in range(len(spec.layers) - 1, -1, -1):
             cin, cout, ks, pool = spec.layers[l]
-            act, y, coef, wd, (Dl, Hl, Wl) = saved[l]
+            act, y, coef, wd, (Dl, Hl, Wl), ymax = saved[l]
             count = B * Dl * Hl * Wl
             sums = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0))
-            L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
-                   B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
+            if ymax is not None:
+                L.call("tmf_bn_maxpool_bwd_reduce_kept", ng, L.ptrs(dout), dout_fp32, L.ptrs(ymax), L.ptrs(coef),
+                       L.ptrs(sums), B, Dl // 2, Hl // 2, Wl // 2, cout, LRELU_SLOPE,
+                       tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
+            else:
+                L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
+                       B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
             dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
