@@ -171,6 +171,37 @@ __global__ void __launch_bounds__(256, KEEP ? 3 : 4) bn_act_pool_fwd_kernel(ActP
   }
 }
 
+// Per-channel partial sums of a block -> red[2][C] (shared).  A thread owns channel chunk cq = threadIdx.x % CQ for the
+// whole kernel; when CQ is a power of two (C = 32, 64, 128, 256) the lanes of a warp that share a chunk are first
+// combined with shuffles, so a block issues 8*CQ*16 shared atomics instead of 256*16 on the same few addresses
+// (measured: the atomics, not HBM, bounded the small reductions).
+__device__ __forceinline__ void block_channel_sums(float* red, int C, int CQ, int c0, bool active, float (&s1)[8],
+                                                   float (&s2)[8]) {
+  const bool pow2 = (CQ & (CQ - 1)) == 0 && CQ <= 32;          // block-uniform; then every thread is active
+  if (pow2) {
+    for (int off = 16; off >= CQ; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+      }
+    }
+    if ((int)(threadIdx.x & 31) < CQ) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[c0 + j], s1[j]);
+        atomicAdd(&red[C + c0 + j], s2[j]);
+      }
+    }
+  } else if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[c0 + j], s1[j]);
+      atomicAdd(&red[C + c0 + j], s2[j]);
+    }
+  }
+}
+
 // Backward over 2x2x2 windows (or single voxels when pool == NONE).  REDUCE: accumulate sum dz, sum dz*xhat.
 // APPLY: write dy = scale * (dz - m1 - xhat*m2) for every existing input voxel (incl. those dropped by floor pooling).
 //
@@ -313,13 +344,7 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
    }
   }
   if (!APPLY) {
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[c0 + j], s1[j]);
-        atomicAdd(&red[p.C + c0 + j], s2[j]);
-      }
-    }
+    block_channel_sums(red, p.C, CQ, c0, active, s1, s2);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
   }
@@ -361,12 +386,8 @@ __global__ void __launch_bounds__(256) bn_maxpool_bwd_reduce_kept_kernel(ActPool
         s2[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s2[j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[p.C + c0 + j], s2[j]);
-    }
   }
+  block_channel_sums(red, p.C, CQ, c0, active, s1, s2);
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
 }
@@ -490,7 +511,7 @@ int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp3
   TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
   const int pstep = 256 / (C / 8);
   int blocks = ceil_div(npos, (int64_t)pstep * 4);                 // >= 4 positions per thread
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 2 * C * sizeof(float), st>>>(p, (int)npos);
   TMF_LAUNCH_CHECK();

@@ -31,6 +31,8 @@ struct C1UParams {
   long long M;
   int ntiles;
   uint32_t idesc, tmem_cols;
+  int debug;          // timing-only bring-up switches (TMF_C1U_DEBUG): 1 = one MMA pair instead of three, 2 = no stores,
+                      // 4 = no image loads.  Results are wrong with any of them set.
 };
 
 // byte offset of 16-byte chunk j of row r inside a K-major, 64-byte-row, 64B-swizzled tile (tile base 1024-aligned)
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const bool ok = dok[kd] && hok[kh] && wok[kw];
-            v[(kd * 3 + kh) * 3 + kw] = ok ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
+            v[(kd * 3 + kh) * 3 + kw] = (ok && !(p.debug & 4)) ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
           }
     };
     auto advance = [&]() {
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(ah + 2u * k), desc_hi | (uint64_t)(wh + 2u * k), p.idesc, k ? 1u : 0u);
+          if (p.debug & 1) continue;
           mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(al + 2u * k), desc_hi | (uint64_t)(wh + 2u * k), p.idesc, 1u);
           mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(ah + 2u * k), desc_hi | (uint64_t)(wl + 2u * k), p.idesc, 1u);
         }
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
-          if (valid) {
+          if (valid && !(p.debug & 2)) {
             uint4* yrow = reinterpret_cast<uint4*>(yg + m * p.cout + c * 32);
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) yrow[qd] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
@@ -488,6 +491,10 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   p.ntiles = (int)((p.M + 127) / 128);
   p.idesc = make_idesc_bf16(128, cout, 0, 0);
   p.tmem_cols = (cout == 32) ? 64 : 128;
+  {
+    const char* e = getenv("TMF_C1U_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) {
     TMF_REQUIRE(x[g] && w[g] && y[g], "conv1_fwd_umma: NULL device pointer");
