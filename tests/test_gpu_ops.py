@@ -512,3 +512,18 @@ def test_maxpool_kept_maximum_and_pooled_resolution_reduction(shape, C, last):
     L.call("tmf_bn_maxpool_bwd_reduce_kept", 1, L.ptrs([dout_d]), int(last), L.ptrs([ymax]), L.ptrs([coef]), L.ptrs([s_kept]),
            B, Do, Ho, Wo, C, 0.01)
     assert torch.allclose(s_full, s_kept, rtol=1e-4, atol=1e-3)
+
+
+def test_device_prefetcher_yields_every_batch_and_reuses_buffers():
+    from transmf_ad_b200.train import DevicePrefetcher
+    host = [(torch.full((4, 3), float(i)).pin_memory(), torch.tensor([i, i + 1]).pin_memory()) for i in range(5)]
+    pf, seen = None, []
+    for epoch in range(2):
+        pf = DevicePrefetcher(iter(host), DEV, reuse=pf)
+        ptrs = set()
+        for a, b in pf:
+            seen.append((float(a.sum()), b.tolist()))
+            ptrs.add(a.data_ptr())
+        assert len(ptrs) == 2                               # two device slots, recycled
+    want = [(12.0 * i, [i, i + 1]) for i in range(5)] * 2
+    assert seen == want

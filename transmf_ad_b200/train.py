@@ -113,12 +113,20 @@ class DevicePrefetcher:
     valid until the next ``next()`` call has returned, and everything that reads it must have been enqueued on the
     current stream by then (single-threaded use)."""
 
-    def __init__(self, host_batches, device):
+    def __init__(self, host_batches, device, reuse=None):
+        """``reuse``: an exhausted prefetcher of the same batch shapes whose side stream and device buffers are taken over
+        (one per epoch: no cudaMalloc / stream creation after the first)."""
         self.it = iter(host_batches)
         self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.slots = [None, None]
-        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        if reuse is not None:
+            self.stream, self.slots, self.consumed = reuse.stream, reuse.slots, reuse.consumed
+            if reuse._last is not None:                     # readers of its last batch are already enqueued
+                reuse.consumed[reuse._last].record(torch.cuda.current_stream(self.device))
+                reuse._last = None
+        else:
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.slots = [None, None]
+            self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self.k = 0
         self._last = None
         self._next = None
