@@ -42,7 +42,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     gb = ng * B * D * H * W * (4 + 2 * cout) / 1e9
-    print(f"conv1 fwd B={B} x{ng}: {ms * 1e3:7.1f} us  {gb / ms:7.1f} GB/s algorithmic (TMF_C1U_DEBUG={os.environ.get('TMF_C1U_DEBUG', '0')})",
+    print(f"conv1 fwd B={B} x{ng}: {ms * 1e3:7.1f} us  {gb / ms:7.2f} TB/s algorithmic (TMF_C1U_DEBUG={os.environ.get('TMF_C1U_DEBUG', '0')})",
           flush=True)
 
 

@@ -45,3 +45,35 @@ def test_sass_is_sm100a_only():
         pytest.skip("cuobjdump unavailable")
     archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
     assert archs == {"100a"}, archs
+
+
+def test_streamed_weight_conv_plans_for_the_bench_layers(built_lib):
+    """Host-only introspection of the generic tcgen05 forward/dgrad kernel's launch plan: at the
+    bench shape (B = 8, two towers) conv3.3 dgrad applies each weight box to three 128-row tiles with two issuer warps
+    and one accumulator set, conv4.0 dgrad to two tiles, and conv4.0 forward keeps one tile per pass (wave
+    quantisation); the 1x1x1 layer keeps its weights resident."""
+    import ctypes as C
+    out = (C.c_int * 8)()
+
+    def plan(D, H, W, cin, cout, ks, B=8, ng=2):
+        assert built_lib.tmf_conv3d_umma_plan_info(ng, B, D, H, W, cin, cout, ks, out) == 0
+        keys = ("ok", "mt", "issuers", "acc_sets", "a_stages", "b_stages", "tiles_per_plane", "resident")
+        return dict(zip(keys, list(out)))
+
+    p = plan(22, 27, 22, 128, 64, 3)
+    assert (p["mt"], p["issuers"], p["acc_sets"], p["resident"]) == (3, 2, 1, 0) and p["b_stages"] % 2 == 0
+    p = plan(11, 13, 11, 256, 128, 3)
+    assert (p["mt"], p["acc_sets"], p["resident"]) == (2, 2, 0)
+    p = plan(11, 13, 11, 128, 256, 3)
+    assert (p["mt"], p["issuers"], p["resident"]) == (1, 1, 0)
+    p = plan(11, 13, 11, 256, 128, 1)
+    assert p["resident"] == 1 and p["mt"] == 1
+    # every plan respects the 512-column TMEM budget
+    for args in ((22, 27, 22, 128, 64, 3), (11, 13, 11, 256, 128, 3), (11, 13, 11, 128, 256, 3), (45, 54, 45, 32, 64, 3),
+                 (19, 23, 19, 128, 64, 3), (32, 32, 19, 128, 64, 3)):
+        for B in (1, 2, 8, 32):
+            p = plan(*args, B=B)
+            cout = args[4]
+            assert p["ok"] == 1 and p["acc_sets"] * p["issuers"] * p["mt"] * cout <= 512
+    # unsupported channel counts are refused, not mis-planned
+    assert built_lib.tmf_conv3d_umma_plan_info(2, 8, 22, 27, 22, 24, 64, 3, out) != 0

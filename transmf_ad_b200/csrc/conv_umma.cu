@@ -1,16 +1,20 @@
-// conv_umma.cu -- implicit-GEMM Conv3d (3x3x3 pad 1, or 1x1x1) forward / dgrad on the 5th-gen tensor cores:
+// conv_umma.cu -- generic implicit-GEMM Conv3d (3x3x3 pad 1, or 1x1x1) forward / dgrad on the 5th-gen tensor cores:
 // TMA-staged NDHWC bf16 operands, tcgen05.mma with fp32 accumulators in TMEM, fused bias + bf16 store +
-// BatchNorm statistics epilogue.  One persistent, warp-specialised CTA per SM.
+// BatchNorm statistics epilogue.  One persistent, warp-specialised CTA per SM.  It takes the layers the
+// input-stationary kernel (conv_umma_col.cu) does not: Cin >= 128 (conv3.3 dgrad, conv4.0) and 1x1x1 (conv4.3).
 //
 // Mapping.  For one sample n and output plane d the (h,w) positions are linearised with a padded row pitch
-// Wp = W + 2*hw (hw = ks/2):  q = h*Wp + w'.  An M tile is 128 consecutive q.  For tap (kd,kh,kw) the A operand of the
-// tile is the same 128-row window of the *padded* input plane d+kd-hw shifted by kh*Wp + kw rows, so ONE TMA box
+// Wp = W + 2*hw (hw = ks/2):  q = h*Wp + w'.  A super-tile is mt*128 consecutive q.  For tap (kd,kh,kw) the A operand of
+// a 128-row tile is the same window of the *padded* input plane d+kd-hw shifted by kh*Wp + kw rows, so ONE TMA box
 // (channels x Wp x NH rows, out-of-bounds zero fill = the convolution padding) per (kd, 64-channel chunk) feeds all
 // ks*ks taps of that plane from shared memory: each tap's tcgen05.mma simply uses a shared-memory descriptor whose
 // start address is advanced by (shift * row bytes).  Rows with w' >= W (2 per output row) or h >= H are computed and
 // discarded in the epilogue.  Weights wf[tap][Cout][Cin] are the K-major B operand, one TMA box per (tap, chunk);
-// they stay resident in shared memory for the whole kernel when they fit (the two 32-channel layers) and are streamed
-// through a ring otherwise.
+// they stay resident in shared memory for the whole kernel when they fit and are streamed through a ring otherwise.
+//
+// Streamed weights are bound by the NUMBER of TMA boxes (~500 cycles each, measured), so a tap's box is applied to all
+// mt tiles of the super-tile (mt accumulators in TMEM) and, where N is narrow, two issuer warps share the taps; the
+// host plan (make_plan) picks mt / issuers / accumulator sets with a small cost model -- see DESIGN.md section 3.2.
 #include <cuda.h>
 
 #include "common.cuh"
