@@ -12,6 +12,12 @@
  *     towers run in one launch (grid.z = group).
  *   - activations are NDHWC ("channels-last-3d"): index ((((n*D + d)*H + h)*W + w)*C + c).
  *   - bf16 buffers are passed as void*; fp32 as float*; per-channel statistics accumulate in double.
+ *   - DETERMINISM.  Per-channel statistics buffers (`stats` of the conv forward entry points, `sums` of the BatchNorm
+ *     backward reductions) are double[TMF_STAT_ROWS][2*C]: row r holds the partial {sum, sum of squares} (or {sum dz,
+ *     sum dz*xhat}) of producer CTA r of that tower.  A producer launches at most TMF_STAT_ROWS CTAs per tower, every
+ *     row is written exactly once per call (rows without a CTA are cleared by the kernel, so callers never zero the
+ *     buffer) and tmf_bn_finalize / tmf_bn_bwd_finalize add the rows in index order: no floating-point atomics, bitwise
+ *     reproducible run to run.  (The CUDA-core bring-up kernels, TMF_CONV_DIRECT, still add with atomics.)
  */
 #ifndef TMF_H_
 #define TMF_H_
@@ -24,6 +30,8 @@ extern "C" {
 #endif
 
 #define TMF_MAX_GROUPS 2
+/* rows of a per-channel statistics buffer (see DETERMINISM above): 2 CTAs per SM of a 148-SM B200 */
+#define TMF_STAT_ROWS 296
 
 /* pooling modes fused behind BatchNorm + LeakyReLU (reference models/networks.py:25,34,43 MaxPool3d(2,2);
  * :52 AvgPool3d(2,2); floor mode) */
@@ -44,6 +52,8 @@ int tmf_version(void);
 int tmf_check_device(void);
 /* number of kernel launches issued through this library by the calling process so far */
 int64_t tmf_launch_count(void);
+/* TMF_STAT_ROWS, for callers that size statistics buffers without the header */
+int tmf_stat_rows(void);
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* sNet conv stack -- replaces nn.Conv3d / nn.BatchNorm3d / nn.LeakyReLU / nn.MaxPool3d / nn.AvgPool3d of        */
@@ -55,15 +65,19 @@ int tmf_pack_conv_weights(int ng, const float* const* w, void* const* wf, void* 
                           int cout, int cin, int ksize, void* stream);
 
 /* conv1.0 (Cin = 1, 3x3x3, pad 1), fp32 input and weights, bf16 output y[B,D,H,W,Cout], per-channel
- * sum / sum-of-squares of the stored (rounded) y into stats[2*Cout] (double; zeroed by the call).
+ * sum / sum-of-squares of the stored (rounded) y into stats[TMF_STAT_ROWS][2*Cout] (double partial rows).
  * impl: TMF_CONV_AUTO / _DIRECT (CUDA cores, fp32) / _UMMA (tcgen05 on an in-smem im2col with a bf16 hi/lo split of
  * both operands, fp32-level accuracy).   reference models/networks.py:22 */
 int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const float* const* bias,
                   void* const* y, double* const* stats, int B, int D, int H, int W, int cout, int impl, void* stream);
 
-/* dW[Cout][27] (+ optionally dbias) of conv1.0 from dy (bf16) and x (fp32); dw is overwritten. */
+/* dW[Cout][27] of conv1.0 from dy (bf16) and x (fp32); dw is overwritten.  `ws`: caller-owned, 16-byte aligned scratch
+ * of at least tmf_conv1_wgrad_workspace_bytes(...) bytes (per-CTA partial sums of the tcgen05 path, added in CTA
+ * order -> deterministic); may be NULL when that returns 0 (CUDA-core bring-up path).
+ * reference models/networks.py:22 (autograd backward of Conv3d(1,32,3,p1)) */
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw,
-                    int B, int D, int H, int W, int cout, int impl, void* stream);
+                    int B, int D, int H, int W, int cout, int impl, void* ws, size_t ws_bytes, void* stream);
+int64_t tmf_conv1_wgrad_workspace_bytes(int ng, int impl, int W, int cout);
 
 /* Block-1 backward in one pass over y: the BatchNorm + LeakyReLU + MaxPool3d(2,2) backward "apply" (what
  * tmf_bn_act_pool_bwd_apply computes with pool = TMF_POOL_MAX) fused with the conv1.0 weight gradient, so dy of
@@ -122,13 +136,13 @@ int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, 
 int tmf_bn_act_pool_fwd_keepmax(int ng, const void* const* y, const float* const* coef, void* const* out,
                                 void* const* ymax, int out_fp32, int B, int D, int H, int W, int C, float slope,
                                 void* stream);
-/* sums[2*C] (double) = {sum dz, sum dz*xhat} of a max-pool layer from ymax and dout (both at pooled extents Do,Ho,Wo):
+/* sums[TMF_STAT_ROWS][2*C] (double partial rows) = {sum dz, sum dz*xhat} of a max-pool layer from ymax and dout (both at pooled extents Do,Ho,Wo):
  * same result as tmf_bn_act_pool_bwd_reduce(pool = TMF_POOL_MAX) up to summation order. */
 int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp32, const void* const* ymax,
                                    const float* const* coef, double* const* sums, int B, int Do, int Ho, int Wo, int C,
                                    float slope, void* stream);
 
-/* backward, pass 1: sums[2*C] (double, zeroed by the call) = {sum dz, sum dz*xhat} with
+/* backward, pass 1: sums[TMF_STAT_ROWS][2*C] (double partial rows) = {sum dz, sum dz*xhat} with
  * dz = unpool(dout) * leaky_relu'(z) (max-pool routes to the first maximum in (d,h,w) scan order). */
 int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, const void* const* y,
                                const float* const* coef, double* const* sums, int B, int D, int H, int W, int C,

@@ -42,6 +42,10 @@ CASES = {
     "model_transformer_res": ("model_transformer_res", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=256, dropout=0.), 3, (32, 32, 32), 5),
     "model_cnn": ("model_CNN", dict(dim=128), 2, (32, 32, 32), 6),
     "model_ad_dim64": ("model_ad", dict(dim=64, depth=1, heads=2, dim_head=16, mlp_dim=96, dropout=0.), 8, (32, 36, 32), 7),
+    # BASELINE configurations at the full 91x109x91 volume: C3 / C2 at batch 8, C1 at batch 2
+    "model_ad_full_b8": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 8, (91, 109, 91), 14),   # seed scanned: every train-mode margin > 0.3
+    "model_cnn_ad_full_b8": ("model_CNN_ad", dict(dim=128), 8, (91, 109, 91), 9),
+    "model_ad_full_b2": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 2, (91, 109, 91), 10),
 }
 GRAD_SAMPLE = 48
 
@@ -162,6 +166,10 @@ def main():
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     keys = {}
+    kpath = os.path.join(args.out, "keys.json")
+    if os.path.exists(kpath):
+        with open(kpath) as f:
+            keys = json.load(f)
     for name in args.cases:
         k, manifest = run_case(name, refmods, args.out)
         keys[k] = manifest

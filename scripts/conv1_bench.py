@@ -26,7 +26,7 @@ def main():
     w = [torch.randn((cout, 1, 3, 3, 3), device=dev) * 0.2 for _ in range(ng)]
     b = [torch.zeros(cout, device=dev) for _ in range(ng)]
     y = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
-    stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0))
+    stats = L.stat_buffers(ng, cout, dev)
 
     def fn():
         L.call("tmf_conv1_fwd", ng, L.ptrs(x), L.ptrs(w), L.ptrs(b), L.ptrs(y), L.ptrs(stats), B, D, H, W, cout, L.CONV_AUTO)

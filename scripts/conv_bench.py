@@ -45,7 +45,7 @@ def main():
         y = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
         da = [torch.empty((B, D, H, W, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
         dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
-        stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0))
+        stats = L.stat_buffers(ng, cout, dev)
         ws = TF.wgrad_workspace(ng, L.CONV_AUTO, B, D, H, W, cin, cout, ks, dev)
         flops = 2.0 * B * D * H * W * cout * cin * taps * ng
 

@@ -1,0 +1,130 @@
+"""2+-rank NCCL data-parallel parity worker (launched by tests/test_gpu_dp_nccl.py through torch.distributed.run).
+
+Each rank runs ``model_CNN_ad`` / ``model_ad`` on its shard of a global batch; checks on rank 0:
+  1. eager loop: gradients after ``GradBucketReducer.finish()`` == mean over ranks of the per-rank gradients (all-gathered;
+     exact up to the all-reduce's summation order, 1e-6) and are aligned with the mean of the per-shard Oracle-A
+     gradients (CPU oracle with bf16 rounding emulated; per-rank BatchNorm statistics = DDP semantics);
+  2. timed path: k replays of the single-graph ``GraphedTrainStep`` (all-reduce captured inside, overlapped) + ``FusedAdam``
+     leave the same parameters as k eager data-parallel steps + ``torch.optim.Adam``, on every rank, and all ranks agree.
+Prints ``DP_NCCL_OK`` on success.
+"""
+import copy
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import restatement as R                                     # noqa: E402  (checker only)
+from tests import helpers as H                                           # noqa: E402
+from transmf_ad_b200.dp import GradBucketReducer, shard_slice            # noqa: E402
+from transmf_ad_b200.models import mymodel as M                          # noqa: E402
+from transmf_ad_b200.optim import FusedAdam                              # noqa: E402
+from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state   # noqa: E402
+from transmf_ad_b200.train import GraphedTrainStep                       # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    kind = os.environ.get("DP_MODEL", "model_ad")
+    kwargs = dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.) if kind == "model_ad" else dict(dim=128)
+    per, shape = 4, (33, 36, 34)
+    GB = per * world
+    label = make_labels(GB)
+    mri = make_volumes(GB, shape, seed=41, labels=label)
+    pet = make_volumes(GB, shape, seed=42, labels=label)
+    sl = shard_slice(GB, rank, world)
+    state = procedural_state(getattr(M, kind)(**kwargs).state_dict(), seed=5)
+
+    def fresh():
+        m = getattr(M, kind)(**kwargs)
+        m.load_state_dict(state)
+        m = m.to(dev).train()
+        H.set_head_dropout(m, 0.0)
+        return m
+
+    def loss_fn(outs, lab):
+        ce, ad, total = H.losses(outs, lab)
+        return total, ce, ad
+
+    batch = (mri[sl].to(dev), pet[sl].to(dev), label[sl].to(dev))
+    # ---- 1. eager: reduced gradients == mean of the ranks' own gradients, and ~ mean of per-shard Oracle-A gradients
+    model = fresh()
+    red = GradBucketReducer(model=model).install()
+    own = fresh()                                                        # same step without any reducer
+    loss_fn(own(*batch[:2]), batch[2])[0].backward()
+    loss_fn(model(*batch[:2]), batch[2])[0].backward()
+    red.finish()
+    torch.cuda.synchronize()
+    assert len(red.buckets) >= 2 and red.allreduce_launches == len(red.buckets)
+    names = [k for k, _ in model.named_parameters()]
+    for k, p, q in zip(names, model.parameters(), own.parameters()):
+        gathered = [torch.empty_like(q.grad) for _ in range(world)]
+        dist.all_gather(gathered, q.grad.contiguous())
+        mean = torch.stack(gathered).mean(0)
+        err = float((p.grad - mean).abs().max())
+        assert err <= 1e-6 + 1e-5 * float(mean.abs().max()), f"rank {rank} {k}: reduced gradient differs from the mean ({err})"
+    if rank == 0:
+        acc = None
+        for r in range(world):                                           # Oracle-A on every shard, same weights
+            s = shard_slice(GB, r, world)
+            sd = R.clone_state(state)
+            o = H.oracle_forward(kind, sd, (mri[s], pet[s]), kwargs, True, 0.0, rnd=R.bf16_round)
+            H.losses(o, label[s])[2].backward()
+            g = {k: sd[k].grad for k in names}
+            acc = g if acc is None else {k: acc[k] + g[k] for k in names}
+        ours = torch.cat([p.grad.detach().cpu().flatten() for k, p in zip(names, model.parameters())
+                          if not H.is_conv_bias(k) and float(acc[k].norm()) >= 1e-5 * world])
+        ref = torch.cat([(acc[k] / world).flatten() for k in names
+                         if not H.is_conv_bias(k) and float(acc[k].norm()) >= 1e-5 * world])
+        cos = H.cosine(ours, ref)
+        print(f"[dp] {kind} world {world}: buckets {red.bucket_layout()}; whole-model gradient cosine vs mean of per-shard "
+              f"Oracle-A gradients {cos:.4f}", flush=True)
+        assert cos >= 0.95, cos
+    red.remove()
+    # ---- 2. timed path: single-graph replay + FusedAdam == eager DP + torch.optim.Adam
+    steps, lr = 3, 1e-3
+    ref_m = fresh()
+    ref_red = GradBucketReducer(model=ref_m).install()
+    ref_opt = torch.optim.Adam(ref_m.parameters(), lr=lr)
+    for _ in range(steps):
+        ref_opt.zero_grad()
+        loss_fn(ref_m(*batch[:2]), batch[2])[0].backward()
+        ref_red.finish()
+        ref_opt.step()
+    ref_red.remove()
+    g_m = fresh()
+    g_red = GradBucketReducer(model=g_m)
+    g_opt = FusedAdam(g_m.parameters(), lr=lr)
+    step = GraphedTrainStep(g_m, g_opt, loss_fn, batch[:2], batch[2], reducer=g_red, warmup=3)
+    for _ in range(steps):
+        step(batch[:2], batch[2])
+    torch.cuda.synchronize()
+    sd_r, sd_g = ref_m.state_dict(), g_m.state_dict()
+    for k, v in sd_r.items():
+        w = sd_g[k]
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(w) == steps, k
+            continue
+        err = (w - v).abs()
+        assert bool((err <= 5e-7 + 5e-6 * v.abs()).all()), f"rank {rank} {k}: graph path differs from eager DP ({float(err.max()):.3e})"
+        if "running" not in k:                                            # replicas stay identical
+            other = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(other, w.contiguous())
+            assert all(torch.equal(other[0], o) for o in other), f"{k}: replicas diverged"
+    dist.barrier()
+    if rank == 0:
+        print(f"[dp] graph path: {step.launches_per_step} libtmf launches per step, split={step.split}", flush=True)
+        print("DP_NCCL_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

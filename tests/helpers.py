@@ -140,6 +140,13 @@ def parity_report(name, device="cuda"):
     rep["logit_err_B"] = [float((o.detach().cpu() - b).abs().max()) for o, b in zip(outs, gold["train_outs"])]
     rep["logit_err_A_vs_B"] = [float((a.detach() - b).abs().max()) for a, b in zip(o_outs, gold["train_outs"])]
     rep["loss"] = (float(total.detach()), float(o_total.detach()), gold["train_losses"][2])
+    # train-mode labels (argmax of the classification logits) against the REAL reference's
+    t_ref = gold["train_outs"][0]
+    t_margin = (t_ref[:, 0] - t_ref[:, 1]).abs()
+    rep["train_margin_min"] = float(t_margin.min())
+    rep["train_argmax_equal"] = bool(torch.equal(outs[0].detach().cpu().argmax(1), t_ref.argmax(1)))
+    rep["train_argmax_equal_sure"] = lambda tol: bool(torch.equal(outs[0].detach().cpu().argmax(1)[t_margin > 2 * tol],
+                                                                  t_ref.argmax(1)[t_margin > 2 * tol]))
     grads = {}
     for k, p in model.named_parameters():
         g = None if p.grad is None else p.grad.detach().cpu()

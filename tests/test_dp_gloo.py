@@ -39,7 +39,8 @@ def _worker(rank, world, port, q):
             loss = torch.nn.functional.cross_entropy(model(x[sl]), y[sl])
             loss.backward()
             red.finish()
-        grads = [p.grad.clone() for p in model.parameters()]
+        # plain lists: tensors would travel as shared-memory handles served by this (soon exiting) process
+        grads = [p.grad.tolist() for p in model.parameters()]
         q.put((rank, grads, red.bucket_layout(), red.allreduce_launches))
     finally:
         dist.destroy_process_group()
@@ -72,7 +73,7 @@ def test_bucketed_allreduce_equals_mean_of_shard_gradients():
     for rank, grads, layout, launches in results:
         assert len(layout) > 1 and launches == 2 * len(layout)
         for a, b in zip(grads, expect):
-            assert torch.allclose(a, b, atol=1e-6), rank
+            assert torch.allclose(torch.tensor(a), b, atol=1e-6), rank
 
 
 def test_shard_slice_partitions_the_batch():

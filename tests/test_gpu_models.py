@@ -118,8 +118,8 @@ def test_grouped_towers_equal_separate_towers():
 
 
 def test_full_size_volume_properties():
-    """BASELINE-sized input (91x109x91): shapes, finiteness, BN statistics self-consistency and determinism of the
-    forward; linearity of the gradient-reversal branch in lambda."""
+    """BASELINE-sized input (91x109x91): shapes, finiteness and bitwise determinism of the forward (oracle parity at
+    this size: tests/test_gpu_fullsize.py)."""
     from transmf_ad_b200.synthetic import make_labels, make_volumes
     torch.manual_seed(0)
     model = M.model_ad(128, 3, 4, 32, 512, 0.).to(DEV).train()
@@ -133,8 +133,8 @@ def test_full_size_volume_properties():
     o2 = model(mri, pet)
     for a, b in zip(o1, o2):
         assert a.shape == (2, 2) and torch.isfinite(a).all()
-        # run-to-run: fp32 atomics in the BN statistics are order-dependent and BatchNorm1d over 2 samples amplifies
-        assert float((a - b).abs().max()) < 0.1
+        # run-to-run: per-CTA partial statistics added in a fixed order (include/tmf.h, DETERMINISM) -> bit-identical
+        assert torch.equal(a, b)
     H.losses(o2, label.to(DEV))[2].backward()
     for k, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k

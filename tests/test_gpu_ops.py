@@ -53,14 +53,15 @@ def test_conv1_fwd_and_stats(impl, shape, cout):
     b = g_randn(cout, seed=3, scale=0.1)
     xd, wd_, bd = x.to(DEV), w.to(DEV), b.to(DEV)
     y = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV)
-    stats = torch.empty(2 * cout, dtype=torch.float64, device=DEV)
+    stats = L.stat_buffers(1, cout, DEV)[0]
     L.call("tmf_conv1_fwd", 1, L.ptrs([xd]), L.ptrs([wd_]), L.ptrs([bd]), L.ptrs([y]), L.ptrs([stats]), B, D, H, W, cout, impl)
     ref = F.conv3d(x, w, b, padding=1)
     got = from_ndhwc(y)
     assert max_rel(got, ref) < 6e-3
     yf = y.double()
-    assert torch.allclose(stats[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
-    assert torch.allclose(stats[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
+    stot = stats.sum(0)          # rows = per-CTA partials (include/tmf.h, DETERMINISM)
+    assert torch.allclose(stot[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(stot[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -89,7 +90,7 @@ def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
     a_d, dy_d, b_d = to_ndhwc_bf16(a), to_ndhwc_bf16(dy), bias.to(DEV)
     # ---- forward (+ stats)
     y = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV)
-    stats = torch.empty(2 * cout, dtype=torch.float64, device=DEV)
+    stats = L.stat_buffers(1, cout, DEV)[0]
     L.call("tmf_conv3d_fwd", 1, L.ptrs([a_d]), L.ptrs([wf]), L.ptrs([b_d]), L.ptrs([y]), L.ptrs([stats]),
            B, D, H, W, cin, cout, ks, impl)
     a_ref = a.clone().requires_grad_(True)
@@ -97,8 +98,9 @@ def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
     ref = F.conv3d(a_ref, w_ref, bias, padding=ks // 2)
     assert max_rel(from_ndhwc(y), ref.detach()) < 6e-3, "forward"
     yf = y.double()
-    assert torch.allclose(stats[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
-    assert torch.allclose(stats[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
+    stot = stats.sum(0)
+    assert torch.allclose(stot[:cout].cpu(), yf.sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(stot[cout:].cpu(), (yf * yf).sum(dim=(0, 1, 2, 3)).cpu(), rtol=1e-5, atol=1e-4)
     # ---- dgrad and wgrad
     ref.backward(dy)
     da = torch.empty((B, D, H, W, cin), dtype=torch.bfloat16, device=DEV)
@@ -139,7 +141,9 @@ def test_conv1_wgrad(impl, shape):
     F.conv3d(x, w, None, padding=1).backward(dy)
     dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=DEV)
     dy_d, x_d = to_ndhwc_bf16(dy), x.to(DEV)          # keep references: L.ptrs() only takes raw addresses
-    L.call("tmf_conv1_wgrad", 1, L.ptrs([dy_d]), L.ptrs([x_d]), L.ptrs([dw]), B, D, H, W, cout, impl)
+    nws = int(L.load().tmf_conv1_wgrad_workspace_bytes(1, impl, W, cout))
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=DEV)
+    L.call("tmf_conv1_wgrad", 1, L.ptrs([dy_d]), L.ptrs([x_d]), L.ptrs([dw]), B, D, H, W, cout, impl, L.ptr(ws), nws)
     assert rel_l2(dw.cpu(), w.grad) < 1e-4
 
 
@@ -159,7 +163,8 @@ def test_bn_lrelu_pool_forward_backward(pool, shape, C, training, last):
     y_d = to_ndhwc_bf16(y)
     count = B * D * H * W
     yd64 = y_d.double()
-    stats = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))]).contiguous()
+    stats = torch.zeros((L.stat_rows(), 2 * C), dtype=torch.float64, device=DEV)      # totals in row 0, other rows empty
+    stats[0] = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))])
     g_d, b_d = gamma.to(DEV), beta.to(DEV)
     rm, rv = rm0.clone().to(DEV), rv0.clone().to(DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
@@ -194,7 +199,7 @@ def test_bn_lrelu_pool_forward_backward(pool, shape, C, training, last):
     dout_d = dout.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
     if not last:
         dout_d = dout_d.to(torch.bfloat16)
-    sums = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    sums = L.stat_buffers(1, C, DEV)[0]
     L.call("tmf_bn_act_pool_bwd_reduce", 1, L.ptrs([dout_d]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([sums]),
            B, D, H, W, C, pool, 0.01)
     dgamma, dbeta, dbias = (torch.empty(C, dtype=torch.float32, device=DEV) for _ in range(3))
@@ -356,7 +361,7 @@ def test_conv1_bwd_fused_matches_two_step_path_and_torch(shape, ng, training):
         dw_f.append(torch.zeros(cout, 1, 3, 3, 3, device=DEV)); dw_2.append(torch.zeros(cout, 1, 3, 3, 3, device=DEV))
         dys.append(torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV))
     # bcoef through the library's own reduce + finalize
-    sums = [torch.empty(2 * cout, dtype=torch.float64, device=DEV) for _ in range(ng)]
+    sums = L.stat_buffers(ng, cout, DEV)
     L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(douts), 0, L.ptrs(ys), L.ptrs(coefs), L.ptrs(sums), B, D, H, W, cout,
            L.POOL_MAX, 0.01)
     dgamma = [torch.empty(cout, device=DEV) for _ in range(ng)]
@@ -367,7 +372,7 @@ def test_conv1_bwd_fused_matches_two_step_path_and_torch(shape, ng, training):
     # two-step path
     L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(douts), 0, L.ptrs(ys), L.ptrs(coefs), L.ptrs(bcoefs), L.ptrs(dys),
            B, D, H, W, cout, L.POOL_MAX, 0.01)
-    L.call("tmf_conv1_wgrad", ng, L.ptrs(dys), L.ptrs(xs), L.ptrs(dw_2), B, D, H, W, cout, L.CONV_DIRECT)
+    L.call("tmf_conv1_wgrad", ng, L.ptrs(dys), L.ptrs(xs), L.ptrs(dw_2), B, D, H, W, cout, L.CONV_DIRECT, L.ptr(None), 0)
     # fused path
     ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
     L.call("tmf_conv1_bwd_fused", ng, L.ptrs(douts), L.ptrs(ys), L.ptrs(coefs), L.ptrs(bcoefs), L.ptrs(xs), L.ptrs(dw_f),
@@ -447,7 +452,7 @@ def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_
     res = {}
     for impl in (L.CONV_DIRECT, L.CONV_UMMA):
         y = [torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=DEV) for _ in range(ng)]
-        stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=DEV).unbind(0))
+        stats = L.stat_buffers(ng, cout, DEV)
         L.call("tmf_conv3d_fwd", ng, L.ptrs(a), L.ptrs(wf), L.ptrs(bias), L.ptrs(y), L.ptrs(stats), B, D, H, W, cin, cout,
                3, impl)
         torch.cuda.synchronize()
@@ -458,8 +463,8 @@ def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_
         sd, su = res[L.CONV_DIRECT][1][t], res[L.CONV_UMMA][1][t]
         yu64 = res[L.CONV_UMMA][0][t].double()
         want = torch.cat([yu64.sum(dim=(0, 1, 2, 3)), (yu64 * yu64).sum(dim=(0, 1, 2, 3))])
-        assert torch.allclose(su, want, rtol=1e-5, atol=1e-4)          # statistics of the STORED values
-        assert torch.allclose(sd, su, rtol=2e-2, atol=0.5)
+        assert torch.allclose(su.sum(0), want, rtol=1e-5, atol=1e-4)   # statistics of the STORED values
+        assert torch.allclose(sd.sum(0), su.sum(0), rtol=2e-2, atol=0.5)
 
 
 @pytest.mark.parametrize("shape,C,last", [((2, 9, 11, 7), 32, False), ((1, 8, 8, 8), 16, True), ((2, 5, 6, 13), 64, False)])
@@ -474,7 +479,8 @@ def test_maxpool_kept_maximum_and_pooled_resolution_reduction(shape, C, last):
     y_d = to_ndhwc_bf16(y)
     count = B * D * H * W
     yd64 = y_d.double()
-    stats = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))]).contiguous()
+    stats = torch.zeros((L.stat_rows(), 2 * C), dtype=torch.float64, device=DEV)      # totals in row 0, other rows empty
+    stats[0] = torch.cat([yd64.sum(dim=(0, 1, 2, 3)), (yd64 * yd64).sum(dim=(0, 1, 2, 3))])
     g_d, b_d = gamma.to(DEV), beta.to(DEV)
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
@@ -505,13 +511,13 @@ def test_maxpool_kept_maximum_and_pooled_resolution_reduction(shape, C, last):
     dout_d = dout.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
     if not last:
         dout_d = dout_d.to(torch.bfloat16)
-    s_full = torch.empty(2 * C, dtype=torch.float64, device=DEV)
-    s_kept = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    s_full = L.stat_buffers(1, C, DEV)[0]
+    s_kept = L.stat_buffers(1, C, DEV)[0]
     L.call("tmf_bn_act_pool_bwd_reduce", 1, L.ptrs([dout_d]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([s_full]),
            B, D, H, W, C, L.POOL_MAX, 0.01)
     L.call("tmf_bn_maxpool_bwd_reduce_kept", 1, L.ptrs([dout_d]), int(last), L.ptrs([ymax]), L.ptrs([coef]), L.ptrs([s_kept]),
            B, Do, Ho, Wo, C, 0.01)
-    assert torch.allclose(s_full, s_kept, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(s_full.sum(0), s_kept.sum(0), rtol=1e-4, atol=1e-3)
 
 
 def test_device_prefetcher_yields_every_batch_and_reuses_buffers():

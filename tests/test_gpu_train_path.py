@@ -1,0 +1,150 @@
+"""The path bench.py times -- ``GraphedTrainStep`` (CUDA-graph replay) + ``FusedAdam`` -- against the reference's eager loop
+(kfold_train_adversarial.py:101-136) + ``torch.optim.Adam`` (utils/utils.py:38-41), and run-to-run reproducibility.
+
+The kernels are deterministic (include/tmf.h, DETERMINISM), so k graph replays and k eager steps see bit-identical
+gradients; what may differ is the optimizer arithmetic (one fused kernel vs torch's foreach kernels): <= a few fp32 ulps
+per step.  Tolerance: |dp| <= 2e-7 + 2e-6 * |p| after 3 steps on parameters, exact on ``num_batches_tracked``, 1e-6 relative
+on BatchNorm running statistics.
+"""
+import copy
+
+import pytest
+import torch
+
+from tests import helpers as H
+from transmf_ad_b200.models import mymodel as M
+from transmf_ad_b200.optim import FusedAdam
+from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state
+from transmf_ad_b200.train import GraphedTrainStep
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STEPS = 3
+LR = 1e-3                 # larger than the reference's 1e-4 so that three steps move the weights visibly
+
+
+def _model(kind, kwargs, seed):
+    m = getattr(M, kind)(**kwargs)
+    m.load_state_dict(procedural_state(m.state_dict(), seed=seed))
+    m = m.to(DEV).train()
+    H.set_head_dropout(m, 0.0)          # Dropout(0.5) draws from torch's Philox stream: order-dependent, so off here
+    return m
+
+
+def _batches(B, shape, n):
+    label = make_labels(B).to(DEV)
+    return [(make_volumes(B, shape, seed=100 + i, labels=label.cpu()).to(DEV),
+             make_volumes(B, shape, seed=200 + i, labels=label.cpu()).to(DEV), label) for i in range(n)]
+
+
+def _loss(outs, label):
+    ce, ad, total = H.losses(outs, label)
+    return total, ce, ad
+
+
+def _eager_steps(model, opt, batches):
+    out = []
+    for mri, pet, label in batches:
+        opt.zero_grad()
+        outs = model(mri, pet)
+        total, ce, ad = _loss(outs, label)
+        total.backward()
+        opt.step()
+        out.append(float(total))
+    return out
+
+
+CASES = [("model_CNN_ad", dict(dim=128), 4, (33, 35, 34)),
+         ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 4, (32, 36, 33))]
+
+
+@pytest.mark.parametrize("kind,kwargs,B,shape", CASES)
+def test_graph_replay_with_fused_adam_equals_eager_loop_with_torch_adam(kind, kwargs, B, shape):
+    batches = _batches(B, shape, STEPS)
+    ref = _model(kind, kwargs, seed=3)
+    ours = copy.deepcopy(ref)
+    # reference-style loop: eager launches, torch.optim.Adam exactly as utils/utils.py:38-41 builds it
+    ref_losses = _eager_steps(ref, torch.optim.Adam(ref.parameters(), lr=LR, weight_decay=0.0), batches)
+    # the timed path: graph replay + FusedAdam (warm-up steps inside the constructor must leave no trace)
+    opt = FusedAdam(ours.parameters(), lr=LR, weight_decay=0.0)
+    step = GraphedTrainStep(ours, opt, _loss, batches[0][:2], batches[0][2], warmup=3)
+    assert step.launches_per_step > 50
+    got_losses = []
+    for mri, pet, label in batches:
+        out = step((mri, pet), label)
+        got_losses.append(float(out[0]))
+    torch.cuda.synchronize()
+    assert got_losses == pytest.approx(ref_losses, rel=1e-6, abs=1e-6)
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    for k, v in sd_ref.items():
+        w = sd_ours[k]
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(w) == STEPS, k
+        elif "running_" in k:
+            assert torch.allclose(w, v, rtol=1e-6, atol=1e-7), k
+        else:
+            err = (w - v).abs()
+            assert bool((err <= 2e-7 + 2e-6 * v.abs()).all()), f"{k}: max |dp| {float(err.max()):.3e}"
+    # the weights did move (Adam's first steps are ~lr per element)
+    moved = max(float((sd_ours[k] - procedural_state(sd_ours, seed=3)[k].to(DEV)).abs().max())
+                for k in sd_ours if k.endswith("conv2.0.weight"))
+    assert moved > 0.5 * LR
+
+
+def test_fused_adam_state_dict_round_trip_matches_torch_adam():
+    """a resumed FusedAdam must continue with the loaded step count (bias correction) and moments."""
+    torch.manual_seed(0)
+    p0 = [torch.randn(257, device=DEV), torch.randn(33, 7, device=DEV)]
+    grads = [[torch.randn_like(p) for p in p0] for _ in range(5)]
+
+    def run(make_opt, resume_at=None, make_resumed=None):
+        ps = [p.clone().requires_grad_(True) for p in p0]
+        opt = make_opt(ps)
+        for i, gs in enumerate(grads):
+            if resume_at is not None and i == resume_at:
+                sd = copy.deepcopy(opt.state_dict())
+                opt = make_resumed(ps)
+                opt.load_state_dict(sd)
+            for p, g in zip(ps, gs):
+                p.grad = g.clone()
+            opt.step()
+        return [p.detach() for p in ps]
+
+    want = run(lambda ps: torch.optim.Adam(ps, lr=1e-2))
+    fused = lambda ps: FusedAdam(ps, lr=1e-2)
+    for got in (run(fused), run(fused, 2, fused),
+                run(lambda ps: torch.optim.Adam(ps, lr=1e-2), 3, fused)):        # torch checkpoint -> FusedAdam
+        for a, b in zip(got, want):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
+
+
+def test_full_size_step_is_bitwise_reproducible():
+    """BASELINE-sized volumes (91x109x91, batch 2): two runs from the same state give bit-identical logits, BatchNorm
+    buffers and conv-tower gradients (per-CTA partial statistics, fixed-order sums; no floating-point atomics)."""
+    model = _model("model_ad", CASES[1][1], seed=0)
+    label = make_labels(2).to(DEV)
+    mri = make_volumes(2, seed=1, labels=label.cpu()).to(DEV)
+    pet = make_volumes(2, seed=2, labels=label.cpu()).to(DEV)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    runs = []
+    for _ in range(2):
+        model.load_state_dict(sd0)
+        model.zero_grad(set_to_none=True)
+        outs = model(mri, pet)
+        H.losses(outs, label)[2].backward()
+        torch.cuda.synchronize()
+        runs.append(([o.detach().clone() for o in outs], {k: p.grad.clone() for k, p in model.named_parameters()},
+                     {k: v.clone() for k, v in model.state_dict().items() if "running" in k}))
+    (o1, g1, b1), (o2, g2, b2) = runs
+    for a, b in zip(o1, o2):
+        assert a.shape == (2, 2) and torch.isfinite(a).all()
+        assert torch.equal(a, b)
+    for k in b1:
+        assert torch.equal(b1[k], b2[k]), k
+    for k in g1:
+        assert torch.isfinite(g1[k]).all(), k
+        if "_cnn." in k:
+            assert torch.equal(g1[k], g2[k]), k
+        else:       # fusion transformer: split-K weight gradients still meet in fp32 atomics (order-dependent, ~1 ulp)
+            assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-7), k
+    assert model.mri_cnn(mri).shape == (2, 128, 5, 6, 5)

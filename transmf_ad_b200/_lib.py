@@ -23,7 +23,7 @@ _pp = C.POINTER(C.c_void_p)          # host array of device pointers
 SIGNATURES = {
     "tmf_pack_conv_weights": [_i, _pp, _pp, _pp, _i, _i, _i, _vp],
     "tmf_conv1_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp],
-    "tmf_conv1_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv1_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_conv1_bwd_fused": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _f, _vp, C.c_size_t, _vp],
     "tmf_conv3d_fwd": [_i, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "tmf_conv3d_wgrad": [_i, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
@@ -47,11 +47,11 @@ SIGNATURES = {
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
     "tmf_adam_step": [_vp, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp],
 }
-PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []),
+PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []), "tmf_stat_rows": (_i, []),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
          "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),
-         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_adam_chunk_bytes": (_i, [])}
+         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_conv1_wgrad_workspace_bytes": (_i64, [_i] * 4), "tmf_adam_chunk_bytes": (_i, [])}
 
 _lib = None
 _device_checked = False
@@ -75,6 +75,17 @@ def load():
             fn.restype = res
         _lib = lib
     return _lib
+
+
+def stat_rows():
+    """TMF_STAT_ROWS: rows of a per-channel statistics buffer (include/tmf.h, DETERMINISM)."""
+    return int(load().tmf_stat_rows())
+
+
+def stat_buffers(ng, channels, device):
+    """``ng`` statistics buffers double[TMF_STAT_ROWS][2*channels] carved out of one allocation.  Every producer kernel
+    writes all rows, so the buffer is NOT zeroed; ``tmf_bn_finalize`` / ``tmf_bn_bwd_finalize`` add the rows in order."""
+    return list(torch.empty((ng, stat_rows(), 2 * channels), dtype=torch.float64, device=device).unbind(0))
 
 
 def last_error():

@@ -25,7 +25,9 @@ extern "C" {
 
 const char* tmf_last_error(void) { return tmf::g_err; }
 
-int tmf_version(void) { return 100; }
+int tmf_version(void) { return 200; }
+
+int tmf_stat_rows(void) { return TMF_STAT_ROWS; }
 
 int64_t tmf_launch_count(void) { return tmf::g_launches.load(std::memory_order_relaxed); }
 

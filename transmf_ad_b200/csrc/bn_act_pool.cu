@@ -9,18 +9,52 @@
 namespace tmf {
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const float> gamma,
+// Fixed-order sum of the TMF_STAT_ROWS partial rows of a statistics buffer (include/tmf.h, DETERMINISM): a block of 8
+// warps takes 32 channels; warp w adds rows w, w+8, ... of its lane's channel, then warp 0 adds the 8 warp totals in
+// index order.  Returns (for threads of warp 0) the two totals of channel blockIdx.x*32 + lane.
+__device__ __forceinline__ void sum_stat_rows(const double* __restrict__ st, int C, bool on, double& t1, double& t2) {
+  __shared__ double part[2][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+  if (on && c < C) {
+    int r = w;
+    for (; r + 8 < TMF_STAT_ROWS; r += 16) {          // two independent chains (fixed association)
+      a1 += st[(size_t)r * 2 * C + c];
+      a2 += st[(size_t)r * 2 * C + C + c];
+      b1 += st[(size_t)(r + 8) * 2 * C + c];
+      b2 += st[(size_t)(r + 8) * 2 * C + C + c];
+    }
+    for (; r < TMF_STAT_ROWS; r += 8) {
+      a1 += st[(size_t)r * 2 * C + c];
+      a2 += st[(size_t)r * 2 * C + C + c];
+    }
+  }
+  part[0][w][lane] = a1 + b1;
+  part[1][w][lane] = a2 + b2;
+  __syncthreads();
+  t1 = 0.0; t2 = 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t1 += part[0][i][lane]; t2 += part[1][i][lane]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const float> gamma,
                                    GroupPtr<const float> beta, GroupPtr<float> rmean, GroupPtr<float> rvar,
                                    GroupPtr<int64_t> nbt, GroupPtr<float> coef, int C, double count, float momentum,
                                    float eps, int training) {
   const int g = blockIdx.z;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double t1, t2;
+  sum_stat_rows(stats.p[g], C, training != 0, t1, t2);
+  if (threadIdx.x >= 32) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   if (c == 0 && training && nbt.p[g] != nullptr) nbt.p[g][0] += 1;
   if (c >= C) return;
   float mean, var;
   if (training) {
-    const double m = stats.p[g][c] / count;
-    double v = stats.p[g][C + c] / count - m * m;
+    const double m = t1 / count;
+    double v = t2 / count - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
@@ -41,13 +75,15 @@ __global__ void bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const 
   coef.p[g][3 * C + c] = invstd;
 }
 
-__global__ void bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
                                        GroupPtr<float> dbeta, GroupPtr<float> dbias, GroupPtr<float> bcoef, int C,
                                        double count, int training) {
   const int g = blockIdx.z;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double s1, s2;
+  sum_stat_rows(sums.p[g], C, true, s1, s2);
+  if (threadIdx.x >= 32) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   if (c >= C) return;
-  const double s1 = sums.p[g][c], s2 = sums.p[g][C + c];
   dgamma.p[g][c] = (float)s2;
   dbeta.p[g][c] = (float)s1;
   if (training) {
@@ -171,34 +207,34 @@ __global__ void __launch_bounds__(256, KEEP ? 3 : 4) bn_act_pool_fwd_kernel(ActP
   }
 }
 
-// Per-channel partial sums of a block -> red[2][C] (shared).  A thread owns channel chunk cq = threadIdx.x % CQ for the
-// whole kernel; when CQ is a power of two (C = 32, 64, 128, 256) the lanes of a warp that share a chunk are first
-// combined with shuffles, so a block issues 8*CQ*16 shared atomics instead of 256*16 on the same few addresses
-// (measured: the atomics, not HBM, bounded the small reductions).
-__device__ __forceinline__ void block_channel_sums(float* red, int C, int CQ, int c0, bool active, float (&s1)[8],
-                                                   float (&s2)[8]) {
-  const bool pow2 = (CQ & (CQ - 1)) == 0 && CQ <= 32;          // block-uniform; then every thread is active
-  if (pow2) {
-    for (int off = 16; off >= CQ; off >>= 1) {
+// Per-channel partial sums of a 256-thread block, deterministically: every thread parks its 16 values in shared memory
+// (red[16][256], conflict-free), then one thread per (statistic, channel) adds the 256/CQ contributions of its channel in
+// thread order (four interleaved chains, fixed association) and stores the total into this block's row of the
+// double[TMF_STAT_ROWS][2C] buffer (no atomics: include/tmf.h, DETERMINISM).  A thread owns channel chunk
+// cq = threadIdx.x % CQ for the whole kernel.
+__device__ __forceinline__ void block_channel_sums(float* red, double* rows, int C, int CQ, bool active,
+                                                   const float (&s1)[8], const float (&s2)[8]) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-      }
+  for (int j = 0; j < 8; ++j) {
+    red[j * 256 + threadIdx.x] = active ? s1[j] : 0.f;
+    red[(8 + j) * 256 + threadIdx.x] = active ? s2[j] : 0.f;
+  }
+  __syncthreads();
+  const int pstep = 256 / CQ;
+  for (int o = threadIdx.x; o < 2 * C; o += 256) {
+    const int stat = o / C, ch = o - stat * C;
+    const int cq = ch >> 3, j = ch & 7;
+    const float* src = red + (stat * 8 + j) * 256 + cq;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 3 < pstep; k += 4) {
+      a0 += (double)src[k * CQ];
+      a1 += (double)src[(k + 1) * CQ];
+      a2 += (double)src[(k + 2) * CQ];
+      a3 += (double)src[(k + 3) * CQ];
     }
-    if ((int)(threadIdx.x & 31) < CQ) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[c0 + j], s1[j]);
-        atomicAdd(&red[C + c0 + j], s2[j]);
-      }
-    }
-  } else if (active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[c0 + j], s1[j]);
-      atomicAdd(&red[C + c0 + j], s2[j]);
-    }
+    for (; k < pstep; ++k) a0 += (double)src[k * CQ];
+    stat_row_store(rows, 2 * C, blockIdx.x, gridDim.x, o, (a0 + a1) + (a2 + a3));
   }
 }
 
@@ -214,12 +250,8 @@ __device__ __forceinline__ void block_channel_sums(float* red, int C, int CQ, in
 template <bool APPLY, int POOL>
 __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_pool_bwd_kernel(ActPoolArgs p) {
   const int g = blockIdx.z;
-  extern __shared__ float red[];  // [2][C] (REDUCE only)
+  extern __shared__ float red[];  // [16][256] (REDUCE only)
   const int CQ = p.C >> 3;
-  if (!APPLY) {
-    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
-  }
   const int Dw = APPLY ? p.Dc : p.Do, Hw = APPLY ? p.Hc : p.Ho, Ww = APPLY ? p.Wc : p.Wo;
   const __nv_bfloat16* yg = p.y.p[g];
   constexpr int NPOS = (POOL == TMF_POOL_NONE) ? 1 : 8;
@@ -343,20 +375,14 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
     }
    }
   }
-  if (!APPLY) {
-    block_channel_sums(red, p.C, CQ, c0, active, s1, s2);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
-  }
+  if (!APPLY) block_channel_sums(red, p.sums.p[g], p.C, CQ, active, s1, s2);
 }
 
 // Max-pool backward reduction from ymax (see bn_act_pool_fwd_kernel<true>): sum dz, sum dz*xhat over the pooled
 // positions;  dz = dout * LeakyReLU'(scale*ymax + shift),  xhat = (ymax - mean) * invstd.
-__global__ void __launch_bounds__(256) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
+__global__ void __launch_bounds__(256, 4) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
   const int g = blockIdx.z;
-  extern __shared__ float red[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float red[];  // [16][256]
   const int CQ = p.C >> 3;
   const int cq = threadIdx.x % CQ, pstep = 256 / CQ;
   const bool active = (int)threadIdx.x < pstep * CQ;
@@ -372,7 +398,7 @@ __global__ void __launch_bounds__(256) bn_maxpool_bwd_reduce_kept_kernel(ActPool
   }
   const __nv_bfloat16* ym = p.ymax.p[g];
   if (active) {
-#pragma unroll 2
+#pragma unroll 4
     for (int pos = blockIdx.x * pstep + threadIdx.x / CQ; pos < npos; pos += gridDim.x * pstep) {
       const int64_t off = (int64_t)pos * p.C + c0;
       float f[8], go[8];
@@ -387,9 +413,7 @@ __global__ void __launch_bounds__(256) bn_maxpool_bwd_reduce_kept_kernel(ActPool
       }
     }
   }
-  block_channel_sums(red, p.C, CQ, c0, active, s1, s2);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums.p[g][i], (double)red[i]);
+  block_channel_sums(red, p.sums.p[g], p.C, CQ, active, s1, s2);
 }
 
 template <bool APPLY>
@@ -458,8 +482,8 @@ int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamm
       !load_group(gn, num_batches_tracked, ng, false, "num_batches_tracked") || !load_group(gc, coef, ng, true, "coef"))
     return 1;
   TMF_REQUIRE(count > 0, "bn_finalize: count must be positive");
-  dim3 grid(ceil_div(C, 128), 1, ng);
-  bn_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
+  dim3 grid(ceil_div(C, 32), 1, ng);
+  bn_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
                                                              eps, training);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -508,12 +532,11 @@ int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp3
       !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
   const int pstep = 256 / (C / 8);
   int blocks = ceil_div(npos, (int64_t)pstep * 4);                 // >= 4 positions per thread
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > TMF_STAT_ROWS) blocks = TMF_STAT_ROWS;              // one statistics row per block
   if (blocks < 1) blocks = 1;
-  bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 2 * C * sizeof(float), st>>>(p, (int)npos);
+  bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st>>>(p, (int)npos);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -528,9 +551,8 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
       !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  TMF_CUDA(zero_group_buffers((void* const*)sums, ng, sizeof(double) * 2 * C, st));
-  dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 3, &p.nch, &p.hcr), 1, ng);
-  launch_bwd<false>(p, grid, 2 * C * sizeof(float), st);
+  dim3 grid(plan_units(B, p.Do, p.Ho, TMF_STAT_ROWS, &p.nch, &p.hcr), 1, ng);   // one statistics row per block
+  launch_bwd<false>(p, grid, 16 * 256 * sizeof(float), st);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -546,8 +568,8 @@ int tmf_bn_bwd_finalize(int ng, const double* const* sums, const float* const* c
       !load_group(gdg, dgamma, ng, true, "dgamma") || !load_group(gdb, dbeta, ng, true, "dbeta") ||
       !load_group(gdbias, dbias, ng, false, "dbias") || !load_group(gbc, bcoef, ng, true, "bcoef"))
     return 1;
-  dim3 grid(ceil_div(C, 128), 1, ng);
-  bn_bwd_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
+  dim3 grid(ceil_div(C, 32), 1, ng);
+  bn_bwd_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
                                                                  training);
   TMF_LAUNCH_CHECK();
   return 0;

@@ -85,6 +85,14 @@ static inline cudaError_t zero_group_buffers(void* const* bufs, int ng, size_t b
 }
 
 // ---- device helpers -------------------------------------------------------------------------------------
+// Deterministic cross-CTA statistics (include/tmf.h, DETERMINISM): CTA `part` of the `nparts` (<= TMF_STAT_ROWS) CTAs that
+// produce column `col` of a double[TMF_STAT_ROWS][ncols] buffer owns row `part` and clears rows part + k*nparts, so
+// every row is written exactly once per launch: no memset by the caller, no atomics, fixed-order sum in the finalize.
+__device__ __forceinline__ void stat_row_store(double* buf, int ncols, int part, int nparts, int col, double v) {
+  buf[(size_t)part * ncols + col] = v;
+  for (int r = part + nparts; r < TMF_STAT_ROWS; r += nparts) buf[(size_t)r * ncols + col] = 0.0;
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

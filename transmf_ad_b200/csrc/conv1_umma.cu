@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   const uint32_t bars = smW + 2 * 4096;
   const uint32_t full = bars, empty = bars + 8 * C1U_STAGES, acc_full = empty + 8 * C1U_STAGES, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
-  float* stats_ptr = reinterpret_cast<float*>(gen + (tmem_slot + 16 - smem_base));        // float [2][64]
+  float* stats_ptr = reinterpret_cast<float*>(gen + (tmem_slot + 16 - smem_base));        // float [4 warps][2][64]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 128; i += C1U_THREADS) stats_ptr[i] = 0.f;
   // weights: fp32 (Cout,27) -> bf16 hi / lo tiles, K-major rows of 32 taps (taps 27..31 zero)
   for (int i = threadIdx.x; i < p.cout * 4; i += C1U_THREADS) {
     const int co = i >> 2, j = i & 3;
@@ -276,15 +275,18 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
               ssq[c][i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
             }
           }
-          atomicAdd(&stats_ptr[c * 32 + lane], ssum[c][0]);
-          atomicAdd(&stats_ptr[64 + c * 32 + lane], ssq[c][0]);
+          stats_ptr[quarter * 128 + c * 32 + lane] = ssum[c][0];
+          stats_ptr[quarter * 128 + 64 + c * 32 + lane] = ssq[c][0];
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 288;             // 0..127 over the four epilogue warps
-      if (e < p.cout) {
-        atomicAdd(&p.stats[g][e], (double)stats_ptr[e]);
-        atomicAdd(&p.stats[g][p.cout + e], (double)stats_ptr[64 + e]);
+      if (e < p.cout) {                            // fixed-order sum over the four warps -> this CTA's row
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) { s1 += (double)stats_ptr[w4 * 128 + e]; s2 += (double)stats_ptr[w4 * 128 + 64 + e]; }
+        stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, e, s1);
+        stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, p.cout + e, s2);
       }
     }
   }
@@ -307,7 +309,8 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 //   B (N = 16)        = x patches, K-major: row n = kd*3+kh holds x(d+kd-1, h+kh-1, c-1) for the tile's 128 voxels --
 //       contiguous pieces of image rows, written by builder warps as bf16 hi / lo tiles (128B swizzle), so the fp32
 //       image enters as xh + xl (two MMAs per K step).
-// Accumulation stays in TMEM (16 columns) over the CTA's whole tile range; 864 atomics per CTA at the end.
+// Accumulation stays in TMEM (16 columns) over the CTA's whole tile range; each CTA stores its 864 partial sums into
+// its slot of the caller's workspace and conv1_wgrad_reduce_kernel adds the slots in CTA order (deterministic).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int C1W_U_THREADS = 320;          // warp 0: TMA (dY), warps 1-8: patch builders (two groups), warp 9: MMA
 constexpr int C1W_U_STAGES = 4;
@@ -316,7 +319,7 @@ constexpr uint32_t C1W_U_PTILE = 2 * 16 * 128;     // [2 K-blocks][16 rows][128 
 struct alignas(64) C1WParams {
   CUtensorMap tmY[TMF_MAX_GROUPS];
   const float* x[TMF_MAX_GROUPS];
-  float* dw[TMF_MAX_GROUPS];
+  float* part[TMF_MAX_GROUPS];     // per-CTA partial dW [ncta][Cout*27] (caller workspace; reduced in CTA order)
   int ng, B, D, H, W, Wp, NHy, QT, ntiles;
   uint32_t y_tx, y_slab_bytes, stage_bytes, idesc;
 };
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(C1W_U_THREADS, 1) conv1_umma_wgrad_kernel(cons
       tmem_ld_wait();
       if (j < 3) {
 #pragma unroll
-        for (int nn = 0; nn < 9; ++nn) atomicAdd(&p.dw[g][co * 27 + nn * 3 + (2 - j)], __uint_as_float(raw[nn]));
+        for (int nn = 0; nn < 9; ++nn) p.part[g][(size_t)cta * 864 + co * 27 + nn * 3 + (2 - j)] = __uint_as_float(raw[nn]);
       }
     }
   } else {
@@ -471,6 +474,15 @@ __global__ void __launch_bounds__(C1W_U_THREADS, 1) conv1_umma_wgrad_kernel(cons
   }
 }
 
+__global__ void conv1_wgrad_reduce_kernel(GroupPtr<const float> part, GroupPtr<float> dw, int ncta, int n) {
+  const int g = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < ncta; ++k) s += part.p[g][(size_t)k * n + i];
+  dw.p[g][i] = s;
+}
+
 }  // namespace tmf
 
 using namespace tmf;
@@ -503,8 +515,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
     p.y[g] = (__nv_bfloat16*)y[g];
     p.stats[g] = stats ? stats[g] : nullptr;
   }
-  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
-  const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 512 + 64;
+  const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 2048 + 64;
   static bool attr_done = false;
   if (!attr_done) {
     TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -517,6 +528,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   int per_group = sms / ng;
   if (per_group > p.ntiles) per_group = p.ntiles;
   if (per_group < 1) per_group = 1;
+  if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;
   if (cout == 32) conv1_umma_fwd_kernel<1><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
   else conv1_umma_fwd_kernel<2><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
   TMF_LAUNCH_CHECK();
@@ -529,9 +541,13 @@ bool tmf_conv1_wgrad_umma_supported(int W, int cout) {
   return cout == 32 && W + 2 <= 256;
 }
 
+size_t tmf_conv1_wgrad_umma_workspace(int ng, int cout) { return (size_t)ng * 148 * 27 * cout * sizeof(float); }
+
 int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
-                         int W, int cout, void* stream) {
+                         int W, int cout, void* ws, size_t ws_bytes, void* stream) {
   TMF_CHECK_NG(ng);
+  TMF_REQUIRE(ws != nullptr && ws_bytes >= tmf_conv1_wgrad_umma_workspace(ng, cout) && ((uintptr_t)ws & 15) == 0,
+              "conv1_wgrad_umma: needs a 16-byte aligned workspace of tmf_conv1_wgrad_workspace_bytes() bytes");
   TMF_REQUIRE(tmf_conv1_wgrad_umma_supported(W, cout) || cout == 32, "conv1_wgrad_umma: needs Cout = 32 (got %d)", cout);
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -559,8 +575,7 @@ int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, f
   for (int g = 0; g < ng; ++g) {
     TMF_REQUIRE(dy[g] && x[g] && dw[g], "conv1_wgrad_umma: NULL device pointer");
     p.x[g] = x[g];
-    p.dw[g] = dw[g];
-    TMF_CUDA(cudaMemsetAsync(dw[g], 0, sizeof(float) * 27 * cout, st));
+    p.part[g] = (float*)ws + (size_t)g * 148 * 27 * cout;
     cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
     cuuint64_t strides[4] = {(cuuint64_t)cout * 2, (cuuint64_t)W * cout * 2, (cuuint64_t)H * W * cout * 2,
                              (cuuint64_t)D * H * W * cout * 2};
@@ -583,8 +598,14 @@ int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, f
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_group = sms / ng;
   if (per_group > p.ntiles) per_group = p.ntiles;
+  if (per_group > 148) per_group = 148;
   if (per_group < 1) per_group = 1;
   conv1_umma_wgrad_kernel<<<dim3(per_group * ng), C1W_U_THREADS, smem, st>>>(p);
+  TMF_LAUNCH_CHECK();
+  GroupPtr<const float> gpart;
+  GroupPtr<float> gdw;
+  for (int g = 0; g < TMF_MAX_GROUPS; ++g) { gpart.p[g] = g < ng ? p.part[g] : nullptr; gdw.p[g] = g < ng ? dw[g] : nullptr; }
+  conv1_wgrad_reduce_kernel<<<dim3(ceil_div(27 * cout, 128), 1, ng), 128, 0, st>>>(gpart, gdw, per_group, 27 * cout);
   TMF_LAUNCH_CHECK();
   return 0;
 }

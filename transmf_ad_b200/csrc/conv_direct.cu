@@ -136,8 +136,9 @@ conv1_fwd_kernel(GroupPtr<const float> x, GroupPtr<const float> w, GroupPtr<cons
     }
     __syncthreads();
     if (threadIdx.x < cout) {
-      atomicAdd(&stats.p[g][threadIdx.x], (double)red[0][threadIdx.x]);
-      atomicAdd(&stats.p[g][cout + threadIdx.x], (double)red[1][threadIdx.x]);
+      double* row = stats.p[g] + (size_t)(blockIdx.x % TMF_STAT_ROWS) * 2 * cout;   // bring-up path: atomics, spread over rows
+      atomicAdd(&row[threadIdx.x], (double)red[0][threadIdx.x]);
+      atomicAdd(&row[cout + threadIdx.x], (double)red[1][threadIdx.x]);
     }
   }
 }
@@ -365,8 +366,9 @@ __global__ void __launch_bounds__(256) conv3d_direct_kernel(ConvDirectArgs p) {
     }
     __syncthreads();
     if (tid < DT_N && co0 + tid < p.cout) {
-      atomicAdd(&p.stats.p[g][co0 + tid], (double)red[0][tid]);
-      atomicAdd(&p.stats.p[g][p.cout + co0 + tid], (double)red[1][tid]);
+      double* row = p.stats.p[g] + (size_t)(blockIdx.x % TMF_STAT_ROWS) * 2 * p.cout;
+      atomicAdd(&row[co0 + tid], (double)red[0][tid]);
+      atomicAdd(&row[p.cout + co0 + tid], (double)red[1][tid]);
     }
   }
 }
@@ -460,8 +462,9 @@ bool tmf_conv1_fwd_umma_supported(int cout);
 int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, const float* const* bias, void* const* y,
                        double* const* stats, int B, int D, int H, int W, int cout, void* stream);
 bool tmf_conv1_wgrad_umma_supported(int W, int cout);
+size_t tmf_conv1_wgrad_umma_workspace(int ng, int cout);
 int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
-                         int W, int cout, void* stream);
+                         int W, int cout, void* ws, size_t ws_bytes, void* stream);
 // implemented in conv_umma.cu
 int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, const float* const* bias,
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout,
@@ -531,7 +534,7 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats != nullptr)
-    for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
+    for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout * TMF_STAT_ROWS, st));
   const int64_t M = (int64_t)B * D * H * W;
   dim3 grid(min(ceil_div(M, C1_THREADS), 148 * 6), 1, ng);
   conv1_fwd_kernel<<<grid, C1_THREADS, 0, st>>>(gx, gw, gb, gy, gs, B, D, H, W, cout);
@@ -539,13 +542,18 @@ int tmf_conv1_fwd(int ng, const float* const* x, const float* const* w, const fl
   return 0;
 }
 
+int64_t tmf_conv1_wgrad_workspace_bytes(int ng, int impl, int W, int cout) {
+  if (impl == TMF_CONV_AUTO) impl = tmf_conv1_wgrad_umma_supported(W, cout) ? TMF_CONV_UMMA : TMF_CONV_DIRECT;
+  return impl == TMF_CONV_UMMA ? (int64_t)tmf_conv1_wgrad_umma_workspace(ng, cout) : 0;
+}
+
 int tmf_conv1_wgrad(int ng, const void* const* dy, const float* const* x, float* const* dw, int B, int D, int H,
-                    int W, int cout, int impl, void* stream) {
+                    int W, int cout, int impl, void* ws, size_t ws_bytes, void* stream) {
   TMF_CHECK_NG(ng);
   if (impl == TMF_CONV_AUTO) impl = tmf_conv1_wgrad_umma_supported(W, cout) ? TMF_CONV_UMMA : TMF_CONV_DIRECT;
   if (impl == TMF_CONV_UMMA) {
     TMF_REQUIRE(tmf_conv1_wgrad_umma_supported(W, cout), "conv1_wgrad: tcgen05 path needs Cout = 32 (got %d)", cout);
-    return tmf_conv1_wgrad_umma(ng, dy, x, dw, B, D, H, W, cout, stream);
+    return tmf_conv1_wgrad_umma(ng, dy, x, dw, B, D, H, W, cout, ws, ws_bytes, stream);
   }
   TMF_REQUIRE(cout >= 8 && cout <= 64 && cout % 8 == 0, "conv1_wgrad: Cout must be a multiple of 8 in [8,64] (got %d)",
               cout);
@@ -597,7 +605,7 @@ int tmf_conv3d_fwd(int ng, const void* const* a, const void* const* wf, const fl
   p.M = (int64_t)B * D * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   if (stats != nullptr)
-    for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout, st));
+    for (int g = 0; g < ng; ++g) TMF_CUDA(cudaMemsetAsync(stats[g], 0, sizeof(double) * 2 * cout * TMF_STAT_ROWS, st));
   dim3 grid(ceil_div(p.M, DT_M), ceil_div(cout, DT_N), ng);
   conv3d_direct_kernel<<<grid, 256, 0, st>>>(p);
   TMF_LAUNCH_CHECK();

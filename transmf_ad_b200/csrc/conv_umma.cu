@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
   const uint32_t b_full = a_empty + 8 * UC_MAX_ASTAGES, b_empty = b_full + 8 * UC_MAX_BSTAGES;
   const uint32_t acc_full = b_empty + 8 * UC_MAX_BSTAGES, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
-  const uint32_t stats_sm = tmem_slot + 16;                             // float [2][256]
+  const uint32_t stats_sm = tmem_slot + 16;                             // float [4 epilogue warps][2][256]
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   float* stats_ptr = reinterpret_cast<float*>(gen_base + (stats_sm - smem_base));
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
     prefetch_tmap(&p.tmA[g]);
     prefetch_tmap(&p.tmB[g]);
   }
-  for (int i = threadIdx.x; i < 512; i += NTHREADS) stats_ptr[i] = 0.f;
+  for (int i = threadIdx.x; i < 2048; i += NTHREADS) stats_ptr[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
               sq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
             }
           }
-          atomicAdd(&stats_ptr[c0 + lane], v[0]);
-          atomicAdd(&stats_ptr[256 + c0 + lane], sq[0]);
+          // each epilogue warp owns a slice of the shared accumulators (program order -> deterministic)
+          stats_ptr[quarter * 512 + c0 + lane] += v[0];
+          stats_ptr[quarter * 512 + 256 + c0 + lane] += sq[0];
         }
       }
       }
@@ -325,8 +326,11 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
     if (want_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = threadIdx.x - EPI0; i < p.cout; i += 128) {
-        atomicAdd(&p.stats[g][i], (double)stats_ptr[i]);
-        atomicAdd(&p.stats[g][p.cout + i], (double)stats_ptr[256 + i]);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) { s1 += (double)stats_ptr[w4 * 512 + i]; s2 += (double)stats_ptr[w4 * 512 + 256 + i]; }
+        stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, i, s1);
+        stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, p.cout + i, s2);
       }
     }
   }
@@ -407,7 +411,7 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
   pl.b_tx = (uint32_t)cout * pl.row_bytes;
   pl.b_stage_bytes = (pl.b_tx + 1023u) & ~1023u;
   const int taps = ks * ks * ks;
-  const uint32_t fixed = 1024 /*align slack*/ + 8 * (2 * UC_MAX_ASTAGES + 2 * UC_MAX_BSTAGES) + 64 + 2048 + 256;
+  const uint32_t fixed = 1024 /*align slack*/ + 8 * (2 * UC_MAX_ASTAGES + 2 * UC_MAX_BSTAGES) + 64 + 8192 /*stats*/ + 256;
   const uint32_t budget = UC_SMEM_BUDGET - fixed;
   const uint32_t total_b = (uint32_t)taps * pl.nchunk * pl.b_stage_bytes;
   if (taps * pl.nchunk <= UC_MAX_BSTAGES && total_b + 2 * pl.a_stage_bytes <= budget) {
@@ -564,7 +568,6 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
       TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_umma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
   }
-  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -575,6 +578,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
     if (e != nullptr && atoi(e) > 0 && per_group > atoi(e)) per_group = atoi(e);
   }
   if (per_group < 1) per_group = 1;
+  if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;
   dim3 grid(per_group * ng, 1, 1);
   const int ksteps = pl.chunk / 16;
 #define TMF_LAUNCH_CONV(KST, KSZ, RES, NI)                                                                          \

@@ -47,7 +47,7 @@ constexpr int CC_NBUF = 4;                      // accumulator buffers
 constexpr int CC_MAX_VG = 8;                    // towers x Cout slices
 constexpr uint32_t CC_SMEM_BUDGET = 227 * 1024;
 constexpr uint32_t CC_XCHG_BYTES = 2 * 2 * 4 * 3 * 32 * 4;   // [parity][group][quarter][D1_0, D2_0, D2_1][32 ch] floats
-constexpr uint32_t CC_FIXED_SMEM = 1024 /*align*/ + 8 * (2 * CC_MAX_SLOTS) + 8 + 8 * 2 * CC_NBUF + 24 + CC_XCHG_BYTES + 256 /*stats*/ +
+constexpr uint32_t CC_FIXED_SMEM = 1024 /*align*/ + 8 * (2 * CC_MAX_SLOTS) + 8 + 8 * 2 * CC_NBUF + 24 + CC_XCHG_BYTES + 2048 /*stats: [8 warps][2][32]*/ +
                                    128 /*bias*/ + 64;
 
 struct alignas(64) ColConvParams {
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
   const uint32_t acc_full = b_full + 8, acc_empty = acc_full + 8 * CC_NBUF;
   const uint32_t tmem_slot = acc_empty + 8 * CC_NBUF;
   const uint32_t xchg_sm = tmem_slot + 24;                               // 16-byte aligned (bars is 1024-aligned)
-  const uint32_t stats_sm = xchg_sm + CC_XCHG_BYTES;                     // float [2][32]
-  const uint32_t bias_sm = stats_sm + 256;                               // float [32]
+  const uint32_t stats_sm = xchg_sm + CC_XCHG_BYTES;                     // float [8 epilogue warps][2][32]
+  const uint32_t bias_sm = stats_sm + 2048;                              // float [32]
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   float* xchg_ptr = reinterpret_cast<float*>(gen_base + (xchg_sm - smem_base));
@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
     prefetch_tmap(&p.tmA[g]);
     prefetch_tmap(&p.tmB[g]);
   }
-  if (threadIdx.x < 64) stats_ptr[threadIdx.x] = 0.f;
   if (threadIdx.x < CC_CO) bias_ptr[threadIdx.x] = (p.bias[g] != nullptr) ? p.bias[g][co_off + threadIdx.x] : 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -361,20 +360,24 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
     if (prof && blockIdx.x == 0 && ew == 0 && lane == 0)
       printf("col prof: epilogue warp 0: total %lld cyc, waiting for a finished accumulator %lld\n", clock64() - t_epi0, t_epi);
     if (want_stats) {
+      // deterministic: shuffle tree per warp -> one slot per warp -> fixed-order sum -> this CTA's row of the buffer
 #pragma unroll
       for (int j = 0; j < CC_CO; ++j) {
         const float ssum = warp_sum(acc_s[j]);
         const float qsum = warp_sum(acc_q[j]);
         if (lane == 0) {
-          atomicAdd(&stats_ptr[j], ssum);
-          atomicAdd(&stats_ptr[32 + j], qsum);
+          stats_ptr[ew * 64 + j] = ssum;
+          stats_ptr[ew * 64 + 32 + j] = qsum;
         }
       }
       asm volatile("bar.sync 3, %0;" ::"r"(32 * CC_EPI_WARPS) : "memory");
       const int i = threadIdx.x - 32 * CC_FIRST_EPI;
-      if (i < CC_CO) {
-        atomicAdd(&p.stats[g][co_off + i], (double)stats_ptr[i]);
-        atomicAdd(&p.stats[g][p.cout + co_off + i], (double)stats_ptr[32 + i]);
+      if (i < 2 * CC_CO) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < CC_EPI_WARPS; ++w8) tot += (double)stats_ptr[w8 * 64 + i];
+        const int col = (i < CC_CO) ? (co_off + i) : (p.cout + co_off + (i - CC_CO));
+        stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, col, tot);
       }
     }
   }
@@ -498,13 +501,13 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
       TMF_REQUIRE(r == CUDA_SUCCESS, "conv3d_fwd_col: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
   }
-  if (stats) TMF_CUDA(zero_group_buffers((void* const*)stats, ng, sizeof(double) * 2 * cout, st));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ngv = ng * pl.nsplit;
   int per_group = sms / ngv;
   if (per_group > p.steps_per_group) per_group = p.steps_per_group;
+  if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;        // one statistics row per CTA of a (tower, slice)
   if (per_group < 1) per_group = 1;
   dim3 grid(per_group * ngv, 1, 1);
 #define TMF_LAUNCH_COL(KST)                                                                                              \

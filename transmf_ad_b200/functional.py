@@ -15,6 +15,20 @@ from . import _lib as L
 BN_EPS, BN_MOMENTUM, LRELU_SLOPE, LN_EPS = 1e-5, 0.1, 0.01, 1e-5
 
 
+# Data parallelism (dp.GradBucketReducer.install): called from SNetFunction.backward with (parameters, gradients) of one
+# conv layer of every tower as soon as they exist, so that their all-reduce overlaps the rest of the conv backward.
+_GRAD_SINK = None
+
+
+def set_grad_sink(fn):
+    global _GRAD_SINK
+    _GRAD_SINK = fn
+
+
+def get_grad_sink():
+    return _GRAD_SINK
+
+
 def conv_impl():
     """TMF_CONV_IMPL = auto | direct | umma  (bring-up / cross-check switch; default auto)."""
     return {"auto": L.CONV_AUTO, "direct": L.CONV_DIRECT, "umma": L.CONV_UMMA}[os.environ.get("TMF_CONV_IMPL", "auto")]
@@ -41,10 +55,23 @@ class SNetSpec:
     """Static description of one sNet: per layer (Cin, Cout, ksize, pool)."""
 
     def __init__(self, dim):
+        if dim < 32 or dim % 32 != 0:
+            raise ValueError(f"sNet(dim={dim}): the B200 kernels work on 8-channel vectors of dim/4 channels; "
+                             f"dim must be a positive multiple of 32")
         q, h = dim // 4, dim // 2
         self.layers = [(1, q, 3, L.POOL_MAX), (q, q, 3, L.POOL_NONE), (q, h, 3, L.POOL_MAX), (h, h, 3, L.POOL_NONE),
                        (h, dim, 3, L.POOL_MAX), (dim, 2 * dim, 3, L.POOL_NONE), (2 * dim, dim, 1, L.POOL_AVG)]
         self.dim = dim
+
+
+class SNetRun:
+    """Per-call settings of the conv stack: train / eval, whether autograd is recording (``torch.is_grad_enabled()`` at
+    the call site: inside ``Function.forward`` grad mode is always off), and the hyper-parameters read from the
+    ``nn.BatchNorm3d`` / ``nn.LeakyReLU`` children -- per layer (eps, momentum, negative_slope)."""
+
+    def __init__(self, training, grad_enabled, hyper=None):
+        self.training, self.grad_enabled = bool(training), bool(grad_enabled)
+        self.hyper = hyper if hyper is not None else [(BN_EPS, BN_MOMENTUM, LRELU_SLOPE)] * 7
 
 
 def wgrad_workspace(ng, impl, B, D, H, W, cin, cout, ks, dev):
@@ -60,14 +87,20 @@ def _pooled(D, H, W, pool):
 class SNetFunction(torch.autograd.Function):
     """Both towers (or one) of the 3D-CNN encoder as ONE autograd node.
 
-    apply(spec, training, buffers, x_0[, x_1], *params) with params = for each tower, for each of the 7 layers:
+    apply(spec, run, buffers, ng, x_0[, x_1], *params) with run an ``SNetRun`` and params = for each tower, for each of the 7 layers:
     conv.weight, conv.bias, bn.weight, bn.bias;  buffers[t][l] = (running_mean, running_var, num_batches_tracked).
     Returns one fp32 tensor per tower with logical shape (B, dim, d, h, w) in channels-last-3d memory, i.e. the
     token matrix (B, d*h*w, dim) is a free view of it.
     """
 
     @staticmethod
-    def forward(ctx, spec, training, buffers, ng, *args):
+    def forward(ctx, spec, run, buffers, ng, *args):
+        if not isinstance(run, SNetRun):
+            run = SNetRun(bool(run), True)
+        training = run.training
+        if run.grad_enabled and any(ctx.needs_input_grad[4:4 + ng]):
+            raise RuntimeError("sNet: gradients with respect to the input volumes are not implemented (conv1.0 has no "
+                               "dgrad kernel); detach the inputs or compute saliency with the reference modules")
         xs = [_f32c(a) for a in args[:ng]]
         params = args[ng:]
         assert len(params) == ng * 7 * 4
@@ -78,7 +111,7 @@ class SNetFunction(torch.autograd.Function):
             if tuple(x.shape) != tuple(xs[0].shape):
                 raise RuntimeError("MRI and PET volumes must have the same shape")
         dev = xs[0].device
-        need_grad = any(ctx.needs_input_grad[4 + ng:])      # (grad mode is always off inside forward)
+        need_grad = run.grad_enabled and any(ctx.needs_input_grad[4 + ng:])
         impl = conv_impl()
         P = lambda t, l, k: params[(t * 7 + l) * 4 + k]
         saved = []
@@ -87,9 +120,10 @@ class SNetFunction(torch.autograd.Function):
         for l, (cin, cout, ks, pool) in enumerate(spec.layers):
             Dl, Hl, Wl = dims
             count = B * Dl * Hl * Wl
+            bn_eps, bn_momentum, slope = run.hyper[l]
             y = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
-            # one allocation for both towers: the library clears adjacent buffers with a single memset node
-            stats = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0)) if training else None
+            # per-CTA partial rows, summed in a fixed order by tmf_bn_finalize (deterministic; never zeroed)
+            stats = L.stat_buffers(ng, cout, dev) if training else None
             w = [P(t, l, 0) for t in range(ng)]
             b = [P(t, l, 1) for t in range(ng)]
             wd = None
@@ -108,7 +142,7 @@ class SNetFunction(torch.autograd.Function):
             L.call("tmf_bn_finalize", ng, L.ptrs(stats), L.ptrs([P(t, l, 2) for t in range(ng)]),
                    L.ptrs([P(t, l, 3) for t in range(ng)]), L.ptrs([buffers[t][l][0] for t in range(ng)]),
                    L.ptrs([buffers[t][l][1] for t in range(ng)]), L.ptrs([buffers[t][l][2] for t in range(ng)]),
-                   L.ptrs(coef), cout, count, BN_MOMENTUM, BN_EPS, int(training))
+                   L.ptrs(coef), cout, count, bn_momentum, bn_eps, int(training))
             last = l == len(spec.layers) - 1
             Do, Ho, Wo = _pooled(Dl, Hl, Wl, pool)
             out = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if last else torch.bfloat16, device=dev)
@@ -119,15 +153,17 @@ class SNetFunction(torch.autograd.Function):
                 # 1/8 of the voxels instead of all of y
                 ymax = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
                 L.call("tmf_bn_act_pool_fwd_keepmax", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), L.ptrs(ymax), int(last),
-                       B, Dl, Hl, Wl, cout, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
+                       B, Dl, Hl, Wl, cout, slope, tag=f"tmf_bn_act_pool_fwd@L{l}")
             else:
                 L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs(coef), L.ptrs(out), int(last), B, Dl, Hl, Wl, cout,
-                       pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_fwd@L{l}")
+                       pool, slope, tag=f"tmf_bn_act_pool_fwd@L{l}")
             if need_grad:
                 saved.append((act, y, coef, wd, dims, ymax))
             act = out
             dims = (Do, Ho, Wo)
         ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
+        ctx.hyper = run.hyper
+        ctx.params = params if need_grad else None          # references only (for the early gradient hand-off)
         ctx.impl = impl
         outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)      # logical (B,C,d,h,w), channels-last memory
         return outs if ng > 1 else outs[0]
@@ -136,6 +172,10 @@ class SNetFunction(torch.autograd.Function):
     def backward(ctx, *grads):
         spec, ng, B, training = ctx.spec, ctx.ng, ctx.B, ctx.training
         saved = ctx.saved
+        if saved is None or len(saved) != len(spec.layers):
+            raise RuntimeError("sNet backward: the saved activations are gone -- backward through this forward ran "
+                               "already (they are freed layer by layer; retain_graph / double backward are not "
+                               "supported), or the forward ran without autograd recording")
         dev = saved[0][1][0].device
         dout = []
         for t in range(ng):
@@ -153,14 +193,15 @@ class SNetFunction(torch.autograd.Function):
             cin, cout, ks, pool = spec.layers[l]
             act, y, coef, wd, (Dl, Hl, Wl), ymax = saved[l]
             count = B * Dl * Hl * Wl
-            sums = list(torch.empty((ng, 2 * cout), dtype=torch.float64, device=dev).unbind(0))
+            slope = ctx.hyper[l][2]
+            sums = L.stat_buffers(ng, cout, dev)
             if ymax is not None:
                 L.call("tmf_bn_maxpool_bwd_reduce_kept", ng, L.ptrs(dout), dout_fp32, L.ptrs(ymax), L.ptrs(coef),
-                       L.ptrs(sums), B, Dl // 2, Hl // 2, Wl // 2, cout, LRELU_SLOPE,
+                       L.ptrs(sums), B, Dl // 2, Hl // 2, Wl // 2, cout, slope,
                        tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
             else:
                 L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
-                       B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
+                       B, Dl, Hl, Wl, cout, pool, slope, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
             dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
             dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
@@ -175,17 +216,18 @@ class SNetFunction(torch.autograd.Function):
                 # block 1: BN/LeakyReLU/MaxPool backward "apply" + conv1.0 weight gradient in one pass; dy stays on chip
                 ws = torch.empty(fused_ws, dtype=torch.uint8, device=dev)
                 L.call("tmf_conv1_bwd_fused", ng, L.ptrs(dout), L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef), L.ptrs(act),
-                       L.ptrs(dw), B, Dl, Hl, Wl, cout, LRELU_SLOPE, L.ptr(ws), fused_ws)
-                for t in range(ng):
-                    base = (t * 7 + l) * 4
-                    pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
+                       L.ptrs(dw), B, Dl, Hl, Wl, cout, slope, L.ptr(ws), fused_ws)
+                SNetFunction._layer_grads(ctx, pgrads, l, dw, dbias, dgamma, dbeta)
                 saved[l] = None
                 continue
             dy = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
             L.call("tmf_bn_act_pool_bwd_apply", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef),
-                   L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, LRELU_SLOPE, tag=f"tmf_bn_act_pool_bwd_apply@L{l}")
+                   L.ptrs(dy), B, Dl, Hl, Wl, cout, pool, slope, tag=f"tmf_bn_act_pool_bwd_apply@L{l}")
             if l == 0:
-                L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout, ctx.impl)
+                nws = int(L.load().tmf_conv1_wgrad_workspace_bytes(ng, ctx.impl, Wl, cout))
+                ws = torch.empty(nws, dtype=torch.uint8, device=dev) if nws > 0 else None
+                L.call("tmf_conv1_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cout, ctx.impl,
+                       L.ptr(ws), nws)
             else:
                 ws = wgrad_workspace(ng, ctx.impl, B, Dl, Hl, Wl, cin, cout, ks, dev)
                 L.call("tmf_conv3d_wgrad", ng, L.ptrs(dy), L.ptrs(act), L.ptrs(dw), B, Dl, Hl, Wl, cin, cout, ks,
@@ -194,12 +236,27 @@ class SNetFunction(torch.autograd.Function):
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(dy), L.ptrs(wd), L.ptrs(None), L.ptrs(da), L.ptrs(None),
                        B, Dl, Hl, Wl, cout, cin, ks, ctx.impl, tag=f"tmf_conv3d_dgrad@L{l}")
                 dout, dout_fp32 = da, 0
-            for t in range(ng):
-                base = (t * 7 + l) * 4
-                pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
+            SNetFunction._layer_grads(ctx, pgrads, l, dw, dbias, dgamma, dbeta)
             saved[l] = None
         ctx.saved = None
+        ctx.params = None
         return (None, None, None, None) + (None,) * ng + tuple(pgrads)
+
+    @staticmethod
+    def _layer_grads(ctx, pgrads, l, dw, dbias, dgamma, dbeta):
+        """Record layer l's parameter gradients and hand them to the data-parallel reducer, if one is installed."""
+        ps, gs = [], []
+        for t in range(ctx.ng):
+            base = (t * 7 + l) * 4
+            pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
+            if _GRAD_SINK is not None and ctx.params is not None:
+                for k, g in enumerate((dw[t], dbias[t], dgamma[t], dbeta[t])):
+                    p = ctx.params[base + k]
+                    if p.requires_grad and p.grad is None:      # (an existing .grad means accumulation: leave it to autograd)
+                        ps.append(p)
+                        gs.append(g)
+        if ps:
+            _GRAD_SINK(ps, gs)
 
 
 # ==============================================================================================================

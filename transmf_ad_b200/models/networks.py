@@ -46,6 +46,22 @@ class sNet(nn.Module):
                 (self.conv3[0], self.conv3[1]), (self.conv3[3], self.conv3[4]), (self.conv4[0], self.conv4[1]),
                 (self.conv4[3], self.conv4[4])]
 
+    def _hyper(self):
+        """Per layer (eps, momentum, negative_slope) read from the BatchNorm3d / LeakyReLU children."""
+        seqs = [(self.conv1, 0), (self.conv2, 0), (self.conv2, 3), (self.conv3, 0), (self.conv3, 3), (self.conv4, 0),
+                (self.conv4, 3)]
+        out = []
+        for seq, i in seqs:
+            bn, act = seq[i + 1], seq[i + 2]
+            if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+                raise NotImplementedError("sNet on the B200 kernels needs affine BatchNorm3d with running statistics and "
+                                          "a numeric momentum (the reference's nn.BatchNorm3d defaults)")
+            out.append((float(bn.eps), float(bn.momentum), float(act.negative_slope)))
+        return out
+
+    def _run(self):
+        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper())
+
     def _params_and_buffers(self):
         params, bufs = [], []
         for conv, bn in self._units():
@@ -55,16 +71,17 @@ class sNet(nn.Module):
 
     def forward(self, mri):
         params, bufs = self._params_and_buffers()
-        return TF.SNetFunction.apply(self._spec, self.training, [bufs], 1, mri, *params)
+        return TF.SNetFunction.apply(self._spec, self._run(), [bufs], 1, mri, *params)
 
 
 def snet_pair_forward(net_a: sNet, net_b: sNet, xa, xb):
     """Run two towers of identical shape as one grouped launch sequence (grid.z = tower)."""
-    if net_a._spec.dim != net_b._spec.dim or net_a.training != net_b.training or tuple(xa.shape) != tuple(xb.shape):
+    if (net_a._spec.dim != net_b._spec.dim or net_a.training != net_b.training or tuple(xa.shape) != tuple(xb.shape)
+            or net_a._hyper() != net_b._hyper()):
         return net_a(xa), net_b(xb)
     pa, ba = net_a._params_and_buffers()
     pb, bb = net_b._params_and_buffers()
-    return TF.SNetFunction.apply(net_a._spec, net_a.training, [ba, bb], 2, xa, xb, *pa, *pb)
+    return TF.SNetFunction.apply(net_a._spec, net_a._run(), [ba, bb], 2, xa, xb, *pa, *pb)
 
 
 def tokens_of(feat):

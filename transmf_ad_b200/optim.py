@@ -44,9 +44,21 @@ class FusedAdam(torch.optim.Optimizer):
         for p in params:
             s = self.state[p]
             if "exp_avg" not in s:
-                s["step"] = st["step"]                      # one device counter shared by the group (same value for all)
                 s["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 s["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if s.get("step") is not st["step"]:
+                # state that came from load_state_dict (ours or torch.optim.Adam's) carries its own step value: the
+                # group's device counter -- the only one the kernel reads -- is seeded from it, then shared again
+                old = s.get("step")
+                if old is not None:
+                    val = float(old)
+                    if st.get("seeded") is not None and st["seeded"] != val:
+                        raise RuntimeError("FusedAdam: parameters of one group carry different step counts "
+                                           f"({st['seeded']} vs {val}); one device counter per group is supported")
+                    if st.get("seeded") is None:
+                        st["step"].fill_(val)
+                        st["seeded"] = val
+                s["step"] = st["step"]                      # one device counter shared by the group (same value for all)
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
                      self.state[p]["exp_avg_sq"].data_ptr(), p.numel()) for p in params)
         if key != st["key"]:
@@ -76,6 +88,12 @@ class FusedAdam(torch.optim.Optimizer):
             st["lr_pinned"][0] = float(group["lr"])
             st["lr"].copy_(st["lr_pinned"], non_blocking=True)
             st["lr_host"] = group["lr"]
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Adam-compatible: moments and the step count are restored (the per-parameter ``step`` entries are
+        re-bound to the group's device counter on the next ``step()``); chunk tables are rebuilt."""
+        super().load_state_dict(state_dict)
+        self._tables = {}
 
     def refresh_hyperparams(self):
         """Push a changed learning rate to the device without running ``step()`` (CUDA-graph replays skip the Python

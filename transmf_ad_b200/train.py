@@ -33,25 +33,40 @@ class GraphedTrainStep:
     (``.item()``) before the next call.
 
     world size 1 : zero_grad + forward + loss + backward + optimizer.step in ONE graph.
-    world size N : graph A = zero_grad + forward + loss + backward; then the bucketed NCCL all-reduce of ``reducer``
-                   on the (static) gradient tensors, eagerly; then graph B = optimizer.step.
+    world size N : the same ONE graph with the data-parallel exchange inside it: the reducer's autograd hooks and the conv
+                   stack's per-layer hand-off (``dp.GradBucketReducer.install``) run while the backward pass is being
+                   captured, so every bucket's pack -> ncclAllReduce -> unpack becomes a branch of the graph that
+                   overlaps the remaining backward kernels; ``reducer.finish()`` joins before the optimizer.
+                   ``TMF_DP_GRAPH=split`` selects the older, serial form (graph A = forward + backward; eager bucketed
+                   all-reduce; graph B = optimizer).
 
     The optimizer must be graph-capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).
+
+    Warm-up.  CUDA-graph capture needs ``warmup`` real steps on the example batch first (allocator, lazy inits).  With
+    ``restore_state=True`` (default) the model's parameters and buffers (BatchNorm running statistics,
+    ``num_batches_tracked``) and the optimizer's moments / step counts are put back afterwards, in place, so that the
+    first replay is step 1 of training exactly as in the eager loop (tests/test_gpu_train_path.py).
     """
 
-    def __init__(self, model, optimizer, loss_fn, example_inputs, example_targets, reducer=None, warmup=3):
+    def __init__(self, model, optimizer, loss_fn, example_inputs, example_targets, reducer=None, warmup=3,
+                 restore_state=True):
         self.model, self.optimizer, self.loss_fn, self.reducer = model, optimizer, loss_fn, reducer
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self.world > 1 and reducer is None:
             raise ValueError("world size > 1 needs a GradBucketReducer")
+        import os
+        self.split = self.world > 1 and os.environ.get("TMF_DP_GRAPH", "fused") == "split"
         if reducer is not None:
-            reducer.remove()                               # graph replays do not run autograd hooks: reduce_now() instead
+            if self.split or self.world == 1:
+                reducer.remove()                           # serial form: no hooks, reduce_now() between the two graphs
+            else:
+                reducer.install()                          # hooks + per-layer hand-off are captured with the backward
         self.launches_per_step = 0                         # libtmf kernel launches captured per step
         self.static_inputs = [t.clone() for t in _as_tuple(example_inputs)]
         self.static_targets = [t.clone() for t in _as_tuple(example_targets)]
         self.graph_fb, self.graph_opt = torch.cuda.CUDAGraph(), None
         self.outputs, self.losses = None, None
-        self._capture(warmup)
+        self._capture(warmup, restore_state)
 
     # ---- the step, in eager form (used for warm-up and as the thing that is captured) ---------------------------
     def _fwd_bwd(self):
@@ -63,17 +78,49 @@ class GraphedTrainStep:
 
     def _reduce(self):
         if self.world > 1:
-            self.reducer.reduce_now()
+            if self.split:
+                self.reducer.reduce_now()
+            else:
+                self.reducer.finish()
 
-    def _capture(self, warmup):
+    # ---- state snapshot around the warm-up steps ------------------------------------------------------------------
+    def _snapshot(self):
+        model = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        opt = {}
+        for p, st in self.optimizer.state.items():
+            opt[p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return model, opt
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        model, opt = snap
+        for k, v in self.model.state_dict().items():
+            v.copy_(model[k])                              # in place: the captured graph keeps these addresses
+        for p, st in self.optimizer.state.items():
+            old = opt.get(p)
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    if old is not None and k in old:
+                        v.copy_(old[k])
+                    else:
+                        v.zero_()                          # state created by the warm-up: back to "no step taken"
+                elif old is not None and k in old:
+                    st[k] = old[k]
+                elif isinstance(v, (int, float)):
+                    st[k] = type(v)(0)
+
+    def _capture(self, warmup, restore_state=True):
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        snap = self._snapshot() if restore_state else None
         with torch.cuda.stream(side):                      # warm-up on a side stream (allocator + lazy inits + autotune)
             for _ in range(max(1, warmup)):
                 self._fwd_bwd()
                 self._reduce()
                 self.optimizer.step()
+            if snap is not None:
+                self._restore(snap)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
@@ -82,12 +129,17 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph_fb):
                 self.outputs, self.losses = self._fwd_bwd()
                 self.optimizer.step()
-        else:
-            with torch.cuda.graph(self.graph_fb):
+        elif not self.split:
+            # NCCL's watchdog thread polls CUDA events while we capture: only this thread's calls are policed
+            with torch.cuda.graph(self.graph_fb, capture_error_mode="thread_local"):
                 self.outputs, self.losses = self._fwd_bwd()
-            self.reducer.bind_static_grads()               # the captured backward's .grad tensors are static from here on
+                self.reducer.finish()
+                self.optimizer.step()
+        else:
+            with torch.cuda.graph(self.graph_fb, capture_error_mode="thread_local"):
+                self.outputs, self.losses = self._fwd_bwd()
             self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool(), capture_error_mode="thread_local"):
                 self.optimizer.step()
         self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.synchronize()
@@ -101,7 +153,7 @@ class GraphedTrainStep:
         if refresh is not None:
             refresh()                                      # e.g. FusedAdam: a scheduler-changed lr reaches the device scalar
         self.graph_fb.replay()
-        if self.world > 1:
+        if self.split:
             self.reducer.reduce_now()
             self.graph_opt.replay()
         return self.losses
