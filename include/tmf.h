@@ -169,15 +169,22 @@ int tmf_linear_fwd(const float* x, const float* w, const float* bias, const floa
                    int M, int K, int N, int act, void* stream);
 /* dx[M,K] (+)= dy[M,N] . w[N,K] */
 int tmf_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, int N, int accumulate, void* stream);
+/* Scratch buffer of the entry points below that take `ws`: caller-owned, 256-byte aligned, tmf_scratch_bytes() bytes,
+ * ZERO-INITIALISED ONCE (its first 16 KB hold "last block" tickets that every kernel leaves zero again); one buffer per
+ * stream may be shared by all calls.  It carries split-K / per-block partial sums that the last block to finish adds
+ * in index order: the weight gradients of the fusion transformer are bitwise reproducible (no float atomics). */
+int64_t tmf_scratch_bytes(void);
 /* dw[N,K] = dy^T . x ; dbias[N] = column sums of dy (dbias may be NULL); both overwritten */
-int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* stream);
+int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* ws,
+                     size_t ws_bytes, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta (+ residual); saves mean / rstd per row.  reference models/networks.py:117,219 */
 int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
                       float* mean, float* rstd, int rows, int dim, float eps, void* stream);
-/* dx (+)= LN backward; dgamma / dbeta are ACCUMULATED into (caller zeroes). */
+/* dx (+)= LN backward; dgamma / dbeta are OVERWRITTEN (deterministic two-level sum; `ws` as described above). */
 int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* stream);
+                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* dx = dy * gelu'(pre)  (exact erf form, reference models/networks.py:129) */
 int tmf_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream);

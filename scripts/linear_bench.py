@@ -35,7 +35,7 @@ def main():
         ops = {
             "fwd": lambda: L.call("tmf_linear_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(None), L.ptr(y), L.ptr(None), m, K, N, 0),
             "dgrad": lambda: L.call("tmf_linear_dgrad", L.ptr(dy), L.ptr(w), L.ptr(dx), m, K, N, 0),
-            "wgrad": lambda: L.call("tmf_linear_wgrad", L.ptr(dy), L.ptr(x), L.ptr(dw), L.ptr(db), m, K, N),
+            "wgrad": lambda: L.call("tmf_linear_wgrad", L.ptr(dy), L.ptr(x), L.ptr(dw), L.ptr(db), m, K, N, L.ptr(L.scratch("cuda")[0]), L.scratch("cuda")[1]),
         }
         for op, fn in ops.items():
             for _ in range(3):

@@ -174,6 +174,10 @@ def parity_report(name, device="cuda"):
                        if not is_conv_bias(k) and float(sd[k].grad.norm()) >= 1e-5])
     rep["global_grad_cos_B"] = cosine(ours, ref32)
     rep["global_grad_cos_A_vs_B"] = cosine(ref, ref32)
+    for k, p in model.named_parameters():          # per tensor: how far bf16 rounding alone moves the gradient (full tensors)
+        if not grads[k]["missing"]:
+            grads[k]["cos_AB_full"] = cosine(sd[k].grad, sd32[k].grad)
+            grads[k]["cos_B_full"] = cosine(p.grad.detach().cpu(), sd32[k].grad)
     msd = model.state_dict()
     rep["buffers"] = {k: (int(msd[k]) == int(v)) if k.endswith("num_batches_tracked")
                       else float((msd[k].cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))

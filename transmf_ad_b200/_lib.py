@@ -36,9 +36,9 @@ SIGNATURES = {
     "tmf_bn_act_pool_bwd_apply": [_i, _pp, _i, _pp, _pp, _pp, _pp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_linear_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tmf_linear_dgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "tmf_linear_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tmf_linear_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
-    "tmf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tmf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "tmf_attn_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
@@ -47,7 +47,7 @@ SIGNATURES = {
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
     "tmf_adam_step": [_vp, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp],
 }
-PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []), "tmf_stat_rows": (_i, []),
+PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []), "tmf_stat_rows": (_i, []), "tmf_scratch_bytes": (_i64, []),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
          "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),
@@ -86,6 +86,21 @@ def stat_buffers(ng, channels, device):
     """``ng`` statistics buffers double[TMF_STAT_ROWS][2*channels] carved out of one allocation.  Every producer kernel
     writes all rows, so the buffer is NOT zeroed; ``tmf_bn_finalize`` / ``tmf_bn_bwd_finalize`` add the rows in order."""
     return list(torch.empty((ng, stat_rows(), 2 * channels), dtype=torch.float64, device=device).unbind(0))
+
+
+_SCRATCH = {}
+
+
+def scratch(device):
+    """(tensor, nbytes): the zero-initialised scratch buffer of include/tmf.h (tickets + deterministic partial sums), one
+    per (device, stream): kernels that share it are stream-ordered, and every kernel leaves the ticket area zero."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        buf = torch.zeros(int(load().tmf_scratch_bytes()), dtype=torch.uint8, device=dev)
+        _SCRATCH[key] = buf
+    return buf, buf.numel()
 
 
 def last_error():

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
 
 // Max-pool backward reduction from ymax (see bn_act_pool_fwd_kernel<true>): sum dz, sum dz*xhat over the pooled
 // positions;  dz = dout * LeakyReLU'(scale*ymax + shift),  xhat = (ymax - mean) * invstd.
-__global__ void __launch_bounds__(256, 4) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
+__global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
   const int g = blockIdx.z;
   extern __shared__ float red[];  // [16][256]
   const int CQ = p.C >> 3;
@@ -534,7 +534,8 @@ int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp3
   cudaStream_t st = (cudaStream_t)stream;
   const int pstep = 256 / (C / 8);
   int blocks = ceil_div(npos, (int64_t)pstep * 4);                 // >= 4 positions per thread
-  if (blocks > TMF_STAT_ROWS) blocks = TMF_STAT_ROWS;              // one statistics row per block
+  if (blocks > 148) blocks = 148;                                  // one statistics row per block (<= TMF_STAT_ROWS); with two
+                                                                   // towers that is 2 blocks of <= 128 registers per SM
   if (blocks < 1) blocks = 1;
   bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st>>>(p, (int)npos);
   TMF_LAUNCH_CHECK();

@@ -93,6 +93,30 @@ __device__ __forceinline__ void stat_row_store(double* buf, int ncols, int part,
   for (int r = part + nparts; r < TMF_STAT_ROWS; r += nparts) buf[(size_t)r * ncols + col] = 0.0;
 }
 
+// "Last block" rendezvous for deterministic cross-block reductions without a second launch: every block stores its partial
+// result to global scratch and calls this (all threads); it returns true in exactly one block -- the last of `nblocks` to
+// arrive -- after the other blocks' stores are visible to it, and re-zeroes the ticket for the next launch.  The caller's
+// last block then adds the partials in block-index order.  `ticket` must be zero before the first launch ever.
+__device__ __forceinline__ bool last_block_arrives(unsigned* ticket, unsigned nblocks) {
+  __shared__ int s_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_is_last = (t == nblocks - 1u) ? 1 : 0;
+    if (s_is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  const bool last = s_is_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// Layout of the caller-owned scratch buffer (`ws`) of the fusion-transformer entry points: tickets first (zero before the
+// first use, left zero by every kernel), then partial results.  tmf_scratch_bytes() is the size callers allocate.
+constexpr size_t TMF_WS_TICKET_BYTES = 16384;                 // 4096 tickets: [0,1024) LayerNorm, [1024,3072) GEMM tiles, [3072,4096) column sums
+constexpr size_t TMF_WS_BYTES = (size_t)16 << 20;
+
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -22,8 +22,25 @@ struct GemmArgs {
   int M, N, K;
   int64_t sAm, sAk, sBk, sBn;
   int act, accumulate;
-  int kchunk;                          // 0: whole K in one CTA; else K range per blockIdx.z, results added atomically to a zeroed C
+  int kchunk;                          // 0: whole K in one CTA; else K range per blockIdx.z: partial tiles go to `part`
+  float* part;                         // [gridDim.z][M][N] split-K partials (caller scratch)
+  unsigned* tickets;                   // one per output tile (zero; self-resetting): the last split adds the partials in order
 };
+
+// Split-K epilogue: after every thread of the block has stored its partial outputs to p.part[blockIdx.z], the last of
+// the gridDim.z blocks of this output tile adds the splits in index order (deterministic) and writes C.
+__device__ __forceinline__ void splitk_finish(const GemmArgs& p, int m0, int n0, int TM, int TN) {
+  if (!last_block_arrives(p.tickets + (blockIdx.y * gridDim.x + blockIdx.x), gridDim.z)) return;
+  const size_t mn = (size_t)p.M * p.N;
+  for (int idx = threadIdx.x; idx < TM * TN; idx += blockDim.x) {
+    const int m = m0 + idx / TN, n = n0 + idx % TN;
+    if (m >= p.M || n >= p.N) continue;
+    const size_t o = (size_t)m * p.N + n;
+    float s = 0.f;
+    for (unsigned z = 0; z < gridDim.z; ++z) s += __ldcg(p.part + z * mn + o);
+    p.C[o] = s;
+  }
+}
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       const int64_t o = (int64_t)m * p.N + n;
-      if (p.kchunk) { atomicAdd(p.C + o, v); continue; }
+      if (p.kchunk) { p.part[(size_t)blockIdx.z * p.M * p.N + o] = v; continue; }
       if (p.bias) v += p.bias[n];
       if (p.pre) p.pre[o] = v;
       if (p.act == 1) v = gelu_exact(v);
@@ -98,10 +115,13 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
       p.C[o] = v;
     }
   }
+  if (p.kchunk) splitk_finish(p, m0, n0, G_TM, G_TN);
 }
 
-// column sums: out[n] += sum over this block's rows of x[m,n]   (out zeroed by the caller; grid.y splits the rows)
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int rows_per_block) {
+// column sums: out[n] = sum over m of x[m,n].  grid.y splits the rows; partial sums go to part[gridDim.y][N] and the last
+// block of a column group adds them in index order (deterministic; no atomics, nothing to zero).
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int rows_per_block,
+                              float* __restrict__ partbuf, unsigned* __restrict__ tickets) {
   __shared__ float part[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r = threadIdx.x >> 5;
@@ -117,7 +137,13 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
-    atomicAdd(out + n, t);
+    partbuf[(size_t)blockIdx.y * N + n] = t;
+  }
+  if (!last_block_arrives(tickets + blockIdx.x, gridDim.y)) return;
+  if (r == 0 && n < N) {
+    float t = 0.f;
+    for (unsigned y = 0; y < gridDim.y; ++y) t += __ldcg(partbuf + (size_t)y * N + n);
+    out[n] = t;
   }
 }
 
@@ -176,7 +202,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim, int accumulate) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim, int accumulate,
+                     float* __restrict__ partbuf, unsigned* __restrict__ ticket) {
   extern __shared__ float sm[];  // [2][dim]
   for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -221,20 +248,31 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       }
     }
   }
+  // deterministic: the warps add their column sums into shared memory one after the other, the block stores its partial,
+  // and the last block to finish adds the blocks' partials in index order (dgamma / dbeta are overwritten)
+  for (int w = 0; w < 8; ++w) {
+    if ((int)(threadIdx.x >> 5) == w) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nv) {
-      atomicAdd(&sm[c * 4 + 0], ag[i].x); atomicAdd(&sm[c * 4 + 1], ag[i].y);
-      atomicAdd(&sm[c * 4 + 2], ag[i].z); atomicAdd(&sm[c * 4 + 3], ag[i].w);
-      atomicAdd(&sm[dim + c * 4 + 0], ab[i].x); atomicAdd(&sm[dim + c * 4 + 1], ab[i].y);
-      atomicAdd(&sm[dim + c * 4 + 2], ab[i].z); atomicAdd(&sm[dim + c * 4 + 3], ab[i].w);
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+          float4* sg = reinterpret_cast<float4*>(sm) + c;
+          float4* sb = reinterpret_cast<float4*>(sm + dim) + c;
+          float4 a = *sg, b = *sb;
+          a.x += ag[i].x; a.y += ag[i].y; a.z += ag[i].z; a.w += ag[i].w;
+          b.x += ab[i].x; b.y += ab[i].y; b.z += ab[i].z; b.w += ab[i].w;
+          *sg = a; *sb = b;
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sm[i]);
-    atomicAdd(&dbeta[i], sm[dim + i]);
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) partbuf[(size_t)blockIdx.x * 2 * dim + i] = sm[i];
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) {
+    float t = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partbuf + (size_t)b * 2 * dim + i);
+    if (i < dim) dgamma[i] = t; else dbeta[i - dim] = t;
   }
 }
 
@@ -612,7 +650,7 @@ __global__ void __launch_bounds__(F_THREADS) gemm_pipe_kernel(GemmArgs p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       const int64_t o = (int64_t)m * p.N + n;
-      if (p.kchunk) { atomicAdd(p.C + o, v); continue; }
+      if (p.kchunk) { p.part[(size_t)blockIdx.z * p.M * p.N + o] = v; continue; }
       if (p.bias) v += __ldg(p.bias + n);
       if (p.pre) p.pre[o] = v;
       if (p.act == 1) v = gelu_exact(v);
@@ -621,6 +659,7 @@ __global__ void __launch_bounds__(F_THREADS) gemm_pipe_kernel(GemmArgs p) {
       p.C[o] = v;
     }
   }
+  if (p.kchunk) splitk_finish(p, m0, n0, F_TM, F_TN);
 }
 
 
@@ -753,7 +792,7 @@ __global__ void __launch_bounds__(V_THREADS) gemm_ksplit_kernel(GemmArgs p) {
         if (n >= p.N) continue;
         float val = o4[e];
         const int64_t o = (int64_t)m * p.N + n;
-        if (p.kchunk) { atomicAdd(p.C + o, val); continue; }
+        if (p.kchunk) { p.part[(size_t)blockIdx.z * p.M * p.N + o] = val; continue; }
         if (p.bias) val += __ldg(p.bias + n);
         if (p.pre) p.pre[o] = val;
         if (p.act == 1) val = gelu_exact(val);
@@ -763,6 +802,7 @@ __global__ void __launch_bounds__(V_THREADS) gemm_ksplit_kernel(GemmArgs p) {
       }
     }
   }
+  if (p.kchunk) splitk_finish(p, m0, n0, V_TM, V_TN);
 }
 
 static bool gemm_pipe_eligible(const GemmArgs& p) {
@@ -866,8 +906,19 @@ int tmf_linear_dgrad(const float* dy, const float* w, float* dx, int M, int K, i
   return launch_gemm(p, (cudaStream_t)stream);
 }
 
-int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* stream) {
+static int check_ws(const char* who, void* ws, size_t ws_bytes) {
+  TMF_REQUIRE(ws != nullptr && ws_bytes >= TMF_WS_BYTES && ((uintptr_t)ws & 255) == 0,
+              "%s: needs the 256-byte aligned scratch buffer of tmf_scratch_bytes() bytes (tickets zero-initialised)", who);
+  return 0;
+}
+
+int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int M, int K, int N, void* ws,
+                     size_t ws_bytes, void* stream) {
   TMF_REQUIRE(dy && x && dw, "linear_wgrad: NULL pointer");
+  if (check_ws("linear_wgrad", ws, ws_bytes)) return 1;
+  unsigned* tickets = reinterpret_cast<unsigned*>(ws);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + TMF_WS_TICKET_BYTES);
+  const size_t part_floats = (TMF_WS_BYTES - TMF_WS_TICKET_BYTES) / sizeof(float);
   GemmArgs p{};
   p.A = dy; p.B = x; p.C = dw;
   p.M = N; p.N = K; p.K = M;          // dw[N,K] = dy^T[N,M] . x[M,K]
@@ -888,18 +939,32 @@ int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, i
         p.kchunk = ceil_div(ceil_div(M, splits), F_TK) * F_TK;
       }
     }
-    TMF_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    // split-K partial tiles meet in the scratch buffer; the last split of a tile adds them in order (deterministic)
+    const int splits = ceil_div(M, p.kchunk);
+    const int tiles = gemm_pipe_eligible(p) ? (gemm_variant() >= 2 ? ceil_div(N, V_TM) * ceil_div(K, V_TN)
+                                                                    : ceil_div(N, F_TM) * ceil_div(K, F_TN))
+                                            : ceil_div(N, G_TM) * ceil_div(K, G_TN);
+    if (tiles > 2048 || (size_t)splits * N * K > part_floats) {
+      p.kchunk = 0;                      // too large for the scratch buffer: one CTA per tile walks the whole reduction
+    } else {
+      p.part = partials;
+      p.tickets = tickets + 1024;
+    }
   }
   if (launch_gemm(p, st)) return 3;
   if (dbias) {
-    TMF_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)N, st));
-    const int rows = 128;
+    int rows = 128;
+    while ((size_t)ceil_div(M, rows) * N > part_floats) rows *= 2;
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows), 1);
-    colsum_kernel<<<grid, 256, 0, st>>>(dy, dbias, M, N, rows);
+    TMF_REQUIRE(grid.x <= 1024, "linear_wgrad: N=%d too wide for the column-sum tickets", N);
+    // (runs after the GEMM in stream order, so it may reuse the partial area)
+    colsum_kernel<<<grid, 256, 0, st>>>(dy, dbias, M, N, rows, partials, tickets + 3072);
     TMF_LAUNCH_CHECK();
   }
   return 0;
 }
+
+int64_t tmf_scratch_bytes(void) { return (int64_t)TMF_WS_BYTES; }
 
 int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
                       float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
@@ -912,13 +977,15 @@ int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, con
 }
 
 int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* stream) {
+                      float* dx, float* dgamma, float* dbeta, int rows, int dim, int accumulate, void* ws,
+                      size_t ws_bytes, void* stream) {
   TMF_REQUIRE(dim % 4 == 0 && dim <= 128 * LN_MAXV, "layernorm: dim must be a multiple of 4 and <= %d (got %d)",
               128 * LN_MAXV, dim);
+  if (check_ws("layernorm_bwd", ws, ws_bytes)) return 1;
   const int grid = max(1, min(ceil_div(rows, 8 * 4), 148));
-  layernorm_bwd_kernel<<<grid, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx,
-                                                                                      dgamma, dbeta, rows, dim,
-                                                                                      accumulate);
+  layernorm_bwd_kernel<<<grid, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, dim, accumulate,
+      reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + TMF_WS_TICKET_BYTES), reinterpret_cast<unsigned*>(ws));
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -300,7 +300,8 @@ class LinearFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
             db = torch.empty(N, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
-            L.call("tmf_linear_wgrad", L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, K, N)
+            ws, nws = L.scratch(dy2.device)
+            L.call("tmf_linear_wgrad", L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, K, N, L.ptr(ws), nws)
         return dx, dw, db, dres, None
 
 
@@ -332,9 +333,10 @@ class LayerNormFunction(torch.autograd.Function):
         rows, dim = x2.shape
         dy2 = _f32c(dy).reshape(rows, dim)
         dx = torch.empty_like(x2)
-        dgb = torch.zeros((2, dim), dtype=torch.float32, device=x2.device)
+        dgb = torch.empty((2, dim), dtype=torch.float32, device=x2.device)
+        ws, nws = L.scratch(x2.device)
         L.call("tmf_layernorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dgb[0]),
-               L.ptr(dgb[1]), rows, dim, 0)
+               L.ptr(dgb[1]), rows, dim, 0, L.ptr(ws), nws)
         return dx.reshape(dy.shape), dgb[0], dgb[1], (dy if ctx.has_res else None), None
 
 
