@@ -1,26 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- train subjects/s (MRI+PET pairs) of the TransMF_AD hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--workload cnn_ad|ad|single] [--batch B] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload both|ad|cnn_ad|single] [--batch B] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 One "step" = the caller's train_step (reference kfold_train_adversarial.py:101-136): forward, CE + adversarial
 losses, backward, (gradient all-reduce for N > 1) and the Adam step of utils/utils.py:38-41, on one batch of
-synthetic paired volumes of shape (B,1,91,109,91).  Weak scaling: B per GPU is fixed.  Rank 0 prints ONE JSON line.
+synthetic paired volumes of shape (B,1,91,109,91).  Rank 0 prints ONE JSON line.
 
-``value``   device-timed (CUDA events, max over ranks) with the batch already resident in HBM.
-``e2e``     same step driven from PINNED HOST buffers: H2D copy of MRI/PET/labels and the two ``.item()`` loss
-            reads (D2H) inside the timed region.
-``roofline``     conv3d kernels (fwd + dgrad + wgrad, algorithmic FLOPs of SURVEY.md section 8d) timed live with CUDA
-                 events around each launch in a separate profiled pass, against the measured bf16 peak.
-``cpu_baseline`` the CPU oracle port (oracle/restatement.py; the reference is pure PyTorch) timed on the host cores
-                 on a bounded sample (B=2) of the same workload.
-``--impl reference`` times that CPU port alone and prints the same line shape with "impl": "reference".
+Headline (``value``, ``e2e``, ``roofline``): BASELINE configs[2] = ``model_ad`` (``--model Transformer``, the reference's
+main entry), batch 8 per GPU, weak scaling.  ``workloads`` carries the same numbers for configs[1] (``model_CNN_ad``,
+``--model CNN``) beside it.
+
+``value``         device-timed (CUDA events, max over ranks) with the batch already resident in HBM.
+``e2e``           same step driven from PINNED HOST buffers: H2D copy of MRI/PET/labels and the two loss reads (D2H) inside
+                  the timed region.
+``roofline``      conv3d kernels conv2.0 .. conv4.3 (fwd + dgrad + wgrad, algorithmic FLOPs of SURVEY.md section 8d): CUDA events
+                  around every launch of one step whose launches were enqueued behind a spin kernel (so the events see
+                  back-to-back device execution, not host launch gaps), against the measured BURST bf16 peak (kernels of
+                  20-230 us timed one by one run at full clock); the sustained-peak fraction is given beside it.
+``eager_dropin``  what the UNCHANGED reference loop gets: eager launches + torch.optim.Adam + .item() reads, host buffers.
+``sustained``     >= 2000 graph replays back to back with the clock record (steady-state clocks / power).
+``c4``            (N > 1) BASELINE configs[3]: model_ad, global batch 64 split over the ranks (strong scaling).
+``cpu_baseline``  the CPU oracle port (oracle/restatement.py; the reference is pure PyTorch) timed on the host cores on
+                  BASELINE configs[0] (model_ad, batch 2).
+``--impl reference`` times that CPU port alone (batch 2 per step -- stated in config.workload -- honouring --steps/--warmup)
+                  and prints the same line shape with "impl": "reference".
 """
 from __future__ import annotations
 
 import argparse
+import gc
+import hashlib
 import json
 import os
 import statistics
@@ -43,6 +55,7 @@ WORKLOADS = {
            "model_ad (--model Transformer) adversarial train step"),
     "single": ("model_single", dict(dim=128), 1, "model_single (kfold_train_single) train step"),
 }
+CPU_SAMPLE_BATCH = 2      # BASELINE configs[0] / the reference's default --batch_size
 
 
 def conv_flops_per_subject(shape, dim=128, towers=2, first_layer=True, other_layers=True):
@@ -95,6 +108,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def library_hash():
+    """sha256 (first 16 hex) of the loaded libtmf_sm100a.so and of the sources it was built from (stale-binary check)."""
+    from transmf_ad_b200 import _lib, build
+    with open(_lib.LIB_PATH, "rb") as f:
+        so = hashlib.sha256(f.read()).hexdigest()[:16]
+    return {"so_sha256_16": so, "sources_sha256_16": build.source_hash()[:16], "built_from": build.recorded_hash()[:16]}
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -141,6 +162,46 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_local_numa(local_rank, world):
+    """CPU affinity of this rank = its share of the cores of the GPU's NUMA node (pinned-buffer pages are then allocated and
+    copied from node-local memory; round 1 had every rank on cores 0-31 of node 0: 31 GB/s H2D per rank at N = 8)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=20).stdout
+        node_of = {}
+        for line in out.strip().splitlines():
+            idx, bus = [x.strip() for x in line.split(",")]
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:                  # 00000000:1b:00.0 -> 0000:1b:00.0
+                bus = bus[4:]
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node_of[int(idx)] = int(f.read().strip())
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = [int(x) for x in visible.split(",")] if visible and all(x.strip().isdigit() for x in visible.split(",")) \
+            else sorted(node_of)
+        node = node_of[phys[local_rank]]
+        if node < 0:
+            return {"numa_node": -1}
+        cpus = []
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        peers = [r for r in range(world) if r < len(phys) and node_of.get(phys[r]) == node]      # ranks sharing the node
+        if local_rank in peers and len(peers) > 1:
+            per = max(1, len(allowed) // len(peers))
+            i = peers.index(local_rank)
+            mine = allowed[i * per:(i + 1) * per] or allowed
+        else:
+            mine = allowed
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), 8)))
+        return {"numa_node": node, "cpus": f"{mine[0]}-{mine[-1]} ({len(mine)})"}
+    except Exception as e:                                    # affinity is an optimisation, never a failure
+        return {"error": str(e)[:120]}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_port_step_fn(workload, batch):
     """The CPU oracle port of the same train step (fwd + losses + bwd + Adam) on a bounded sample."""
@@ -171,7 +232,7 @@ def cpu_port_step_fn(workload, batch):
             total = torch.nn.functional.cross_entropy(outs[0], label)
         total.backward()
         opt.step()
-        return float(total)
+        return float(total.detach())
 
     return step
 
@@ -186,83 +247,96 @@ def time_cpu_port(workload, batch, steps, warmup):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    return batch / min(ts), sum(ts) / len(ts)
+    return batch * len(ts) / sum(ts), sum(ts) / len(ts), batch / min(ts)
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    sample_b = 2
-    kind, kwargs, towers, desc = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))
-    warm = 1
-    sps, mean_s = time_cpu_port(args.workload, sample_b, steps, warm)
+    workload = "ad" if args.workload == "both" else args.workload
+    kind, kwargs, towers, desc = WORKLOADS[workload]
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sps, mean_s, best = time_cpu_port(workload, CPU_SAMPLE_BATCH, steps, warm)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "subjects/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{desc}, batch {args.batch}/GPU, volumes 91x109x91", "timed_on": "host CPU"},
-        "cpu_baseline": {"value": sps, "unit": "subjects/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of batch {sample_b} (best step), fwd+bwd+Adam, fp32, torch CPU "
-                                   f"{torch.__version__}; oracle/restatement.py (the reference is pure PyTorch)"},
+        "config": {"workload": f"{desc}, volumes 91x109x91 fp32, Adam lr 1e-4; CPU arm: bounded sample of batch "
+                               f"{CPU_SAMPLE_BATCH} per step (the reference's default --batch_size, BASELINE configs[0]); "
+                               f"subjects/s does not depend on the batch on the CPU (8.4 s at batch 8 vs 2.2 s at batch 2, "
+                               f"BASELINE.md section 2)",
+                   "timed_on": "host CPU", "sample_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": sps, "unit": "subjects/s", "cores": cores, "kind": "port", "best_step_value": best,
+                         "sample": f"{steps} steps (after {warm} warm-up) of batch {CPU_SAMPLE_BATCH}, mean step, fwd+bwd+Adam, fp32, "
+                                   f"torch CPU {torch.__version__}; oracle/restatement.py (the reference is pure PyTorch)"},
         "e2e": {"value": sps, "unit": "subjects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cnn_ad", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8, help="subjects per GPU per step")
-    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
-                    help="graph: the step replayed as CUDA graphs (transmf_ad_b200.train.GraphedTrainStep); "
-                         "eager: the reference's Python loop, one launch at a time")
-    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
-                    help="fused: transmf_ad_b200.optim.FusedAdam (one launch); torch: torch.optim.Adam as the reference builds it")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+class Job:
+    """One process of the job: device, process group, helpers shared by the measurement legs."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank)
-        return
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args, self.dist = args, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.affinity = pin_to_local_numa(self.local_rank, self.world) if self.world > 1 else None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        if self.world != args.gpus and self.rank == 0:
+            print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={self.world}", file=sys.stderr)
 
-    import torch.distributed as dist
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def timed(self, fn, steps):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+
+def measure(job, workload, B, steps, warmup, mode="graph", optimizer="fused", want_e2e=True, want_roofline=False,
+            sustained_steps=0, sample_clocks=False):
+    """All legs for one workload at per-GPU batch B.  Returns a dict (rank 0 fills the clock record)."""
     from transmf_ad_b200 import _lib
     from transmf_ad_b200.dp import GradBucketReducer
     from transmf_ad_b200.models import mymodel as M
     from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    if world != args.gpus and rank == 0:
-        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-
-    kind, kwargs, towers, desc = WORKLOADS[args.workload]
-    B = args.batch
+    rank, world, dev = job.rank, job.world, job.dev
+    kind, kwargs, towers, desc = WORKLOADS[workload]
     model = getattr(M, kind)(**kwargs)
     model.load_state_dict(procedural_state(model.state_dict(), seed=0))     # identical replicas on every rank
     model = model.to(dev).train()
-    graph_mode = args.mode == "graph"
-    if args.optimizer == "fused":                                            # utils/utils.py:38-41 (Adam branch), one launch
+    graph_mode = mode == "graph"
+    if optimizer == "fused":                                                 # utils/utils.py:38-41 (Adam branch), one launch
         from transmf_ad_b200.optim import FusedAdam
         opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)
     else:
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0, capturable=graph_mode)
-    reducer = GradBucketReducer(model.parameters())
+    reducer = GradBucketReducer(model=model)
+    if world > 1:
+        reducer.install()
     ce_fn = torch.nn.CrossEntropyLoss()
     ones = torch.ones(B, dtype=torch.int64, device=dev)
     zeros = torch.zeros(B, dtype=torch.int64, device=dev)
@@ -299,24 +373,6 @@ def main():
         opt.step()
         return vals
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
     def inputs_of(batch):
         return batch[:1] if towers == 1 else batch[:2]
 
@@ -328,11 +384,10 @@ def main():
             ce, ad, total = losses(outs, label)
             return (total, ce) if ad is None else (total, ce, ad)
 
-        for i in range(args.warmup):                         # eager warm-up (lazy inits, allocator, attribute calls)
+        for i in range(2):                                   # eager warm-up (lazy inits, allocator, attribute calls)
             train_step(pool_d[i % npool], False)
-        barrier()
-        graphed = GraphedTrainStep(model, opt, graph_loss, inputs_of(pool_d[0]), pool_d[0][2], reducer=reducer,
-                                   warmup=args.warmup)
+        job.barrier()
+        graphed = GraphedTrainStep(model, opt, graph_loss, inputs_of(pool_d[0]), pool_d[0][2], reducer=reducer, warmup=3)
 
         def dev_step(i):
             b = pool_d[i % npool]
@@ -342,90 +397,105 @@ def main():
             train_step(pool_d[i % npool], False)
 
     # ---- warm-up, then the device-resident timed region ---------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         dev_step(i)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(job.local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
     n0 = _lib.launch_count()
-    total_ms = timed(dev_step, args.steps)
-    launches = (graphed.launches_per_step * args.steps) if graph_mode else (_lib.launch_count() - n0)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = total_ms / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    total_ms = job.timed(dev_step, steps)
+    launches = (graphed.launches_per_step * steps) if graph_mode else (_lib.launch_count() - n0)
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = total_ms / steps
+    res = {"workload": workload, "desc": desc, "batch_per_gpu": B, "value": world * B / (ms_per_step * 1e-3),
+           "ms_per_step": ms_per_step, "gpu_launches": int(launches), "clocks": clocks, "steps": steps,
+           "launches_per_step": int(launches // max(steps, 1))}
 
-    # ---- end-to-end: pinned host buffers, H2D inside the timed region, loss .item() reads ----------------------------
-    if graph_mode:
-        # batch i+1 is copied from pinned host memory on a side stream while step i runs (DevicePrefetcher); every
-        # step's inputs cross PCIe inside the timed region and both loss values are read back each step.
-        reader = LossReader(2 if towers > 1 else 1, dev)
-        e2e_state = {}
+    # ---- end-to-end: pinned host buffers, H2D inside the timed region, loss reads ------------------------------------
+    if want_e2e:
+        if graph_mode:
+            # batch i+1 is copied from pinned host memory on a side stream while step i runs (DevicePrefetcher); every
+            # step's inputs cross PCIe inside the timed region and both loss values are read back each step, the host
+            # blocking on step i's values only after step i+1 has been enqueued (LossReader).
+            reader = LossReader(2 if towers > 1 else 1, dev)
+            e2e_state = {}
 
-        def e2e_run(steps):
-            def host_batches():
-                for i in range(steps):
-                    hb = pool_h[i % npool]
-                    yield (hb[0], hb[2]) if towers == 1 else hb
-            # every step's two loss values cross to the host inside the timed region, but the host blocks on step
-            # i's values only after step i+1 has been enqueued (LossReader), so the graph launch, the H2D of the next
-            # batch and the device work of the current one overlap instead of serialising on .item().
-            vals = None
-            pf = DevicePrefetcher(host_batches(), dev, reuse=e2e_state.get("pf"))
-            e2e_state["pf"] = pf                             # the next "epoch" reuses its stream and device buffers
-            for db in pf:
-                out = graphed(db[:-1], db[-1])
-                vals = reader.push(out[1:])
-            vals = reader.flush()
-            return vals
+            def e2e_run(n):
+                def host_batches():
+                    for i in range(n):
+                        hb = pool_h[i % npool]
+                        yield (hb[0], hb[2]) if towers == 1 else hb
+                pf = DevicePrefetcher(host_batches(), dev, reuse=e2e_state.get("pf"))
+                e2e_state["pf"] = pf                         # the next "epoch" reuses its stream and device buffers
+                for db in pf:
+                    out = graphed(db[:-1], db[-1])
+                    reader.push(out[1:])
+                return reader.flush()
 
-        e2e_run(2)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_run(args.steps)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(ms) / args.steps
-    else:
-        def e2e_step(i):
-            hb = pool_h[i % npool]
-            db = tuple(t.to(dev, non_blocking=True) for t in hb)
-            train_step(db, True)
+            e2e_run(2)
+            job.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            e2e_run(steps)
+            e1.record()
+            job.barrier()
+            e2e_ms = job.max_over_ranks(e0.elapsed_time(e1)) / steps
+        else:
+            def e2e_step(i):
+                hb = pool_h[i % npool]
+                db = tuple(t.to(dev, non_blocking=True) for t in hb)
+                train_step(db, True)
 
-        for i in range(2):
-            e2e_step(i)
-        e2e_ms = timed(e2e_step, args.steps) / args.steps
-    h2d = sum(t.numel() * t.element_size() for t in pool_h[0][: (1 if towers == 1 else 2)]) + pool_h[0][2].numel() * 8
-    # the PCIe leg on its own (pinned host -> device, nothing else running): when e2e ~= this, the step is link-bound
-    probe_dst = [torch.empty_like(t, device=dev) for t in pool_h[0][: (1 if towers == 1 else 2)]]
-    h2d_ms_alone = []
-    for _ in range(3):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for d, hsrc in zip(probe_dst, pool_h[0]):
-            d.copy_(hsrc, non_blocking=True)
-        e1.record()
-        torch.cuda.synchronize()
-        h2d_ms_alone.append(e0.elapsed_time(e1))
-    del probe_dst
-    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "subjects/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": (8 if towers > 1 else 4) * world,   # whole job
-           "h2d_ms_alone": round(min(h2d_ms_alone), 4), "h2d_gbs_alone": round(h2d / min(h2d_ms_alone) / 1e6, 2),      # one rank's link
-           "h2d_bytes_per_rank": int(h2d)}
+            for i in range(2):
+                e2e_step(i)
+            e2e_ms = job.timed(e2e_step, steps) / steps
+        h2d = sum(t.numel() * t.element_size() for t in pool_h[0][: (1 if towers == 1 else 2)]) + pool_h[0][2].numel() * 8
+        # the PCIe leg on its own (pinned host -> device, nothing else running): when e2e ~= this, the step is link-bound
+        probe_dst = [torch.empty_like(t, device=dev) for t in pool_h[0][: (1 if towers == 1 else 2)]]
+        h2d_ms_alone = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for d, hsrc in zip(probe_dst, pool_h[0]):
+                d.copy_(hsrc, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            h2d_ms_alone.append(e0.elapsed_time(e1))
+        del probe_dst
+        res["e2e"] = {"value": world * B / (e2e_ms * 1e-3), "unit": "subjects/s", "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": (8 if towers > 1 else 4) * world,
+                      "h2d_ms_alone": round(min(h2d_ms_alone), 4), "h2d_gbs_alone": round(h2d / min(h2d_ms_alone) / 1e6, 2),
+                      "h2d_bytes_per_rank": int(h2d)}
+
+    # ---- sustained: thousands of replays back to back, clocks recorded ---------------------------------------------
+    if sustained_steps > 0 and graph_mode:
+        s2 = ClockSampler(job.local_rank) if rank == 0 else None
+        if s2:
+            s2.start()
+        ms = job.timed(dev_step, sustained_steps)
+        c2 = s2.stop() if s2 else None
+        res["sustained"] = {"steps": sustained_steps, "ms_per_step": ms / sustained_steps,
+                            "value": world * B / (ms / sustained_steps * 1e-3), "unit": "subjects/s",
+                            "seconds": round(ms * 1e-3, 2), "clocks": c2}
 
     # ---- roofline leg: CUDA events around every C-ABI launch (separate pass; not part of `value`) --------------------
-    roofline, breakdown = None, None
-    if not args.no_roofline:
+    if want_roofline:
         peaks = measured_peaks()
-        _lib.TIMER.start()
-        nprof = 2
+        nprof = 3
+        rec = {}
         for i in range(nprof):
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(1.5e8))                    # ~75 ms spin: the host enqueues the whole step behind it, so
+            _lib.TIMER.start()                               # the events bracket back-to-back device execution
             train_step(pool_d[i % npool], False)
-        rec = _lib.TIMER.stop()
+            r = _lib.TIMER.stop()
+            if i == 0:
+                continue                                     # first pass: warm-up of the timing path itself
+            for t, (ms, n) in r.items():
+                a = rec.get(t, (0.0, 0))
+                rec[t] = (a[0] + ms, a[1] + n)
+        nprof -= 1
         # dominant kernel family: the tcgen05 implicit-GEMM convolutions conv2.0 .. conv4.3 (fwd, dgrad, wgrad), the
         # layers SURVEY.md section 8d puts under the tensor roofline.  conv1.0 (Cin = 1, 26 FLOP/B) is HBM-bound and
         # is reported against the copy bandwidth below, together with the other block-1 passes.
@@ -437,7 +507,6 @@ def main():
         flops_all = conv_flops_per_subject(SHAPE, kwargs["dim"], towers) * B
         achieved = flops / (gemm_ms * 1e-3) / 1e12
         achieved_all = flops_all / ((gemm_ms + conv1_ms) * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
         traffic = committed_traffic()
         hbm = {}
         for tag, nbytes in block1_bytes_per_subject(SHAPE, kwargs["dim"], towers).items():
@@ -446,51 +515,115 @@ def main():
                 gbs = nbytes * B / (ms * 1e-3) / 1e9
                 hbm[tag] = {"ms": round(ms, 4), "algorithmic_mb": round(nbytes * B / 1e6, 1), "achieved_gbs": round(gbs, 1),
                             "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3)}
-        roofline = {"bound": "tensor",
-                    "kernel": "conv3d implicit GEMM on tcgen05: fwd + dgrad + wgrad of conv2.0 .. conv4.3, both towers "
-                              "(18 launches per step)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic["dram_bytes_per_step"] if traffic else None,
-                    "traffic_source": traffic["source"] if traffic else None,
-                    "peak_source": f"{peaks['source']} bf16 sustained (kernels timed inside the step)",
-                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
-                    "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": gemm_ms,
-                    "all_conv_incl_conv1": {"achieved": achieved_all, "frac": achieved_all / peak,
-                                            "algorithmic_gflop_per_step": flops_all / 1e9,
-                                            "ms_per_step": gemm_ms + conv1_ms,
-                                            "note": "conv1.0 fwd and the fused block-1 backward (BN/LeakyReLU/MaxPool "
-                                                    "backward + conv1.0 wgrad) are HBM-bound passes; their whole time is "
-                                                    "counted here"},
-                    "hbm_bound_block1": {"peak_gbs": peaks["hbm_gbs"], "kernels": hbm}}
-        breakdown = {t: round(rec[t][0] / nprof, 4) for t in sorted(rec)}          # ms per step per entry point (@L = layer)
+        res["roofline"] = {
+            "bound": "tensor",
+            "kernel": "conv3d implicit GEMM on tcgen05: fwd + dgrad + wgrad of conv2.0 .. conv4.3, both towers (18 launches per step)",
+            "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+            "peak_source": f"{peaks['source']} bf16 BURST (each launch is 20-230 us, event-timed on its own at full clock)",
+            "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+            "traffic": traffic["dram_bytes_per_step"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else None,
+            "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": gemm_ms,
+            "timing": "CUDA events around each launch; launches enqueued behind a spin kernel (no host gaps inside the brackets)",
+            "all_conv_incl_conv1": {"achieved": achieved_all, "frac": achieved_all / peaks["bf16_tflops"],
+                                    "algorithmic_gflop_per_step": flops_all / 1e9, "ms_per_step": gemm_ms + conv1_ms,
+                                    "note": "conv1.0 fwd and the fused block-1 backward (BN/LeakyReLU/MaxPool backward + conv1.0 "
+                                            "wgrad) are HBM-bound passes; their whole time is counted here"},
+            "hbm_bound_block1": {"peak_gbs": peaks["hbm_gbs"], "kernels": hbm}}
+        res["breakdown"] = {t: round(rec[t][0] / nprof, 4) for t in sorted(rec)}   # ms per step per entry point (@L = layer)
 
-    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------
+    reducer.remove()
+    del graphed, model, opt, reducer, pool_d, pool_h
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="both", choices=sorted(WORKLOADS) + ["both"],
+                    help="both: model_ad is the headline, model_CNN_ad rides in `workloads`")
+    ap.add_argument("--batch", type=int, default=8, help="subjects per GPU per step")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the step replayed as CUDA graphs (transmf_ad_b200.train.GraphedTrainStep); "
+                         "eager: the reference's Python loop, one launch at a time")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: transmf_ad_b200.optim.FusedAdam (one launch); torch: torch.optim.Adam as the reference builds it")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the eager_dropin / sustained / c4 sub-records")
+    ap.add_argument("--sustained-steps", type=int, default=2000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args, int(os.environ.get("RANK", "0")))
+        return
+    args.warmup = max(args.warmup, 3)
+
+    job = Job(args)
+    rank, world = job.rank, job.world
+    B = args.batch
+    head_name = "ad" if args.workload == "both" else args.workload
+    head = measure(job, head_name, B, args.steps, args.warmup, args.mode, args.optimizer, want_e2e=True,
+                   want_roofline=not args.no_roofline, sample_clocks=True,
+                   sustained_steps=(args.sustained_steps if (world == 1 and not args.no_extras and args.mode == "graph") else 0))
+    others = {}
+    if args.workload == "both":
+        r = measure(job, "cnn_ad", B, args.steps, args.warmup, args.mode, args.optimizer, want_e2e=True, want_roofline=False)
+        others["cnn_ad"] = {k: r[k] for k in ("desc", "batch_per_gpu", "value", "ms_per_step", "e2e", "launches_per_step")}
+    extras = {}
+    if not args.no_extras and world == 1 and args.mode == "graph":
+        r = measure(job, head_name, B, max(5, min(args.steps, 10)), 3, "eager", "torch", want_e2e=True, want_roofline=False)
+        extras["eager_dropin"] = {"what": "the reference's unchanged loop on these modules: eager launches, torch.optim.Adam, "
+                                          "host batches copied with .to(device), two .item() loss reads per step",
+                                  "value": r["e2e"]["value"], "unit": "subjects/s", "ms_per_step": r["e2e"]["ms_per_step"],
+                                  "device_resident_value": r["value"], "launches_per_step": r["launches_per_step"]}
+    if not args.no_extras and world > 1 and args.mode == "graph" and 64 % world == 0:
+        # BASELINE configs[3]: model_ad, global batch 64 data-parallel over the ranks (strong scaling; task pMCIsMCI only
+        # changes labels).  Batch 64/N per GPU.
+        r = measure(job, "ad", 64 // world, max(5, min(args.steps, 10)), 3, "graph", args.optimizer, want_e2e=True,
+                    want_roofline=False)
+        extras["c4"] = {"what": "BASELINE configs[3]: model_ad, global batch 64 split over the ranks (strong scaling)",
+                        "global_batch": 64, "batch_per_gpu": 64 // world, "value": r["value"], "unit": "subjects/s",
+                        "ms_per_step": r["ms_per_step"], "e2e": r["e2e"]}
+
+    # ---- CPU baseline (rank 0, N = 1 only): BASELINE configs[0] ------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, mean_s = time_cpu_port(args.workload, 2, 3, 1)
+        sps, mean_s, best = time_cpu_port("ad" if head_name == "ad" else head_name, CPU_SAMPLE_BATCH, 3, 1)
         cpu_baseline = {"value": sps, "unit": "subjects/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": "3 steps of batch 2 (best step) of the same workload, fwd+bwd+Adam, fp32 torch CPU; "
-                                  "oracle/restatement.py (the reference is pure PyTorch, its kernels are ATen's)"}
+                        "best_step_value": best,
+                        "sample": f"3 steps (after 1 warm-up) of batch {CPU_SAMPLE_BATCH} (BASELINE configs[0]) of the same workload, "
+                                  "mean step, fwd+bwd+Adam, fp32 torch CPU; oracle/restatement.py (the reference is pure PyTorch, "
+                                  "its kernels are ATen's)"}
 
     if rank == 0:
+        graph_mode = args.mode == "graph"
         line = {
-            "metric": METRIC, "value": value, "unit": "subjects/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": head["value"], "unit": "subjects/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{desc}, batch {B}/GPU, volumes 91x109x91 fp32, Adam lr 1e-4",
+            "config": {"workload": f"{head['desc']}, batch {B}/GPU, volumes 91x109x91 fp32, Adam lr 1e-4",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "conv_impl": os.environ.get("TMF_CONV_IMPL", "auto"),
                        "optimizer": "FusedAdam (tmf_adam_step)" if args.optimizer == "fused" else "torch.optim.Adam",
-                       "mode": ("CUDA-graph replay of the whole step (transmf_ad_b200.train.GraphedTrainStep); e2e adds "
-                                "DevicePrefetcher (H2D of batch i+1 on a side stream) and LossReader (losses of step i "
-                                "read on the host after step i+1 is enqueued)") if graph_mode else "eager launches",
-                       "l2": "per-step working set (~0.2 GB/subject of activations) >> 126 MB L2; inputs rotate over a pool"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "breakdown": breakdown,
+                       "mode": ("CUDA-graph replay of the whole step incl. the gradient all-reduce "
+                                "(transmf_ad_b200.train.GraphedTrainStep); e2e adds DevicePrefetcher (H2D of batch i+1 on a side "
+                                "stream) and LossReader (losses of step i read on the host after step i+1 is enqueued)")
+                               if graph_mode else "eager launches",
+                       "l2": "per-step working set (~0.2 GB/subject of activations) >> 126 MB L2; inputs rotate over a pool",
+                       "library": library_hash(), "cpu_affinity": job.affinity},
+            "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "roofline": head.get("roofline"), "cpu_baseline": cpu_baseline, "workloads": others or None,
+            "sustained": head.get("sustained"), "eager_dropin": extras.get("eager_dropin"), "c4": extras.get("c4"),
+            "breakdown": head.get("breakdown"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -20,12 +20,34 @@ def _nvcc():
     return "nvcc"
 
 
+HASH_FILE = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over every file under csrc/ (sorted by name), include/tmf.h and the nvcc flags: the identity of a build."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "tmf.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
+def recorded_hash():
+    """The source hash the in-tree .so was built from ('' if unknown)."""
+    try:
+        with open(HASH_FILE) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "tmf.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    """Content-based (not mtime-based): a .so that does not match the sources is never used silently."""
+    return not os.path.exists(LIB) or recorded_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -53,6 +75,8 @@ def build(force=False, verbose=False):
         print("\n".join(log))
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-lcuda"]
     subprocess.run(cmd, check=True)
+    with open(HASH_FILE, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 
