@@ -320,7 +320,7 @@ def measure(job, workload, B, steps, warmup, mode="graph", optimizer="fused", wa
             sustained_steps=0, sample_clocks=False):
     """All legs for one workload at per-GPU batch B.  Returns a dict (rank 0 fills the clock record)."""
     from transmf_ad_b200 import _lib
-    from transmf_ad_b200.dp import GradBucketReducer
+    from transmf_ad_b200.dp import FlatGradReducer
     from transmf_ad_b200.models import mymodel as M
     from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state
     rank, world, dev = job.rank, job.world, job.dev
@@ -334,7 +334,7 @@ def measure(job, workload, B, steps, warmup, mode="graph", optimizer="fused", wa
         opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)
     else:
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0.0, capturable=graph_mode)
-    reducer = GradBucketReducer(model=model)
+    reducer = FlatGradReducer(model=model)
     if world > 1:
         reducer.install()
     ce_fn = torch.nn.CrossEntropyLoss()

@@ -9,38 +9,38 @@
 namespace tmf {
 
 // ------------------------------------------------------------------------------------------------------------
-// Fixed-order sum of the TMF_STAT_ROWS partial rows of a statistics buffer (include/tmf.h, DETERMINISM): a block of 8
-// warps takes 32 channels; warp w adds rows w, w+8, ... of its lane's channel, then warp 0 adds the 8 warp totals in
-// index order.  Returns (for threads of warp 0) the two totals of channel blockIdx.x*32 + lane.
+// Fixed-order sum of the TMF_STAT_ROWS partial rows of a statistics buffer (include/tmf.h, DETERMINISM): a block of 32
+// warps takes 32 channels; warp w adds rows w, w+32, ... of its lane's channel (all of a warp's loads are independent and
+// issued together: one L2 round trip), then warp 0 adds the 32 warp totals in index order.  Returns (for threads of
+// warp 0) the two totals of channel blockIdx.x*32 + lane.
+constexpr int FIN_WARPS = 32;
 __device__ __forceinline__ void sum_stat_rows(const double* __restrict__ st, int C, bool on, double& t1, double& t2) {
-  __shared__ double part[2][8][32];
+  __shared__ double part[2][FIN_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
-  if (on && c < C) {
-    int r = w;
-    for (; r + 8 < TMF_STAT_ROWS; r += 16) {          // two independent chains (fixed association)
-      a1 += st[(size_t)r * 2 * C + c];
-      a2 += st[(size_t)r * 2 * C + C + c];
-      b1 += st[(size_t)(r + 8) * 2 * C + c];
-      b2 += st[(size_t)(r + 8) * 2 * C + C + c];
-    }
-    for (; r < TMF_STAT_ROWS; r += 8) {
-      a1 += st[(size_t)r * 2 * C + c];
-      a2 += st[(size_t)r * 2 * C + C + c];
-    }
+  constexpr int NR = (TMF_STAT_ROWS + FIN_WARPS - 1) / FIN_WARPS;
+  double v1[NR], v2[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int r = w + i * FIN_WARPS;
+    const bool ok = on && c < C && r < TMF_STAT_ROWS;
+    v1[i] = ok ? st[(size_t)r * 2 * C + c] : 0.0;
+    v2[i] = ok ? st[(size_t)r * 2 * C + C + c] : 0.0;
   }
-  part[0][w][lane] = a1 + b1;
-  part[1][w][lane] = a2 + b2;
+  double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) { a1 += v1[i]; a2 += v2[i]; }
+  part[0][w][lane] = a1;
+  part[1][w][lane] = a2;
   __syncthreads();
   t1 = 0.0; t2 = 0.0;
   if (w == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t1 += part[0][i][lane]; t2 += part[1][i][lane]; }
+    for (int i = 0; i < FIN_WARPS; ++i) { t1 += part[0][i][lane]; t2 += part[1][i][lane]; }
   }
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const float> gamma,
+__global__ void __launch_bounds__(32 * FIN_WARPS) bn_finalize_kernel(GroupPtr<const double> stats, GroupPtr<const float> gamma,
                                    GroupPtr<const float> beta, GroupPtr<float> rmean, GroupPtr<float> rvar,
                                    GroupPtr<int64_t> nbt, GroupPtr<float> coef, int C, double count, float momentum,
                                    float eps, int training) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(GroupPtr<const double>
   coef.p[g][3 * C + c] = invstd;
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
+__global__ void __launch_bounds__(32 * FIN_WARPS) bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
                                        GroupPtr<float> dbeta, GroupPtr<float> dbias, GroupPtr<float> bcoef, int C,
                                        double count, int training) {
   const int g = blockIdx.z;
@@ -483,7 +483,7 @@ int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamm
     return 1;
   TMF_REQUIRE(count > 0, "bn_finalize: count must be positive");
   dim3 grid(ceil_div(C, 32), 1, ng);
-  bn_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
+  bn_finalize_kernel<<<grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
                                                              eps, training);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -570,7 +570,7 @@ int tmf_bn_bwd_finalize(int ng, const double* const* sums, const float* const* c
       !load_group(gdbias, dbias, ng, false, "dbias") || !load_group(gbc, bcoef, ng, true, "bcoef"))
     return 1;
   dim3 grid(ceil_div(C, 32), 1, ng);
-  bn_bwd_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
+  bn_bwd_finalize_kernel<<<grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
                                                                  training);
   TMF_LAUNCH_CHECK();
   return 0;

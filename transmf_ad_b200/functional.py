@@ -15,18 +15,27 @@ from . import _lib as L
 BN_EPS, BN_MOMENTUM, LRELU_SLOPE, LN_EPS = 1e-5, 0.1, 0.01, 1e-5
 
 
-# Data parallelism (dp.GradBucketReducer.install): called from SNetFunction.backward with (parameters, gradients) of one
-# conv layer of every tower as soon as they exist, so that their all-reduce overlaps the rest of the conv backward.
-_GRAD_SINK = None
+# Data parallelism (dp.FlatGradReducer.install): parameter data_ptr -> (slot view of the flat gradient buffer, parameter).
+# The backward kernels write weight gradients straight into the slots, autograd adopts the view as ``.grad`` without a
+# copy, and the gradient exchange is one all-reduce over the flat buffer.
+_GRAD_SLOTS = None
 
 
-def set_grad_sink(fn):
-    global _GRAD_SINK
-    _GRAD_SINK = fn
+def set_grad_slots(table):
+    global _GRAD_SLOTS
+    _GRAD_SLOTS = table
 
 
-def get_grad_sink():
-    return _GRAD_SINK
+def grad_out(param, shape=None, dtype=torch.float32):
+    """Output tensor for the gradient of ``param``: its slot of the flat buffer when one is registered (and the parameter
+    is not accumulating into an existing ``.grad``), else a fresh tensor."""
+    if _GRAD_SLOTS is not None and param is not None:
+        hit = _GRAD_SLOTS.get(param.data_ptr())
+        if hit is not None:
+            slot, owner = hit
+            if owner.grad is None and (shape is None or tuple(slot.shape) == tuple(shape)) and slot.dtype == dtype:
+                return slot.detach()        # a fresh alias: autograd adopts it as .grad only if nobody else holds it
+    return torch.empty(tuple(param.shape) if shape is None else tuple(shape), dtype=dtype, device=param.device)
 
 
 def conv_impl():
@@ -163,7 +172,7 @@ class SNetFunction(torch.autograd.Function):
             dims = (Do, Ho, Wo)
         ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
         ctx.hyper = run.hyper
-        ctx.params = params if need_grad else None          # references only (for the early gradient hand-off)
+        ctx.params = params if need_grad else None          # references only (gradient slots of the flat DP buffer)
         ctx.impl = impl
         outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)      # logical (B,C,d,h,w), channels-last memory
         return outs if ng > 1 else outs[0]
@@ -202,13 +211,14 @@ class SNetFunction(torch.autograd.Function):
             else:
                 L.call("tmf_bn_act_pool_bwd_reduce", ng, L.ptrs(dout), dout_fp32, L.ptrs(y), L.ptrs(coef), L.ptrs(sums),
                        B, Dl, Hl, Wl, cout, pool, slope, tag=f"tmf_bn_act_pool_bwd_reduce@L{l}")
-            dgamma = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
-            dbeta = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
-            dbias = [torch.empty(cout, dtype=torch.float32, device=dev) for _ in range(ng)]
+            PG = lambda t, k: ctx.params[(t * 7 + l) * 4 + k]
+            dbias = [grad_out(PG(t, 1)) for t in range(ng)]
+            dgamma = [grad_out(PG(t, 2)) for t in range(ng)]
+            dbeta = [grad_out(PG(t, 3)) for t in range(ng)]
             bcoef = list(torch.empty((ng, 2 * cout), dtype=torch.float32, device=dev).unbind(0))
             L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(dgamma), L.ptrs(dbeta),
                    L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
-            dw = [torch.empty((cout, cin, ks, ks, ks), dtype=torch.float32, device=dev) for _ in range(ng)]
+            dw = [grad_out(PG(t, 0)) for t in range(ng)]
             fused_ws = 0
             if l == 0 and pool == L.POOL_MAX and not dout_fp32 and ctx.impl != L.CONV_DIRECT:
                 fused_ws = int(L.load().tmf_conv1_bwd_fused_workspace_bytes(ng, B, Dl, Hl, Wl, cout))
@@ -244,19 +254,9 @@ class SNetFunction(torch.autograd.Function):
 
     @staticmethod
     def _layer_grads(ctx, pgrads, l, dw, dbias, dgamma, dbeta):
-        """Record layer l's parameter gradients and hand them to the data-parallel reducer, if one is installed."""
-        ps, gs = [], []
         for t in range(ctx.ng):
             base = (t * 7 + l) * 4
             pgrads[base + 0], pgrads[base + 1], pgrads[base + 2], pgrads[base + 3] = dw[t], dbias[t], dgamma[t], dbeta[t]
-            if _GRAD_SINK is not None and ctx.params is not None:
-                for k, g in enumerate((dw[t], dbias[t], dgamma[t], dbeta[t])):
-                    p = ctx.params[base + k]
-                    if p.requires_grad and p.grad is None:      # (an existing .grad means accumulation: leave it to autograd)
-                        ps.append(p)
-                        gs.append(g)
-        if ps:
-            _GRAD_SINK(ps, gs)
 
 
 # ==============================================================================================================
@@ -277,6 +277,7 @@ class LinearFunction(torch.autograd.Function):
         L.call("tmf_linear_fwd", L.ptr(x2), L.ptr(w), L.ptr(None if b is None else _f32c(b)), L.ptr(res2), L.ptr(y),
                L.ptr(pre), M, K, N, int(gelu))
         ctx.save_for_backward(x2, w, pre)
+        ctx.bias_ref = b                                     # reference only: its gradient slot (flat DP buffer)
         ctx.has_bias, ctx.has_res, ctx.gelu = b is not None, residual is not None, gelu
         ctx.xshape = x.shape
         return y.reshape(*x.shape[:-1], N)
@@ -298,8 +299,8 @@ class LinearFunction(torch.autograd.Function):
             L.call("tmf_linear_dgrad", L.ptr(dy2), L.ptr(w), L.ptr(dx), M, K, N, 0)
             dx = dx.reshape(ctx.xshape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
-            db = torch.empty(N, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
+            dw = grad_out(w, (N, K))
+            db = grad_out(ctx.bias_ref, (N,)) if ctx.has_bias else None
             ws, nws = L.scratch(dy2.device)
             L.call("tmf_linear_wgrad", L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, K, N, L.ptr(ws), nws)
         return dx, dw, db, dres, None
@@ -324,6 +325,7 @@ class LayerNormFunction(torch.autograd.Function):
         L.call("tmf_layernorm_fwd", L.ptr(x2), L.ptr(g), L.ptr(_f32c(beta)), L.ptr(res2), L.ptr(y), L.ptr(mean),
                L.ptr(rstd), rows, dim, eps)
         ctx.save_for_backward(x2, g, mean, rstd)
+        ctx.beta_ref = beta
         ctx.has_res = residual is not None
         return y.reshape(x.shape)
 
@@ -333,11 +335,11 @@ class LayerNormFunction(torch.autograd.Function):
         rows, dim = x2.shape
         dy2 = _f32c(dy).reshape(rows, dim)
         dx = torch.empty_like(x2)
-        dgb = torch.empty((2, dim), dtype=torch.float32, device=x2.device)
+        dgamma, dbeta = grad_out(g, (dim,)), grad_out(ctx.beta_ref, (dim,))
         ws, nws = L.scratch(x2.device)
-        L.call("tmf_layernorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dgb[0]),
-               L.ptr(dgb[1]), rows, dim, 0, L.ptr(ws), nws)
-        return dx.reshape(dy.shape), dgb[0], dgb[1], (dy if ctx.has_res else None), None
+        L.call("tmf_layernorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dgamma),
+               L.ptr(dbeta), rows, dim, 0, L.ptr(ws), nws)
+        return dx.reshape(dy.shape), dgamma, dbeta, (dy if ctx.has_res else None), None
 
 
 def layer_norm(x, gamma, beta, residual=None, eps=LN_EPS):

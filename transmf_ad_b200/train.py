@@ -33,12 +33,10 @@ class GraphedTrainStep:
     (``.item()``) before the next call.
 
     world size 1 : zero_grad + forward + loss + backward + optimizer.step in ONE graph.
-    world size N : the same ONE graph with the data-parallel exchange inside it: the reducer's autograd hooks and the conv
-                   stack's per-layer hand-off (``dp.GradBucketReducer.install``) run while the backward pass is being
-                   captured, so every bucket's pack -> ncclAllReduce -> unpack becomes a branch of the graph that
-                   overlaps the remaining backward kernels; ``reducer.finish()`` joins before the optimizer.
-                   ``TMF_DP_GRAPH=split`` selects the older, serial form (graph A = forward + backward; eager bucketed
-                   all-reduce; graph B = optimizer).
+    world size N : the same ONE graph with the data-parallel exchange inside it: ``reducer.finish()`` -- one ncclAllReduce
+                   over the flat gradient buffer the backward kernels wrote into (``dp.FlatGradReducer``) -- is captured
+                   between the backward pass and the optimizer.  ``TMF_DP_GRAPH=split`` keeps the collective outside
+                   (graph A = forward + backward; eager all-reduce; graph B = optimizer).
 
     The optimizer must be graph-capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).
 
@@ -57,10 +55,7 @@ class GraphedTrainStep:
         import os
         self.split = self.world > 1 and os.environ.get("TMF_DP_GRAPH", "fused") == "split"
         if reducer is not None:
-            if self.split or self.world == 1:
-                reducer.remove()                           # serial form: no hooks, reduce_now() between the two graphs
-            else:
-                reducer.install()                          # hooks + per-layer hand-off are captured with the backward
+            reducer.install()                              # weight gradients are written straight into the flat buffer
         self.launches_per_step = 0                         # libtmf kernel launches captured per step
         self.static_inputs = [t.clone() for t in _as_tuple(example_inputs)]
         self.static_targets = [t.clone() for t in _as_tuple(example_targets)]
@@ -78,10 +73,7 @@ class GraphedTrainStep:
 
     def _reduce(self):
         if self.world > 1:
-            if self.split:
-                self.reducer.reduce_now()
-            else:
-                self.reducer.finish()
+            self.reducer.finish()
 
     # ---- state snapshot around the warm-up steps ------------------------------------------------------------------
     def _snapshot(self):
@@ -154,7 +146,7 @@ class GraphedTrainStep:
             refresh()                                      # e.g. FusedAdam: a scheduler-changed lr reaches the device scalar
         self.graph_fb.replay()
         if self.split:
-            self.reducer.reduce_now()
+            self.reducer.finish()
             self.graph_opt.replay()
         return self.losses
 
