@@ -66,8 +66,13 @@ def main():
     n_torch_native = sum(1 for k in (n for n, _ in model.named_parameters()) if k.split(".")[-2] in ("1", "5") and
                          (k.startswith("D.") or k.startswith("fc_cls.")))            # BatchNorm1d affine parameters
     assert red.allreduce_launches == 1
-    # zero-copy: only the gradients torch's own autograd produced had to be copied into their slots
-    assert red.packed_last == n_torch_native, (red.packed_last, n_torch_native)
+    # zero-copy: only the gradients torch's own autograd produced (BatchNorm1d) or summed (the discriminator D runs twice per
+    # step, so autograd adds its two weight-gradient contributions in a buffer of its own) had to be copied into their slots
+    assert red.packed_last == n_torch_native + 4, (red.packed_last, n_torch_native)
+    slot_of = {id(p): s for p, s in zip(red.params, red.slots)}
+    for k, p in model.named_parameters():
+        if "_cnn." in k or "fuse_transformer" in k:
+            assert p.grad.data_ptr() == slot_of[id(p)].data_ptr(), f"{k}: gradient was not born in its flat-buffer slot"
     names = [k for k, _ in model.named_parameters()]
     for k, p, q in zip(names, model.parameters(), own.parameters()):
         gathered = [torch.empty_like(q.grad) for _ in range(world)]
