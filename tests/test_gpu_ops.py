@@ -533,3 +533,63 @@ def test_device_prefetcher_yields_every_batch_and_reuses_buffers():
         assert len(ptrs) == 2                               # two device slots, recycled
     want = [(12.0 * i, [i, i + 1]) for i in range(5)] * 2
     assert seen == want
+
+
+@pytest.mark.parametrize("B,Nq,Nk,heads,mlp,add_input", [(8, 150, 150, 4, 512, True), (3, 8, 8, 8, 256, True),
+                                                        (2, 37, 64, 4, 128, False), (1, 1, 5, 4, 512, True),
+                                                        (2, 150, 300, 4, 256, True)])
+def test_fused_encoder_matches_fp32_oracle_and_unfused_path(B, Nq, Nk, heads, mlp, add_input, monkeypatch):
+    """csrc/enc_fused.cu (3 forward + 5 backward launches, TF32x3 tensor-core GEMMs) against the CPU oracle's fp32 encoder
+    (reference models/networks.py:215-230) and against the unfused kernels: output, input / context gradients and all 14
+    parameter gradients.  Tolerance 2e-5 relative to the tensor's largest magnitude (fp32-level: the 3-pass split drops
+    ~2^-22 per product) -- the unfused fp32-FMA path meets the same bound."""
+    from oracle import restatement as R
+    from transmf_ad_b200.models import networks as N
+    torch.manual_seed(7)
+    enc = N.Transformer(128, 1, heads, 128 // heads, mlp).to(DEV)
+    with torch.no_grad():
+        for k, p in enc.named_parameters():
+            if "norm" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    x0 = torch.randn(B, Nq, 128, generator=torch.Generator().manual_seed(1))
+    c0 = torch.randn(B, Nk, 128, generator=torch.Generator().manual_seed(2))
+    wy = torch.randn(B, Nq, 128, generator=torch.Generator().manual_seed(3))
+
+    def run(fused):
+        monkeypatch.setenv("TMF_ENC_FUSED", "1" if fused else "0")
+        enc.zero_grad(set_to_none=True)
+        x = x0.to(DEV).requires_grad_(True)
+        c = c0.to(DEV).requires_grad_(True)
+        n0 = L.launch_count()
+        y = enc(x, context=c, add_input=add_input)
+        (y * wy.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        return (y.detach().cpu(), x.grad.cpu(), c.grad.cpu(), {k: p.grad.cpu().clone() for k, p in enc.named_parameters()},
+                L.launch_count() - n0)
+
+    yf, dxf, dcf, gf, nf = run(True)
+    yu, dxu, dcu, gu, nu = run(False)
+    assert nf <= 10 < nu, (nf, nu)                         # 3 + 5 launches (+ the attention backward's second kernel)
+    sd = {"enc." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    xr, cr = x0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    yr = R.transformer_encoder(sd, "enc", xr, cr, heads)
+    if add_input:
+        yr = yr + xr
+    (yr * wy).sum().backward()
+
+    def close(a, b, what, tol=2e-5):
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a - b).abs().max()) / scale
+        assert err <= tol, f"{what}: {err:.3e}"
+
+    for tag, (y, dx, dc, gr) in (("fused", (yf, dxf, dcf, gf)), ("unfused", (yu, dxu, dcu, gu))):
+        close(y, yr.detach(), f"{tag} y")
+        close(dx, xr.grad, f"{tag} dx")
+        close(dc, cr.grad, f"{tag} dctx")
+        for k, v in gr.items():
+            close(v, sd["enc." + k].grad, f"{tag} grad {k}", 5e-5)
+    # run-to-run: bit-identical (split reductions meet in a fixed order)
+    y2, dx2, dc2, g2, _ = run(True)
+    assert torch.equal(yf, y2) and torch.equal(dxf, dx2) and torch.equal(dcf, dc2)
+    for k in gf:
+        assert torch.equal(gf[k], g2[k]), k

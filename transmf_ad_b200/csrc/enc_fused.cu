@@ -1,0 +1,700 @@
+// enc_fused.cu -- one Transformer(depth=1) encoder of the cross-modal fusion stack (reference models/networks.py:114-175,
+// 215-230, as driven by CrossTransformer_MOD_AVG :272-281) in 3 forward and 5 backward launches instead of ~30:
+//
+//   forward   F1  enc_proj_fwd     x rows:   h1 = LN1(x);  q = h1 Wq^T          ctx rows:  kv = ctx Wkv^T
+//             F2  (attention.cu)   o = softmax(q k^T scale) v
+//             F3  enc_chain_fwd    a = o Wo^T + bo + x;  h2 = LN2(a);  p = h2 W1^T + b1;  f = GELU(p);
+//                                  g = f W2^T + b2 + a;  y = LNf(g) (+ x: the caller's outer residual)
+//   backward  R1  enc_chain_bwd    dy -> dg (LNf) -> df = dg W2 -> dp = df GELU'(p) -> dh2 = dp W1 -> da = dg + LN2'(dh2)
+//                                  -> do = da Wo;  dxp = da (+ dy);  LN parameter gradients
+//             R2  (attention.cu)   do -> dq, dkv
+//             R3  enc_proj_bwd     x rows: dx = dxp + LN1'(dq Wq);  ctx rows: dctx = dkv Wkv;  LN1 parameter gradients
+//             R4  enc_wgrad        dWq, dWkv, dWo, dW1, dW2 (+ bo, b1, b2 gradients): five token-reductions in one launch
+//
+// Every kernel is a chain of small GEMMs on a PANEL of 16 token rows held in shared memory, so the row-local work
+// (LayerNorm, bias, GELU, residuals) rides in the GEMM prologues / epilogues and the intermediate tensors never make a
+// round trip through launches.  The GEMMs run on the tensor cores with mma.sync.m16n8k8 TF32 and the 3-pass split
+//   x*w ~= xl*wh + xh*wl + xh*wh      (xh = tf32(x), xl = tf32(x - xh); dropped term ~2^-22 relative)
+// which keeps fp32-level accuracy (the reference's nn.Linear is fp32; measured <= 2e-6 relative against an fp32 CPU
+// GEMM) -- tcgen05 needs 128-row tiles, and 1200 tokens are 75 panels of 16 rows but only 10 tiles of 128.
+// Weights stream through a 3-stage cp.async ring in [128 x 32] tiles; all weight-side reductions over tokens are
+// split and meet in the caller's scratch buffer, the last block adding the partials in index order (deterministic).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tmf {
+namespace enc {
+
+constexpr int THREADS = 256;
+constexpr int PR = 16;                       // panel rows
+constexpr int WT_FLOATS = 128 * 36;          // one weight stage: [128][32+4] (B_NK) or [32][128+8] (B_KN)
+constexpr int NSTAGE = 3;
+constexpr int LD128 = 132;                   // panel pitch for 128 columns (== 4 mod 32: conflict-free A fragments)
+
+enum { B_NK = 0, B_KN = 1 };                 // weight tile is W[n][k] (forward) or W[k][n] (dgrad / wgrad operand)
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// one weight stage: B_NK: rows n0..n0+127 of W (pitch ldw), columns k0..k0+31 -> Ws[r*36 + c]
+//                   B_KN: rows k0..k0+31 of W (pitch ldw; rows >= kvalid read as zero), columns n0..n0+127 -> Ws[r*136 + c]
+template <int MODE>
+__device__ __forceinline__ void stage_w(float* Ws, const float* __restrict__ W, int ldw, int n0, int k0, int kvalid) {
+  if (MODE == B_NK) {
+#pragma unroll
+    for (int c = threadIdx.x; c < 1024; c += THREADS) {
+      const int r = c >> 3, q = c & 7;
+      cp_async16(Ws + r * 36 + 4 * q, W + (size_t)(n0 + r) * ldw + k0 + 4 * q, true);
+    }
+  } else {
+#pragma unroll
+    for (int c = threadIdx.x; c < 1024; c += THREADS) {
+      const int r = c >> 5, q = c & 31;
+      const bool ok = k0 + r < kvalid;
+      cp_async16(Ws + r * 136 + 4 * q, W + (size_t)(ok ? k0 + r : 0) * ldw + n0 + 4 * q, ok);
+    }
+  }
+}
+
+// C[16*MT rows][N] = A[16*MT][K] . op(W), A in shared memory (pitch lda == 4 mod 32), N % 128 == 0, K % 32 == 0.
+//   MT = 1: warp w owns columns [16w, 16w+16) of every 128-column block (2 n-tiles);
+//   MT = 2: warp w owns m-tile (w & 1) and columns [32(w>>1), +32) (4 n-tiles).
+// epi(row, col, v0, v1) receives two adjacent columns of one row.  Ends with __syncthreads().
+template <int MT, int MODE, typename Epi>
+__device__ __forceinline__ void panel_gemm(const float* As, int lda, const float* __restrict__ W, int ldw, int N, int K,
+                                           int kvalid, float* wstage, Epi epi) {
+  constexpr int NT = (MT == 2) ? 4 : 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int mt = (MT == 2) ? (warp & 1) : 0;
+  const int cbase = ((MT == 2) ? (warp >> 1) : warp) * NT * 8;
+  const int nk = K / 32;
+  const float* arow = As + (mt * 16 + g) * lda + t;
+  for (int nb = 0; nb < N; nb += 128) {
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+      if (s < nk) stage_w<MODE>(wstage + s * WT_FLOATS, W, ldw, nb, s * 32, kvalid);
+      cp_async_commit();
+    }
+    for (int kc = 0; kc < nk; ++kc) {
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();
+      if (kc + NSTAGE - 1 < nk)
+        stage_w<MODE>(wstage + ((kc + NSTAGE - 1) % NSTAGE) * WT_FLOATS, W, ldw, nb, (kc + NSTAGE - 1) * 32, kvalid);
+      cp_async_commit();
+      const float* Ws = wstage + (kc % NSTAGE) * WT_FLOATS;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float* ap = arow + kc * 32 + ks * 8;
+        uint32_t ah[4], al[4];
+        split_tf32(ap[0], ah[0], al[0]);
+        split_tf32(ap[8 * lda], ah[1], al[1]);
+        split_tf32(ap[4], ah[2], al[2]);
+        split_tf32(ap[8 * lda + 4], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          float b0, b1;
+          if (MODE == B_NK) {
+            const float* bp = Ws + (cbase + j * 8 + g) * 36 + ks * 8 + t;
+            b0 = bp[0]; b1 = bp[4];
+          } else {
+            const float* bp = Ws + (ks * 8 + t) * 136 + cbase + j * 8 + g;
+            b0 = bp[0]; b1 = bp[4 * 136];
+          }
+          uint32_t bh[2], bl[2];
+          split_tf32(b0, bh[0], bl[0]);
+          split_tf32(b1, bh[1], bl[1]);
+          mma_tf32(acc[j], al, bh);
+          mma_tf32(acc[j], ah, bl);
+          mma_tf32(acc[j], ah, bh);
+        }
+      }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int col = nb + cbase + j * 8 + 2 * t;
+      epi(mt * 16 + g, col, acc[j][0], acc[j][1]);
+      epi(mt * 16 + g + 8, col, acc[j][2], acc[j][3]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- panel <-> global helpers (all 256 threads; float4, rows >= nvalid read as zero / are not written) ----------------
+__device__ __forceinline__ void load_panel(float* Ps, int lds, const float* __restrict__ src, int ld, int nvalid, int rows,
+                                           int cols) {
+  const int c4 = cols >> 2;
+  for (int i = threadIdx.x; i < rows * c4; i += THREADS) {
+    const int r = i / c4, c = i - r * c4;
+    const float4 v = (r < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Ps + r * lds + 4 * c) = v;
+  }
+}
+__device__ __forceinline__ void store_panel(float* __restrict__ dst, int ld, const float* Ps, int lds, int nvalid, int cols) {
+  const int c4 = cols >> 2;
+  for (int i = threadIdx.x; i < nvalid * c4; i += THREADS) {
+    const int r = i / c4, c = i - r * c4;
+    reinterpret_cast<float4*>(dst + (size_t)r * ld)[c] = *reinterpret_cast<const float4*>(Ps + r * lds + 4 * c);
+  }
+}
+
+// LayerNorm of a 16 x 128 panel, in place or into `out`: warp w takes rows 2w, 2w+1; a lane owns columns 4*lane..4*lane+3.
+// Two-pass statistics exactly like layernorm_fwd_kernel (fusion_ops.cu).
+__device__ __forceinline__ void panel_layernorm(const float* Ps, float* out, int lds, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, float* __restrict__ mean_out,
+                                                float* __restrict__ rstd_out, int row0, int nvalid) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = 2 * warp + rr;
+    const float4 v = *reinterpret_cast<const float4*>(Ps + r * lds + 4 * lane);
+    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    const float rstd = rsqrtf(warp_sum(a * a + b * b + c * c + d * d) * (1.f / 128.f) + eps);
+    if (lane == 0 && r < nvalid) { mean_out[row0 + r] = mean; rstd_out[row0 + r] = rstd; }
+    float4 o;
+    o.x = a * rstd * gm.x + bt.x; o.y = b * rstd * gm.y + bt.y; o.z = c * rstd * gm.z + bt.z; o.w = d * rstd * gm.w + bt.w;
+    *reinterpret_cast<float4*>(out + r * lds + 4 * lane) = o;
+  }
+}
+
+// LayerNorm backward of a 16 x 128 panel: dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)), written to
+// `dxo` (+ `addp` if not null); the lane's column sums of dy*xhat / dy are accumulated into ag / ab (rows >= nvalid skip).
+__device__ __forceinline__ void panel_layernorm_bwd(const float* dys, const float* xs, float* dxo, const float* addp, int lds,
+                                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                    const float* __restrict__ rstd, int row0, int nvalid, float4& ag,
+                                                    float4& ab) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = 2 * warp + rr;
+    const bool ok = r < nvalid;
+    const float mu = ok ? mean[row0 + r] : 0.f, rs = ok ? rstd[row0 + r] : 0.f;
+    const float4 xv = *reinterpret_cast<const float4*>(xs + r * lds + 4 * lane);
+    const float4 gv = *reinterpret_cast<const float4*>(dys + r * lds + 4 * lane);
+    const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+    const float4 gg = make_float4(gv.x * gm.x, gv.y * gm.y, gv.z * gm.z, gv.w * gm.w);
+    const float s1 = warp_sum(gg.x + gg.y + gg.z + gg.w) * (1.f / 128.f);
+    const float s2 = warp_sum(gg.x * xh.x + gg.y * xh.y + gg.z * xh.z + gg.w * xh.w) * (1.f / 128.f);
+    if (ok) {
+      ag.x += gv.x * xh.x; ag.y += gv.y * xh.y; ag.z += gv.z * xh.z; ag.w += gv.w * xh.w;
+      ab.x += gv.x; ab.y += gv.y; ab.z += gv.z; ab.w += gv.w;
+    }
+    float4 o = make_float4(rs * (gg.x - s1 - xh.x * s2), rs * (gg.y - s1 - xh.y * s2), rs * (gg.z - s1 - xh.z * s2),
+                           rs * (gg.w - s1 - xh.w * s2));
+    if (addp != nullptr) {
+      const float4 e = *reinterpret_cast<const float4*>(addp + r * lds + 4 * lane);
+      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+    }
+    *reinterpret_cast<float4*>(dxo + r * lds + 4 * lane) = o;
+  }
+}
+
+// Block-level column sums of per-lane float4 accumulators (8 warps, lane owns columns 4*lane..): the warps add into
+// red[128] one after the other (deterministic), result left in red.
+__device__ __forceinline__ void block_colsum128(float* red, const float4& v) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+      float4* p = reinterpret_cast<float4*>(red) + lane;
+      if (w == 0) *p = v;
+      else { float4 a = *p; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; *p = a; }
+    }
+    __syncthreads();
+  }
+}
+
+// Cross-block finish of per-block LayerNorm parameter partials: part[block][nvec][128] -> outs[v][128], added in block order.
+__device__ __forceinline__ void finish_ln_partials(float* __restrict__ part, int nvec, float* const* outs, unsigned* ticket) {
+  if (!last_block_arrives(ticket, gridDim.x)) return;
+  for (int i = threadIdx.x; i < nvec * 128; i += THREADS) {
+    float s = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (size_t)b * nvec * 128 + i);
+    float* o = outs[i >> 7];
+    if (o != nullptr) o[i & 127] = s;
+  }
+}
+
+// =====================================================================================================================
+// F1: projections.  blocks [0, nbx): x panels;  [nbx, nbx + nbc): ctx panels
+// =====================================================================================================================
+struct ProjFwdArgs {
+  const float *x, *ctx, *ln_w, *ln_b, *wq, *wkv;
+  float *h1, *mean1, *rstd1, *q, *kv;
+  int Mx, Mc, nbx;
+  float eps;
+};
+
+__global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  float* P0 = sm;                           // [16][132] input panel
+  float* P1 = P0 + PR * LD128;              // [16][260] output panel
+  float* wst = P1 + PR * 260;
+  if ((int)blockIdx.x < p.nbx) {
+    const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
+    load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
+    __syncthreads();
+    panel_layernorm(P0, P0, LD128, p.ln_w, p.ln_b, p.eps, p.mean1, p.rstd1, row0, nv);
+    __syncthreads();
+    store_panel(p.h1 + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
+    panel_gemm<1, B_NK>(P0, LD128, p.wq, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+      *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
+    });
+    store_panel(p.q + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  } else {
+    const int row0 = (blockIdx.x - p.nbx) * PR, nv = min(PR, p.Mc - row0);
+    load_panel(P0, LD128, p.ctx + (size_t)row0 * 128, 128, nv, PR, 128);
+    __syncthreads();
+    panel_gemm<1, B_NK>(P0, LD128, p.wkv, 128, 256, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+      *reinterpret_cast<float2*>(P1 + r * 260 + c) = make_float2(v0, v1);
+    });
+    store_panel(p.kv + (size_t)row0 * 256, 256, P1, 260, nv, 256);
+  }
+}
+
+// =====================================================================================================================
+// F3: the row-local chain behind the attention core
+// =====================================================================================================================
+struct ChainFwdArgs {
+  const float *o, *x, *wo, *bo, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2, *lnf_w, *lnf_b;
+  float *a, *h2, *mean2, *rstd2, *pre, *f, *g, *meanf, *rstdf, *y;
+  int M, mlp, add_input;
+  float eps2, epsf;
+};
+
+__global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  const int ldf = p.mlp + 4;
+  float* P0 = sm;                           // o, later g
+  float* P1 = P0 + PR * LD128;              // a
+  float* P2 = P1 + PR * LD128;              // h2
+  float* PF = P2 + PR * LD128;              // [16][mlp+4]: pre-activation, then f
+  float* wst = PF + PR * ldf;
+  const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
+  load_panel(P0, LD128, p.o + (size_t)row0 * 128, 128, nv, PR, 128);
+  load_panel(P2, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);     // x parked in P2 until LN2 overwrites it
+  __syncthreads();
+  // a = o Wo^T + bo + x
+  panel_gemm<1, B_NK>(P0, LD128, p.wo, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    const float2 xb = *reinterpret_cast<const float2*>(P2 + r * LD128 + c);
+    *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0 + __ldg(p.bo + c) + xb.x, v1 + __ldg(p.bo + c + 1) + xb.y);
+  });
+  store_panel(p.a + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  panel_layernorm(P1, P2, LD128, p.ln2_w, p.ln2_b, p.eps2, p.mean2, p.rstd2, row0, nv);
+  __syncthreads();
+  store_panel(p.h2 + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
+  // pre = h2 W1^T + b1
+  panel_gemm<1, B_NK>(P2, LD128, p.w1, 128, p.mlp, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(PF + r * ldf + c) = make_float2(v0 + __ldg(p.b1 + c), v1 + __ldg(p.b1 + c + 1));
+  });
+  store_panel(p.pre + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  __syncthreads();
+  for (int i = threadIdx.x; i < PR * p.mlp; i += THREADS) {
+    const int r = i / p.mlp, c = i - r * p.mlp;
+    PF[r * ldf + c] = gelu_exact(PF[r * ldf + c]);
+  }
+  __syncthreads();
+  store_panel(p.f + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  // g = f W2^T + b2 + a
+  panel_gemm<1, B_NK>(PF, ldf, p.w2, p.mlp, 128, p.mlp, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    const float2 ab = *reinterpret_cast<const float2*>(P1 + r * LD128 + c);
+    *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0 + __ldg(p.b2 + c) + ab.x, v1 + __ldg(p.b2 + c + 1) + ab.y);
+  });
+  store_panel(p.g + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
+  // y = LNf(g) (+ x)
+  panel_layernorm(P0, P2, LD128, p.lnf_w, p.lnf_b, p.epsf, p.meanf, p.rstdf, row0, nv);
+  __syncthreads();
+  if (p.add_input) {
+    for (int i = threadIdx.x; i < nv * 32; i += THREADS) {
+      const int r = i >> 5, c = i & 31;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(p.x + (size_t)(row0 + r) * 128) + c);
+      float4 v = *reinterpret_cast<const float4*>(P2 + r * LD128 + 4 * c);
+      v.x += xv.x; v.y += xv.y; v.z += xv.z; v.w += xv.w;
+      reinterpret_cast<float4*>(p.y + (size_t)(row0 + r) * 128)[c] = v;
+    }
+  } else {
+    store_panel(p.y + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
+  }
+}
+
+// =====================================================================================================================
+// R1: backward of the chain
+// =====================================================================================================================
+struct ChainBwdArgs {
+  const float *dy, *g, *a, *pre, *wo, *w1, *w2, *ln2_w, *lnf_w, *mean2, *rstd2, *meanf, *rstdf;
+  float *dg, *dp, *da, *dout, *dxp;                 // dxp = da (+ dy when the outer residual is fused)
+  float *dlnf_w, *dlnf_b, *dln2_w, *dln2_b;
+  float* part;                                      // [gridDim.x][4][128]
+  unsigned* ticket;
+  int M, mlp, add_input;
+};
+
+__global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  const int ldf = p.mlp + 4;
+  float* P0 = sm;
+  float* P1 = P0 + PR * LD128;
+  float* P2 = P1 + PR * LD128;
+  float* PF = P2 + PR * LD128;
+  float* wst = PF + PR * ldf;
+  float* red = wst + NSTAGE * WT_FLOATS;            // [4][128]
+  const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 agf = z4, abf = z4, ag2 = z4, ab2 = z4;
+  load_panel(P0, LD128, p.dy + (size_t)row0 * 128, 128, nv, PR, 128);
+  load_panel(P1, LD128, p.g + (size_t)row0 * 128, 128, nv, PR, 128);
+  __syncthreads();
+  // dg = LNf'(dy)  -> P2
+  panel_layernorm_bwd(P0, P1, P2, nullptr, LD128, p.lnf_w, p.meanf, p.rstdf, row0, nv, agf, abf);
+  __syncthreads();
+  store_panel(p.dg + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
+  // dp = (dg W2) * GELU'(pre)  -> PF        (W2 is [128][mlp]: reduction over its rows)
+  load_panel(PF, ldf, p.pre + (size_t)row0 * p.mlp, p.mlp, nv, PR, p.mlp);
+  __syncthreads();
+  panel_gemm<1, B_KN>(P2, LD128, p.w2, p.mlp, p.mlp, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    float2* q = reinterpret_cast<float2*>(PF + r * ldf + c);
+    const float2 pr = *q;
+    *q = make_float2(v0 * gelu_grad(pr.x), v1 * gelu_grad(pr.y));
+  });
+  store_panel(p.dp + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  // dh2 = dp W1  -> P0                       (W1 is [mlp][128])
+  panel_gemm<1, B_KN>(PF, ldf, p.w1, 128, 128, p.mlp, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0, v1);
+  });
+  // da = dg + LN2'(dh2)  -> P0
+  load_panel(P1, LD128, p.a + (size_t)row0 * 128, 128, nv, PR, 128);
+  __syncthreads();
+  panel_layernorm_bwd(P0, P1, P0, P2, LD128, p.ln2_w, p.mean2, p.rstd2, row0, nv, ag2, ab2);
+  __syncthreads();
+  store_panel(p.da + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
+  // dxp = da (+ dy: outer residual)
+  for (int i = threadIdx.x; i < nv * 32; i += THREADS) {
+    const int r = i >> 5, c = i & 31;
+    float4 v = *reinterpret_cast<const float4*>(P0 + r * LD128 + 4 * c);
+    if (p.add_input) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(p.dy + (size_t)(row0 + r) * 128) + c);
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    }
+    reinterpret_cast<float4*>(p.dxp + (size_t)(row0 + r) * 128)[c] = v;
+  }
+  // do = da Wo  -> P1                        (Wo is [128][128])
+  panel_gemm<1, B_KN>(P0, LD128, p.wo, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
+  });
+  store_panel(p.dout + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  // LayerNorm parameter gradients: block partials, then the last block adds them in order
+  block_colsum128(red, agf);
+  block_colsum128(red + 128, abf);
+  block_colsum128(red + 256, ag2);
+  block_colsum128(red + 384, ab2);
+  for (int i = threadIdx.x; i < 512; i += THREADS) p.part[(size_t)blockIdx.x * 512 + i] = red[i];
+  float* outs[4] = {p.dlnf_w, p.dlnf_b, p.dln2_w, p.dln2_b};
+  finish_ln_partials(p.part, 4, outs, p.ticket);
+}
+
+// =====================================================================================================================
+// R3: backward of the projections
+// =====================================================================================================================
+struct ProjBwdArgs {
+  const float *dq, *dkv, *dxp, *x, *ln_w, *mean1, *rstd1, *wq, *wkv;
+  float *dx, *dctx, *dln_w, *dln_b;
+  float* part;                                      // [nbx][2][128]
+  unsigned* ticket;
+  int Mx, Mc, nbx;
+};
+
+__global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  float* P0 = sm;                           // [16][260]
+  float* P1 = P0 + PR * 260;                // [16][132]
+  float* P2 = P1 + PR * LD128;              // [16][132]
+  float* wst = P2 + PR * LD128;
+  float* red = wst + NSTAGE * WT_FLOATS;    // [2][128]
+  if ((int)blockIdx.x < p.nbx) {
+    const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
+    load_panel(P0, LD128, p.dq + (size_t)row0 * 128, 128, nv, PR, 128);
+    __syncthreads();
+    // dh1 = dq Wq  -> P1
+    panel_gemm<1, B_KN>(P0, LD128, p.wq, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+      *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
+    });
+    load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
+    load_panel(P2, LD128, p.dxp + (size_t)row0 * 128, 128, nv, PR, 128);
+    __syncthreads();
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    panel_layernorm_bwd(P1, P0, P1, P2, LD128, p.ln_w, p.mean1, p.rstd1, row0, nv, ag, ab);
+    __syncthreads();
+    store_panel(p.dx + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+    block_colsum128(red, ag);
+    block_colsum128(red + 128, ab);
+    for (int i = threadIdx.x; i < 256; i += THREADS) p.part[(size_t)blockIdx.x * 256 + i] = red[i];
+  } else {
+    const int row0 = (blockIdx.x - p.nbx) * PR, nv = min(PR, p.Mc - row0);
+    load_panel(P0, 260, p.dkv + (size_t)row0 * 256, 256, nv, PR, 256);
+    __syncthreads();
+    // dctx = dkv Wkv                          (Wkv is [256][128])
+    panel_gemm<1, B_KN>(P0, 260, p.wkv, 128, 128, 256, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+      *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
+    });
+    store_panel(p.dctx + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  }
+  // every block takes part in the rendezvous; only the x blocks hold partials
+  if (!last_block_arrives(p.ticket, gridDim.x)) return;
+  for (int i = threadIdx.x; i < 256; i += THREADS) {
+    float s = 0.f;
+    for (int b = 0; b < p.nbx; ++b) s += __ldcg(p.part + (size_t)b * 256 + i);
+    if (i < 128) p.dln_w[i] = s; else p.dln_b[i - 128] = s;
+  }
+}
+
+// =====================================================================================================================
+// R4: the five weight gradients (+ three bias gradients) of one encoder in one launch
+//     dW[n][k] = sum_m dY[m][n] * X[m][k];   db[n] = sum_m dY[m][n]
+// A block computes a [32 (n)] x [128 (k)] tile of one problem over one chunk of WG_MC tokens; the chunks of a tile meet
+// in scratch and the last one adds them in order.
+// =====================================================================================================================
+constexpr int WG_MC = 384;                  // tokens per chunk; pitch 388 == 4 mod 32
+constexpr int WG_LDA = WG_MC + 4;
+constexpr int WG_PROBLEMS = 5;
+
+struct WgradProblem {
+  const float* dy; const float* x; float* dw; float* db;
+  int ldy, ldx, N, K, M;
+  int tile0;                                // first tile index of this problem
+};
+struct WgradArgs {
+  WgradProblem pr[WG_PROBLEMS];
+  int ntiles, nsplit;
+  float* part;                              // [ntiles][nsplit][32*128 + 32]
+  unsigned* tickets;                        // [ntiles]
+};
+
+__global__ void __launch_bounds__(THREADS) enc_wgrad_kernel(WgradArgs p) {
+  extern __shared__ __align__(16) float sm[];
+  float* At = sm;                           // [32][WG_LDA]: dY^T chunk
+  float* wst = At + 32 * WG_LDA;
+  const int tile = blockIdx.x / p.nsplit, split = blockIdx.x % p.nsplit;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < WG_PROBLEMS; ++i)
+    if (tile >= p.pr[i].tile0) pi = i;
+  const WgradProblem& q = p.pr[pi];
+  const int lt = tile - q.tile0, kt = q.K / 128;
+  const int n0 = (lt / kt) * 32, k0 = (lt % kt) * 128;
+  const int m0 = split * WG_MC, mv = max(0, min(WG_MC, q.M - m0));
+  // stage dY^T: At[n][m] = dY[m0 + m][n0 + n]   (a warp reads 32 consecutive n of one token: 128 B)
+  for (int i = threadIdx.x; i < WG_MC * 8; i += THREADS) {
+    const int m = i >> 3, c = i & 7;
+    const float4 v = (m < mv) ? __ldg(reinterpret_cast<const float4*>(q.dy + (size_t)(m0 + m) * q.ldy + n0) + c)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    At[(4 * c + 0) * WG_LDA + m] = v.x;
+    At[(4 * c + 1) * WG_LDA + m] = v.y;
+    At[(4 * c + 2) * WG_LDA + m] = v.z;
+    At[(4 * c + 3) * WG_LDA + m] = v.w;
+  }
+  __syncthreads();
+  float* mypart = p.part + ((size_t)tile * p.nsplit + split) * (32 * 128 + 32);
+  if (q.db != nullptr && k0 == 0) {         // bias gradient rides with the first k tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int n = warp * 4 + rr;
+      float s = 0.f;
+      for (int m = lane; m < WG_MC; m += 32) s += At[n * WG_LDA + m];
+      s = warp_sum(s);
+      if (lane == 0) mypart[32 * 128 + n] = s;
+    }
+  }
+  panel_gemm<2, B_KN>(At, WG_LDA, q.x + (size_t)(mv > 0 ? m0 : 0) * q.ldx + k0, q.ldx, 128, WG_MC, mv, wst,
+                      [&](int r, int c, float v0, float v1) { *reinterpret_cast<float2*>(mypart + r * 128 + c) = make_float2(v0, v1); });
+  if (!last_block_arrives(p.tickets + tile, p.nsplit)) return;
+  const float* base = p.part + (size_t)tile * p.nsplit * (32 * 128 + 32);
+  for (int i = threadIdx.x; i < 32 * 128; i += THREADS) {
+    float s = 0.f;
+    for (int z = 0; z < p.nsplit; ++z) s += __ldcg(base + (size_t)z * (32 * 128 + 32) + i);
+    q.dw[(size_t)(n0 + (i >> 7)) * q.K + k0 + (i & 127)] = s;
+  }
+  if (q.db != nullptr && k0 == 0 && threadIdx.x < 32) {
+    float s = 0.f;
+    for (int z = 0; z < p.nsplit; ++z) s += __ldcg(base + (size_t)z * (32 * 128 + 32) + 32 * 128 + threadIdx.x);
+    q.db[n0 + threadIdx.x] = s;
+  }
+}
+
+static int set_smem(const void* fn, size_t bytes) {
+  TMF_REQUIRE(bytes <= 227 * 1024, "encoder kernels: %zu bytes of shared memory needed", bytes);
+  TMF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+// raise a kernel's dynamic shared-memory limit only when a call needs more than any earlier one
+static int grow_smem(const void* fn, size_t bytes, size_t& cur) {
+  if (bytes <= cur) return 0;
+  if (set_smem(fn, bytes)) return 2;
+  cur = bytes;
+  return 0;
+}
+
+}  // namespace enc
+}  // namespace tmf
+
+using namespace tmf;
+using namespace tmf::enc;
+
+static int enc_check_ws(const char* who, void* ws, size_t ws_bytes) {
+  TMF_REQUIRE(ws != nullptr && ws_bytes >= TMF_WS_BYTES && ((uintptr_t)ws & 255) == 0,
+              "%s: needs the 256-byte aligned scratch buffer of tmf_scratch_bytes() bytes (tickets zero-initialised)", who);
+  return 0;
+}
+// ticket slots of the encoder kernels inside the scratch buffer's ticket area (fusion_ops.cu uses [0, 4096) x 4 bytes of
+// the 16 KB; here: the upper words)
+static unsigned* enc_tickets(void* ws, int which) { return reinterpret_cast<unsigned*>(ws) + 3900 + which * 64; }
+static float* enc_partials(void* ws) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + TMF_WS_TICKET_BYTES); }
+
+extern "C" {
+
+int tmf_encoder_supported(int dim, int inner, int mlp) {
+  return (dim == 128 && inner == 128 && mlp % 128 == 0 && mlp >= 128 && mlp <= 1024) ? 1 : 0;
+}
+
+int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, const float* ln_b, const float* wq,
+                         const float* wkv, float* h1, float* mean1, float* rstd1, float* q, float* kv, int Mx, int Mc,
+                         float eps, void* stream) {
+  TMF_REQUIRE(x && ctx && ln_w && ln_b && wq && wkv && h1 && mean1 && rstd1 && q && kv, "encoder_proj_fwd: NULL pointer");
+  TMF_REQUIRE(Mx > 0 && Mc > 0, "encoder_proj_fwd: empty input");
+  ProjFwdArgs p{x, ctx, ln_w, ln_b, wq, wkv, h1, mean1, rstd1, q, kv, Mx, Mc, ceil_div(Mx, PR), eps};
+  const size_t smem = sizeof(float) * (PR * LD128 + PR * 260 + NSTAGE * WT_FLOATS);
+  static bool done = false;
+  if (!done) { if (set_smem((const void*)enc_proj_fwd_kernel, smem)) return 2; done = true; }
+  enc_proj_fwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_encoder_chain_fwd(const float* o, const float* x, const float* wo, const float* bo, const float* ln2_w,
+                          const float* ln2_b, const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* lnf_w, const float* lnf_b, float* a, float* h2, float* mean2, float* rstd2,
+                          float* pre, float* f, float* g, float* meanf, float* rstdf, float* y, int M, int mlp,
+                          int add_input, float eps2, float epsf, void* stream) {
+  TMF_REQUIRE(o && x && wo && bo && ln2_w && ln2_b && w1 && b1 && w2 && b2 && lnf_w && lnf_b && a && h2 && mean2 && rstd2 &&
+                  pre && f && g && meanf && rstdf && y, "encoder_chain_fwd: NULL pointer");
+  TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_chain_fwd: mlp_dim %d not supported", mlp);
+  ChainFwdArgs p{o, x, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf, y,
+                 M, mlp, add_input, eps2, epsf};
+  const size_t smem = sizeof(float) * (3 * PR * LD128 + PR * (mlp + 4) + NSTAGE * WT_FLOATS);
+  static size_t cur_f = 0;
+  if (grow_smem((const void*)enc_chain_fwd_kernel, smem, cur_f)) return 2;
+  enc_chain_fwd_kernel<<<ceil_div(M, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const float* pre, const float* wo,
+                          const float* w1, const float* w2, const float* ln2_w, const float* lnf_w, const float* mean2,
+                          const float* rstd2, const float* meanf, const float* rstdf, float* dg, float* dp, float* da,
+                          float* dout, float* dxp, float* dlnf_w, float* dlnf_b, float* dln2_w, float* dln2_b, int M,
+                          int mlp, int add_input, void* ws, size_t ws_bytes, void* stream) {
+  TMF_REQUIRE(dy && g && a && pre && wo && w1 && w2 && ln2_w && lnf_w && mean2 && rstd2 && meanf && rstdf && dg && dp && da &&
+                  dout && dxp && dlnf_w && dlnf_b && dln2_w && dln2_b, "encoder_chain_bwd: NULL pointer");
+  TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_chain_bwd: mlp_dim %d not supported", mlp);
+  if (enc_check_ws("encoder_chain_bwd", ws, ws_bytes)) return 1;
+  const int nb = ceil_div(M, PR);
+  TMF_REQUIRE((size_t)nb * 512 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_chain_bwd: too many rows");
+  ChainBwdArgs p{dy, g, a, pre, wo, w1, w2, ln2_w, lnf_w, mean2, rstd2, meanf, rstdf, dg, dp, da, dout, dxp,
+                 dlnf_w, dlnf_b, dln2_w, dln2_b, enc_partials(ws), enc_tickets(ws, 0), M, mlp, add_input};
+  const size_t smem = sizeof(float) * (3 * PR * LD128 + PR * (mlp + 4) + NSTAGE * WT_FLOATS + 512);
+  static size_t cur_b = 0;
+  if (grow_smem((const void*)enc_chain_bwd_kernel, smem, cur_b)) return 2;
+  enc_chain_bwd_kernel<<<nb, THREADS, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+int tmf_encoder_proj_bwd(const float* dq, const float* dkv, const float* dxp, const float* x, const float* ln_w,
+                         const float* mean1, const float* rstd1, const float* wq, const float* wkv, float* dx, float* dctx,
+                         float* dln_w, float* dln_b, int Mx, int Mc, void* ws, size_t ws_bytes, void* stream) {
+  TMF_REQUIRE(dq && dkv && dxp && x && ln_w && mean1 && rstd1 && wq && wkv && dx && dctx && dln_w && dln_b,
+              "encoder_proj_bwd: NULL pointer");
+  if (enc_check_ws("encoder_proj_bwd", ws, ws_bytes)) return 1;
+  ProjBwdArgs p{dq, dkv, dxp, x, ln_w, mean1, rstd1, wq, wkv, dx, dctx, dln_w, dln_b, enc_partials(ws), enc_tickets(ws, 1),
+                Mx, Mc, ceil_div(Mx, PR)};
+  TMF_REQUIRE((size_t)p.nbx * 256 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_proj_bwd: too many rows");
+  const size_t smem = sizeof(float) * (PR * 260 + 2 * PR * LD128 + NSTAGE * WT_FLOATS + 256);
+  static bool done = false;
+  if (!done) { if (set_smem((const void*)enc_proj_bwd_kernel, smem)) return 2; done = true; }
+  enc_proj_bwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+/* t[15] = {dq, h1, dWq,  dkv, ctx, dWkv,  da, o, dWo, dbo,  dp, h2, dW1, db1,  dg}; f, dW2, db2 follow as arguments */
+int tmf_encoder_wgrad(const void* const* t, const float* f, float* dw2, float* db2, int Mx, int Mc, int mlp, void* ws,
+                      size_t ws_bytes, void* stream) {
+  TMF_REQUIRE(t != nullptr && f && dw2 && db2, "encoder_wgrad: NULL pointer");
+  for (int i = 0; i < 15; ++i) TMF_REQUIRE(t[i] != nullptr, "encoder_wgrad: NULL tensor %d", i);
+  TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_wgrad: mlp_dim %d not supported", mlp);
+  if (enc_check_ws("encoder_wgrad", ws, ws_bytes)) return 1;
+  WgradArgs p{};
+  auto F = [&](int i) { return (const float*)t[i]; };
+  auto G = [&](int i) { return (float*)const_cast<void*>(t[i]); };
+  p.pr[0] = WgradProblem{F(0), F(1), G(2), nullptr, 128, 128, 128, 128, Mx, 0};
+  p.pr[1] = WgradProblem{F(3), F(4), G(5), nullptr, 256, 128, 256, 128, Mc, 0};
+  p.pr[2] = WgradProblem{F(6), F(7), G(8), G(9), 128, 128, 128, 128, Mx, 0};
+  p.pr[3] = WgradProblem{F(10), F(11), G(12), G(13), mlp, 128, mlp, 128, Mx, 0};
+  p.pr[4] = WgradProblem{F(14), f, dw2, db2, 128, mlp, 128, mlp, Mx, 0};
+  int tiles = 0;
+  for (int i = 0; i < WG_PROBLEMS; ++i) {
+    p.pr[i].tile0 = tiles;
+    tiles += (p.pr[i].N / 32) * (p.pr[i].K / 128);
+  }
+  p.ntiles = tiles;
+  p.nsplit = ceil_div(Mx > Mc ? Mx : Mc, WG_MC);
+  TMF_REQUIRE(tiles <= 64, "encoder_wgrad: too many tiles");
+  TMF_REQUIRE((size_t)tiles * p.nsplit * (32 * 128 + 32) * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES,
+              "encoder_wgrad: token count too large for the scratch buffer");
+  p.part = enc_partials(ws);
+  p.tickets = enc_tickets(ws, 2);
+  const size_t smem = sizeof(float) * (32 * WG_LDA + NSTAGE * WT_FLOATS);
+  static bool done = false;
+  if (!done) { if (set_smem((const void*)enc_wgrad_kernel, smem)) return 2; done = true; }
+  enc_wgrad_kernel<<<tiles * p.nsplit, THREADS, smem, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -377,6 +377,81 @@ def attention_core(q, kv, heads, scale):
     return AttentionCoreFunction.apply(q, kv, heads, scale)
 
 
+class EncoderFunction(torch.autograd.Function):
+    """One ``Transformer(depth=1)`` encoder (reference models/networks.py:215-230) with cross-attention context, as three
+    forward and five backward launches (csrc/enc_fused.cu + the attention core):
+        a = Attn(LN1(x), ctx) + x;   y = LNf(FF(LN2(a)) + a) (+ x when ``add_input``: the caller's outer residual).
+    params = (ln1_w, ln1_b, wq, wkv, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b)."""
+
+    @staticmethod
+    def forward(ctx, x, context, heads, scale, add_input, eps1, eps2, epsf, *params):
+        ln1_w, ln1_b, wq, wkv, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b = [_f32c(t) for t in params]
+        x3, c3 = _f32c(x), _f32c(context)
+        B, Nq, dim = x3.shape
+        Nk = c3.shape[1]
+        Mx, Mc, mlp = B * Nq, B * Nk, w1.shape[0]
+        dev = x3.device
+        E = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        h1, mean1, rstd1, q, kv = E(Mx, dim), E(Mx), E(Mx), E(B, Nq, dim), E(B, Nk, 2 * dim)
+        L.call("tmf_encoder_proj_fwd", L.ptr(x3), L.ptr(c3), L.ptr(ln1_w), L.ptr(ln1_b), L.ptr(wq), L.ptr(wkv), L.ptr(h1),
+               L.ptr(mean1), L.ptr(rstd1), L.ptr(q), L.ptr(kv), Mx, Mc, float(eps1))
+        o, lse = E(B, Nq, dim), E(B, heads, Nq)
+        L.call("tmf_attn_fwd", L.ptr(q), L.ptr(kv), L.ptr(o), L.ptr(lse), B, Nq, Nk, heads, dim // heads, float(scale))
+        a, h2, mean2, rstd2, pre, f, g = E(Mx, dim), E(Mx, dim), E(Mx), E(Mx), E(Mx, mlp), E(Mx, mlp), E(Mx, dim)
+        meanf, rstdf, y = E(Mx), E(Mx), E(B, Nq, dim)
+        L.call("tmf_encoder_chain_fwd", L.ptr(o), L.ptr(x3), L.ptr(wo), L.ptr(bo), L.ptr(ln2_w), L.ptr(ln2_b), L.ptr(w1),
+               L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(lnf_w), L.ptr(lnf_b), L.ptr(a), L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
+               L.ptr(pre), L.ptr(f), L.ptr(g), L.ptr(meanf), L.ptr(rstdf), L.ptr(y), Mx, mlp, int(add_input), float(eps2),
+               float(epsf))
+        ctx.save_for_backward(x3, c3, h1, mean1, rstd1, q, kv, o, lse, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf,
+                              ln1_w, wq, wkv, wo, ln2_w, w1, w2, lnf_w)
+        ctx.param_refs = params                              # references only: gradient slots of the flat DP buffer
+        ctx.cfg = (heads, float(scale), bool(add_input), B, Nq, Nk, dim, mlp)
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x3, c3, h1, mean1, rstd1, q, kv, o, lse, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf,
+         ln1_w, wq, wkv, wo, ln2_w, w1, w2, lnf_w) = ctx.saved_tensors
+        heads, scale, add_input, B, Nq, Nk, dim, mlp = ctx.cfg
+        Mx, Mc = B * Nq, B * Nk
+        dev = x3.device
+        E = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        P = ctx.param_refs
+        G = lambda i: grad_out(P[i])
+        d_ln1_w, d_ln1_b, d_wq, d_wkv, d_wo, d_bo, d_ln2_w, d_ln2_b, d_w1, d_b1, d_w2, d_b2, d_lnf_w, d_lnf_b = [G(i) for i in range(14)]
+        ws, nws = L.scratch(dev)
+        dy2 = _f32c(dy).reshape(Mx, dim)
+        dg, dp, da, dout, dxp = E(Mx, dim), E(Mx, mlp), E(Mx, dim), E(B, Nq, dim), E(Mx, dim)
+        L.call("tmf_encoder_chain_bwd", L.ptr(dy2), L.ptr(g), L.ptr(a), L.ptr(pre), L.ptr(wo), L.ptr(w1), L.ptr(w2), L.ptr(ln2_w),
+               L.ptr(lnf_w), L.ptr(mean2), L.ptr(rstd2), L.ptr(meanf), L.ptr(rstdf), L.ptr(dg), L.ptr(dp), L.ptr(da),
+               L.ptr(dout), L.ptr(dxp), L.ptr(d_lnf_w), L.ptr(d_lnf_b), L.ptr(d_ln2_w), L.ptr(d_ln2_b), Mx, mlp,
+               int(add_input), L.ptr(ws), nws)
+        dq, dkv = E(B, Nq, dim), E(B, Nk, 2 * dim)
+        L.call("tmf_attn_bwd", L.ptr(dout), L.ptr(q), L.ptr(kv), L.ptr(o), L.ptr(lse), L.ptr(dq), L.ptr(dkv), B, Nq, Nk, heads,
+               dim // heads, scale)
+        dx, dctx = E(B, Nq, dim), E(B, Nk, dim)
+        L.call("tmf_encoder_proj_bwd", L.ptr(dq), L.ptr(dkv), L.ptr(dxp), L.ptr(x3), L.ptr(ln1_w), L.ptr(mean1), L.ptr(rstd1),
+               L.ptr(wq), L.ptr(wkv), L.ptr(dx), L.ptr(dctx), L.ptr(d_ln1_w), L.ptr(d_ln1_b), Mx, Mc, L.ptr(ws), nws)
+        table = (ctypes_ptr_array([dq, h1, d_wq, dkv, c3, d_wkv, da, o, d_wo, d_bo, dp, h2, d_w1, d_b1, dg]))
+        L.call("tmf_encoder_wgrad", table, L.ptr(f), L.ptr(d_w2), L.ptr(d_b2), Mx, Mc, mlp, L.ptr(ws), nws)
+        return (dx.reshape(x3.shape), dctx.reshape(c3.shape), None, None, None, None, None, None,
+                d_ln1_w, d_ln1_b, d_wq, d_wkv, d_wo, d_bo, d_ln2_w, d_ln2_b, d_w1, d_b1, d_w2, d_b2, d_lnf_w, d_lnf_b)
+
+
+def ctypes_ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def encoder_supported(dim, inner, mlp):
+    return os.environ.get("TMF_ENC_FUSED", "1") != "0" and bool(L.load().tmf_encoder_supported(int(dim), int(inner), int(mlp)))
+
+
+def encoder(x, context, heads, scale, add_input, eps1, eps2, epsf, params):
+    return EncoderFunction.apply(x, context, heads, scale, add_input, eps1, eps2, epsf, *params)
+
+
 class TokenPoolFunction(torch.autograd.Function):
     """x (B,N,C) -> mean over N (B,C) and/or max over N (B,C) (first-maximum gradient routing)."""
 
