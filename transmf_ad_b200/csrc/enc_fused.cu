@@ -29,7 +29,7 @@ namespace enc {
 constexpr int THREADS = 256;
 constexpr int PR = 16;                       // panel rows
 constexpr int WT_FLOATS = 128 * 36;          // one weight stage: [128][32+4] (B_NK) or [32][128+8] (B_KN)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
 constexpr int LD128 = 132;                   // panel pitch for 128 columns (== 4 mod 32: conflict-free A fragments)
 
 enum { B_NK = 0, B_KN = 1 };                 // weight tile is W[n][k] (forward) or W[k][n] (dgrad / wgrad operand)
@@ -43,14 +43,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 register anyway), lo = x - hi
+// (exact).  One LOP + one FADD per element: cvt.rna.tf32 runs on the quarter-rate conversion pipe and, at 16 conversions
+// per warp and k-step, cost more than the MMAs (measured: 46 us -> see profiles/r2_encoder.md).  lo carries up to 13
+// significant bits of which the tensor core keeps 11: the result is good to ~2^-22 relative, the size of the dropped
+// lo*lo term.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -86,71 +86,113 @@ __device__ __forceinline__ void stage_w(float* Ws, const float* __restrict__ W, 
   }
 }
 
-// C[16*MT rows][N] = A[16*MT][K] . op(W), A in shared memory (pitch lda == 4 mod 32), N % 128 == 0, K % 32 == 0.
-//   MT = 1: warp w owns columns [16w, 16w+16) of every 128-column block (2 n-tiles);
-//   MT = 2: warp w owns m-tile (w & 1) and columns [32(w>>1), +32) (4 n-tiles).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+
+// C[16*MT rows][N] = A[16*MT][K] . op(W), A in shared memory (pitch LDA == 4 mod 32), N % 128 == 0, K % 32 == 0.
+//   MT = 1: warp w owns columns [16w, 16w+16) of every 128-column block (2 n-tiles).  The A panel is split ONCE into a
+//           hi and a lo plane (`asplit`, 2 x 16 x LDA floats) and a warp's A fragments come from two ldmatrix.x4 per k-step
+//           (a 16 x 8 tf32 tile is a 16 x 16 b16 tile to ldmatrix): all 8 warps used to redo the same 4 loads + 8 ALU ops;
+//   MT = 2: warp w owns m-tile (w & 1) and columns [32(w>>1), +32) (4 n-tiles); A is split in registers (weight gradients).
 // epi(row, col, v0, v1) receives two adjacent columns of one row.  Ends with __syncthreads().
-template <int MT, int MODE, typename Epi>
-__device__ __forceinline__ void panel_gemm(const float* As, int lda, const float* __restrict__ W, int ldw, int N, int K,
-                                           int kvalid, float* wstage, Epi epi) {
+template <int MT, int MODE, int LDA, typename Epi>
+__device__ __forceinline__ void panel_gemm(const float* As, const float* __restrict__ W, int ldw, int N, int K, int kvalid,
+                                           float* wstage, float* asplit, Epi epi) {
   constexpr int NT = (MT == 2) ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int mt = (MT == 2) ? (warp & 1) : 0;
   const int cbase = ((MT == 2) ? (warp >> 1) : warp) * NT * 8;
   const int nk = K / 32;
-  const float* arow = As + (mt * 16 + g) * lda + t;
-  for (int nb = 0; nb < N; nb += 128) {
-    float acc[NT][4];
+  const int total = (N / 128) * nk;          // weight stages of the whole GEMM: ONE continuous pipeline over all column blocks
+  const float* arow = As + (mt * 16 + g) * LDA + t;
+  auto issue = [&](int s) {
+    stage_w<MODE>(wstage + (s % NSTAGE) * WT_FLOATS, W, ldw, (s / nk) * 128, (s % nk) * 32, kvalid);
+  };
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-#pragma unroll
-    for (int s = 0; s < NSTAGE - 1; ++s) {
-      if (s < nk) stage_w<MODE>(wstage + s * WT_FLOATS, W, ldw, nb, s * 32, kvalid);
-      cp_async_commit();
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < total) issue(s);
+    cp_async_commit();
+  }
+  uint32_t a_hi_addr = 0, a_lo_addr = 0;
+  if (MT == 1) {
+    // split the panel once (the first __syncthreads of the loop below orders it before any fragment load)
+    for (int i = threadIdx.x; i < PR * (K >> 2); i += THREADS) {
+      const int r = i / (K >> 2), c = i - r * (K >> 2);
+      const float4 v = *reinterpret_cast<const float4*>(As + r * LDA + 4 * c);
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+      *reinterpret_cast<float4*>(asplit + r * LDA + 4 * c) = h;
+      *reinterpret_cast<float4*>(asplit + PR * LDA + r * LDA + 4 * c) = l;
     }
-    for (int kc = 0; kc < nk; ++kc) {
-      cp_async_wait<NSTAGE - 2>();
-      __syncthreads();
-      if (kc + NSTAGE - 1 < nk)
-        stage_w<MODE>(wstage + ((kc + NSTAGE - 1) % NSTAGE) * WT_FLOATS, W, ldw, nb, (kc + NSTAGE - 1) * 32, kvalid);
-      cp_async_commit();
-      const float* Ws = wstage + (kc % NSTAGE) * WT_FLOATS;
+    // ldmatrix row addresses: lane i -> matrix i/8 (0: rows 0-7 k 0-3, 1: rows 8-15 k 0-3, 2: rows 0-7 k 4-7, 3: rows 8-15 k 4-7)
+    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lcol = 4 * (lane >> 4);
+    a_hi_addr = (uint32_t)__cvta_generic_to_shared(asplit + lrow * LDA + lcol);
+    a_lo_addr = a_hi_addr + PR * LDA * 4;
+  }
+  float acc[NT][4], acl[NT][4];        // hi*hi products and the two small cross terms accumulate in separate chains
+  for (int s = 0; s < total; ++s) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    if (s + NSTAGE - 1 < total) issue(s + NSTAGE - 1);
+    cp_async_commit();
+    const int kc = s % nk;
+    if (kc == 0) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const float* ap = arow + kc * 32 + ks * 8;
-        uint32_t ah[4], al[4];
-        split_tf32(ap[0], ah[0], al[0]);
-        split_tf32(ap[8 * lda], ah[1], al[1]);
-        split_tf32(ap[4], ah[2], al[2]);
-        split_tf32(ap[8 * lda + 4], ah[3], al[3]);
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          float b0, b1;
-          if (MODE == B_NK) {
-            const float* bp = Ws + (cbase + j * 8 + g) * 36 + ks * 8 + t;
-            b0 = bp[0]; b1 = bp[4];
-          } else {
-            const float* bp = Ws + (ks * 8 + t) * 136 + cbase + j * 8 + g;
-            b0 = bp[0]; b1 = bp[4 * 136];
-          }
-          uint32_t bh[2], bl[2];
-          split_tf32(b0, bh[0], bl[0]);
-          split_tf32(b1, bh[1], bl[1]);
-          mma_tf32(acc[j], al, bh);
-          mma_tf32(acc[j], ah, bl);
-          mma_tf32(acc[j], ah, bh);
-        }
+      for (int j = 0; j < NT; ++j) {
+        acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f;
+        acl[j][0] = 0.f; acl[j][1] = 0.f; acl[j][2] = 0.f; acl[j][3] = 0.f;
       }
     }
-    cp_async_wait<0>();
+    const float* Ws = wstage + (s % NSTAGE) * WT_FLOATS;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int col = nb + cbase + j * 8 + 2 * t;
-      epi(mt * 16 + g, col, acc[j][0], acc[j][1]);
-      epi(mt * 16 + g + 8, col, acc[j][2], acc[j][3]);
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      if (MT == 1) {
+        const uint32_t koff = (uint32_t)(kc * 32 + ks * 8) * 4u;
+        ldmatrix_x4(ah, a_hi_addr + koff);
+        ldmatrix_x4(al, a_lo_addr + koff);
+      } else {
+        const float* ap = arow + kc * 32 + ks * 8;
+        split_tf32(ap[0], ah[0], al[0]);
+        split_tf32(ap[8 * LDA], ah[1], al[1]);
+        split_tf32(ap[4], ah[2], al[2]);
+        split_tf32(ap[8 * LDA + 4], ah[3], al[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float b0, b1;
+        if (MODE == B_NK) {
+          const float* bp = Ws + (cbase + j * 8 + g) * 36 + ks * 8 + t;
+          b0 = bp[0]; b1 = bp[4];
+        } else {
+          const float* bp = Ws + (ks * 8 + t) * 136 + cbase + j * 8 + g;
+          b0 = bp[0]; b1 = bp[4 * 136];
+        }
+        uint32_t bh[2], bl[2];
+        split_tf32(b0, bh[0], bl[0]);
+        split_tf32(b1, bh[1], bl[1]);
+        mma_tf32(acl[j], al, bh);
+        mma_tf32(acc[j], ah, bh);
+        mma_tf32(acl[j], ah, bl);
+      }
     }
-    __syncthreads();
+    if (kc == nk - 1) {
+      const int nb = (s / nk) * 128;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int col = nb + cbase + j * 8 + 2 * t;
+        epi(mt * 16 + g, col, acc[j][0] + acl[j][0], acc[j][1] + acl[j][1]);
+        epi(mt * 16 + g + 8, col, acc[j][2] + acl[j][2], acc[j][3] + acl[j][3]);
+      }
+    }
   }
+  cp_async_wait<0>();
+  __syncthreads();
 }
 
 // ---- panel <-> global helpers (all 256 threads; float4, rows >= nvalid read as zero / are not written) ----------------
@@ -265,7 +307,8 @@ __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
   extern __shared__ __align__(16) float sm[];
   float* P0 = sm;                           // [16][132] input panel
   float* P1 = P0 + PR * LD128;              // [16][260] output panel
-  float* wst = P1 + PR * 260;
+  float* spl = P1 + PR * 260;               // [2][16][132] hi / lo planes of the GEMM's A panel
+  float* wst = spl + 2 * PR * LD128;
   if ((int)blockIdx.x < p.nbx) {
     const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
     load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
@@ -273,7 +316,7 @@ __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
     panel_layernorm(P0, P0, LD128, p.ln_w, p.ln_b, p.eps, p.mean1, p.rstd1, row0, nv);
     __syncthreads();
     store_panel(p.h1 + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
-    panel_gemm<1, B_NK>(P0, LD128, p.wq, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    panel_gemm<1, B_NK, LD128>(P0, p.wq, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
     store_panel(p.q + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
@@ -281,7 +324,7 @@ __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
     const int row0 = (blockIdx.x - p.nbx) * PR, nv = min(PR, p.Mc - row0);
     load_panel(P0, LD128, p.ctx + (size_t)row0 * 128, 128, nv, PR, 128);
     __syncthreads();
-    panel_gemm<1, B_NK>(P0, LD128, p.wkv, 128, 256, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    panel_gemm<1, B_NK, LD128>(P0, p.wkv, 128, 256, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * 260 + c) = make_float2(v0, v1);
     });
     store_panel(p.kv + (size_t)row0 * 256, 256, P1, 260, nv, 256);
@@ -298,20 +341,22 @@ struct ChainFwdArgs {
   float eps2, epsf;
 };
 
+template <int MLP>
 __global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) {
   extern __shared__ __align__(16) float sm[];
-  const int ldf = p.mlp + 4;
+  constexpr int ldf = MLP + 4;
   float* P0 = sm;                           // o, later g
   float* P1 = P0 + PR * LD128;              // a
   float* P2 = P1 + PR * LD128;              // h2
   float* PF = P2 + PR * LD128;              // [16][mlp+4]: pre-activation, then f
-  float* wst = PF + PR * ldf;
+  float* spl = PF + PR * ldf;               // [2][16][mlp+4] hi / lo planes of the current GEMM's A panel
+  float* wst = spl + 2 * PR * ldf;
   const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
   load_panel(P0, LD128, p.o + (size_t)row0 * 128, 128, nv, PR, 128);
   load_panel(P2, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);     // x parked in P2 until LN2 overwrites it
   __syncthreads();
   // a = o Wo^T + bo + x
-  panel_gemm<1, B_NK>(P0, LD128, p.wo, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_NK, LD128>(P0, p.wo, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     const float2 xb = *reinterpret_cast<const float2*>(P2 + r * LD128 + c);
     *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0 + __ldg(p.bo + c) + xb.x, v1 + __ldg(p.bo + c + 1) + xb.y);
   });
@@ -320,19 +365,19 @@ __global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) 
   __syncthreads();
   store_panel(p.h2 + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
   // pre = h2 W1^T + b1
-  panel_gemm<1, B_NK>(P2, LD128, p.w1, 128, p.mlp, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_NK, LD128>(P2, p.w1, 128, MLP, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     *reinterpret_cast<float2*>(PF + r * ldf + c) = make_float2(v0 + __ldg(p.b1 + c), v1 + __ldg(p.b1 + c + 1));
   });
-  store_panel(p.pre + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  store_panel(p.pre + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
   __syncthreads();
-  for (int i = threadIdx.x; i < PR * p.mlp; i += THREADS) {
-    const int r = i / p.mlp, c = i - r * p.mlp;
+  for (int i = threadIdx.x; i < PR * MLP; i += THREADS) {
+    const int r = i / MLP, c = i - r * MLP;
     PF[r * ldf + c] = gelu_exact(PF[r * ldf + c]);
   }
   __syncthreads();
-  store_panel(p.f + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  store_panel(p.f + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
   // g = f W2^T + b2 + a
-  panel_gemm<1, B_NK>(PF, ldf, p.w2, p.mlp, 128, p.mlp, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_NK, MLP + 4>(PF, p.w2, MLP, 128, MLP, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     const float2 ab = *reinterpret_cast<const float2*>(P1 + r * LD128 + c);
     *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0 + __ldg(p.b2 + c) + ab.x, v1 + __ldg(p.b2 + c + 1) + ab.y);
   });
@@ -365,14 +410,16 @@ struct ChainBwdArgs {
   int M, mlp, add_input;
 };
 
+template <int MLP>
 __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) {
   extern __shared__ __align__(16) float sm[];
-  const int ldf = p.mlp + 4;
+  constexpr int ldf = MLP + 4;
   float* P0 = sm;
   float* P1 = P0 + PR * LD128;
   float* P2 = P1 + PR * LD128;
   float* PF = P2 + PR * LD128;
-  float* wst = PF + PR * ldf;
+  float* spl = PF + PR * ldf;
+  float* wst = spl + 2 * PR * ldf;
   float* red = wst + NSTAGE * WT_FLOATS;            // [4][128]
   const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -385,16 +432,16 @@ __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) 
   __syncthreads();
   store_panel(p.dg + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
   // dp = (dg W2) * GELU'(pre)  -> PF        (W2 is [128][mlp]: reduction over its rows)
-  load_panel(PF, ldf, p.pre + (size_t)row0 * p.mlp, p.mlp, nv, PR, p.mlp);
+  load_panel(PF, ldf, p.pre + (size_t)row0 * MLP, MLP, nv, PR, MLP);
   __syncthreads();
-  panel_gemm<1, B_KN>(P2, LD128, p.w2, p.mlp, p.mlp, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_KN, LD128>(P2, p.w2, MLP, MLP, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     float2* q = reinterpret_cast<float2*>(PF + r * ldf + c);
     const float2 pr = *q;
     *q = make_float2(v0 * gelu_grad(pr.x), v1 * gelu_grad(pr.y));
   });
-  store_panel(p.dp + (size_t)row0 * p.mlp, p.mlp, PF, ldf, nv, p.mlp);
+  store_panel(p.dp + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
   // dh2 = dp W1  -> P0                       (W1 is [mlp][128])
-  panel_gemm<1, B_KN>(PF, ldf, p.w1, 128, 128, p.mlp, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_KN, MLP + 4>(PF, p.w1, 128, 128, MLP, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0, v1);
   });
   // da = dg + LN2'(dh2)  -> P0
@@ -414,7 +461,7 @@ __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) 
     reinterpret_cast<float4*>(p.dxp + (size_t)(row0 + r) * 128)[c] = v;
   }
   // do = da Wo  -> P1                        (Wo is [128][128])
-  panel_gemm<1, B_KN>(P0, LD128, p.wo, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+  panel_gemm<1, B_KN, LD128>(P0, p.wo, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
     *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
   });
   store_panel(p.dout + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
@@ -444,14 +491,15 @@ __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
   float* P0 = sm;                           // [16][260]
   float* P1 = P0 + PR * 260;                // [16][132]
   float* P2 = P1 + PR * LD128;              // [16][132]
-  float* wst = P2 + PR * LD128;
+  float* spl = P2 + PR * LD128;             // [2][16][260]
+  float* wst = spl + 2 * PR * 260;
   float* red = wst + NSTAGE * WT_FLOATS;    // [2][128]
   if ((int)blockIdx.x < p.nbx) {
     const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
     load_panel(P0, LD128, p.dq + (size_t)row0 * 128, 128, nv, PR, 128);
     __syncthreads();
     // dh1 = dq Wq  -> P1
-    panel_gemm<1, B_KN>(P0, LD128, p.wq, 128, 128, 128, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    panel_gemm<1, B_KN, LD128>(P0, p.wq, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
     load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
@@ -469,7 +517,7 @@ __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
     load_panel(P0, 260, p.dkv + (size_t)row0 * 256, 256, nv, PR, 256);
     __syncthreads();
     // dctx = dkv Wkv                          (Wkv is [256][128])
-    panel_gemm<1, B_KN>(P0, 260, p.wkv, 128, 128, 256, 1 << 30, wst, [&](int r, int c, float v0, float v1) {
+    panel_gemm<1, B_KN, 260>(P0, p.wkv, 128, 128, 256, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
     store_panel(p.dctx + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
@@ -489,7 +537,7 @@ __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
 // A block computes a [32 (n)] x [128 (k)] tile of one problem over one chunk of WG_MC tokens; the chunks of a tile meet
 // in scratch and the last one adds them in order.
 // =====================================================================================================================
-constexpr int WG_MC = 384;                  // tokens per chunk; pitch 388 == 4 mod 32
+constexpr int WG_MC = 416;                  // tokens per chunk (3 chunks cover 1200 tokens: 144 blocks); pitch 420 == 4 mod 32
 constexpr int WG_LDA = WG_MC + 4;
 constexpr int WG_PROBLEMS = 5;
 
@@ -519,14 +567,26 @@ __global__ void __launch_bounds__(THREADS) enc_wgrad_kernel(WgradArgs p) {
   const int n0 = (lt / kt) * 32, k0 = (lt % kt) * 128;
   const int m0 = split * WG_MC, mv = max(0, min(WG_MC, q.M - m0));
   // stage dY^T: At[n][m] = dY[m0 + m][n0 + n]   (a warp reads 32 consecutive n of one token: 128 B)
-  for (int i = threadIdx.x; i < WG_MC * 8; i += THREADS) {
-    const int m = i >> 3, c = i & 7;
-    const float4 v = (m < mv) ? __ldg(reinterpret_cast<const float4*>(q.dy + (size_t)(m0 + m) * q.ldy + n0) + c)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-    At[(4 * c + 0) * WG_LDA + m] = v.x;
-    At[(4 * c + 1) * WG_LDA + m] = v.y;
-    At[(4 * c + 2) * WG_LDA + m] = v.z;
-    At[(4 * c + 3) * WG_LDA + m] = v.w;
+  // (batches of 13 independent 128-bit loads per thread before any is stored: one L2 round trip per batch)
+  static_assert(WG_MC * 8 == 13 * THREADS, "staging loop assumes 13 loads per thread");
+  {
+    float4 v[13];
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int i = threadIdx.x + u * THREADS;
+      const int m = i >> 3, c = i & 7;
+      v[u] = (m < mv) ? __ldg(reinterpret_cast<const float4*>(q.dy + (size_t)(m0 + m) * q.ldy + n0) + c)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      const int i = threadIdx.x + u * THREADS;
+      const int m = i >> 3, c = i & 7;
+      At[(4 * c + 0) * WG_LDA + m] = v[u].x;
+      At[(4 * c + 1) * WG_LDA + m] = v[u].y;
+      At[(4 * c + 2) * WG_LDA + m] = v[u].z;
+      At[(4 * c + 3) * WG_LDA + m] = v[u].w;
+    }
   }
   __syncthreads();
   float* mypart = p.part + ((size_t)tile * p.nsplit + split) * (32 * 128 + 32);
@@ -541,7 +601,7 @@ __global__ void __launch_bounds__(THREADS) enc_wgrad_kernel(WgradArgs p) {
       if (lane == 0) mypart[32 * 128 + n] = s;
     }
   }
-  panel_gemm<2, B_KN>(At, WG_LDA, q.x + (size_t)(mv > 0 ? m0 : 0) * q.ldx + k0, q.ldx, 128, WG_MC, mv, wst,
+  panel_gemm<2, B_KN, WG_LDA>(At, q.x + (size_t)(mv > 0 ? m0 : 0) * q.ldx + k0, q.ldx, 128, WG_MC, mv, wst, nullptr,
                       [&](int r, int c, float v0, float v1) { *reinterpret_cast<float2*>(mypart + r * 128 + c) = make_float2(v0, v1); });
   if (!last_block_arrives(p.tickets + tile, p.nsplit)) return;
   const float* base = p.part + (size_t)tile * p.nsplit * (32 * 128 + 32);
@@ -589,7 +649,7 @@ static float* enc_partials(void* ws) { return reinterpret_cast<float*>(reinterpr
 extern "C" {
 
 int tmf_encoder_supported(int dim, int inner, int mlp) {
-  return (dim == 128 && inner == 128 && mlp % 128 == 0 && mlp >= 128 && mlp <= 1024) ? 1 : 0;
+  return (dim == 128 && inner == 128 && (mlp == 128 || mlp == 256 || mlp == 512)) ? 1 : 0;
 }
 
 int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, const float* ln_b, const float* wq,
@@ -598,7 +658,7 @@ int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, co
   TMF_REQUIRE(x && ctx && ln_w && ln_b && wq && wkv && h1 && mean1 && rstd1 && q && kv, "encoder_proj_fwd: NULL pointer");
   TMF_REQUIRE(Mx > 0 && Mc > 0, "encoder_proj_fwd: empty input");
   ProjFwdArgs p{x, ctx, ln_w, ln_b, wq, wkv, h1, mean1, rstd1, q, kv, Mx, Mc, ceil_div(Mx, PR), eps};
-  const size_t smem = sizeof(float) * (PR * LD128 + PR * 260 + NSTAGE * WT_FLOATS);
+  const size_t smem = sizeof(float) * (PR * LD128 + PR * 260 + 2 * PR * LD128 + NSTAGE * WT_FLOATS);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_proj_fwd_kernel, smem)) return 2; done = true; }
   enc_proj_fwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
@@ -616,10 +676,17 @@ int tmf_encoder_chain_fwd(const float* o, const float* x, const float* wo, const
   TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_chain_fwd: mlp_dim %d not supported", mlp);
   ChainFwdArgs p{o, x, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf, y,
                  M, mlp, add_input, eps2, epsf};
-  const size_t smem = sizeof(float) * (3 * PR * LD128 + PR * (mlp + 4) + NSTAGE * WT_FLOATS);
-  static size_t cur_f = 0;
-  if (grow_smem((const void*)enc_chain_fwd_kernel, smem, cur_f)) return 2;
-  enc_chain_fwd_kernel<<<ceil_div(M, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  const size_t smem = sizeof(float) * (3 * PR * LD128 + 3 * PR * (mlp + 4) + NSTAGE * WT_FLOATS);
+#define TMF_LAUNCH_CHAIN_FWD(MLPV)                                                                                 \
+  do {                                                                                                            \
+    static bool done = false;                                                                                     \
+    if (!done) { if (set_smem((const void*)enc_chain_fwd_kernel<MLPV>, smem)) return 2; done = true; }            \
+    enc_chain_fwd_kernel<MLPV><<<ceil_div(M, PR), THREADS, smem, (cudaStream_t)stream>>>(p);                      \
+  } while (0)
+  if (mlp == 128) TMF_LAUNCH_CHAIN_FWD(128);
+  else if (mlp == 256) TMF_LAUNCH_CHAIN_FWD(256);
+  else TMF_LAUNCH_CHAIN_FWD(512);
+#undef TMF_LAUNCH_CHAIN_FWD
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -637,10 +704,17 @@ int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const
   TMF_REQUIRE((size_t)nb * 512 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_chain_bwd: too many rows");
   ChainBwdArgs p{dy, g, a, pre, wo, w1, w2, ln2_w, lnf_w, mean2, rstd2, meanf, rstdf, dg, dp, da, dout, dxp,
                  dlnf_w, dlnf_b, dln2_w, dln2_b, enc_partials(ws), enc_tickets(ws, 0), M, mlp, add_input};
-  const size_t smem = sizeof(float) * (3 * PR * LD128 + PR * (mlp + 4) + NSTAGE * WT_FLOATS + 512);
-  static size_t cur_b = 0;
-  if (grow_smem((const void*)enc_chain_bwd_kernel, smem, cur_b)) return 2;
-  enc_chain_bwd_kernel<<<nb, THREADS, smem, (cudaStream_t)stream>>>(p);
+  const size_t smem = sizeof(float) * (3 * PR * LD128 + 3 * PR * (mlp + 4) + NSTAGE * WT_FLOATS + 512);
+#define TMF_LAUNCH_CHAIN_BWD(MLPV)                                                                                 \
+  do {                                                                                                            \
+    static bool done = false;                                                                                     \
+    if (!done) { if (set_smem((const void*)enc_chain_bwd_kernel<MLPV>, smem)) return 2; done = true; }            \
+    enc_chain_bwd_kernel<MLPV><<<nb, THREADS, smem, (cudaStream_t)stream>>>(p);                                   \
+  } while (0)
+  if (mlp == 128) TMF_LAUNCH_CHAIN_BWD(128);
+  else if (mlp == 256) TMF_LAUNCH_CHAIN_BWD(256);
+  else TMF_LAUNCH_CHAIN_BWD(512);
+#undef TMF_LAUNCH_CHAIN_BWD
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -654,7 +728,7 @@ int tmf_encoder_proj_bwd(const float* dq, const float* dkv, const float* dxp, co
   ProjBwdArgs p{dq, dkv, dxp, x, ln_w, mean1, rstd1, wq, wkv, dx, dctx, dln_w, dln_b, enc_partials(ws), enc_tickets(ws, 1),
                 Mx, Mc, ceil_div(Mx, PR)};
   TMF_REQUIRE((size_t)p.nbx * 256 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_proj_bwd: too many rows");
-  const size_t smem = sizeof(float) * (PR * 260 + 2 * PR * LD128 + NSTAGE * WT_FLOATS + 256);
+  const size_t smem = sizeof(float) * (PR * 260 + 2 * PR * LD128 + 2 * PR * 260 + NSTAGE * WT_FLOATS + 256);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_proj_bwd_kernel, smem)) return 2; done = true; }
   enc_proj_bwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
