@@ -243,8 +243,10 @@ int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int
 /* ---- optimizer -------------------------------------------------------------------------
  * Fused multi-tensor Adam with torch.optim.Adam arithmetic (amsgrad off): replaces the per-parameter launches of the
  * optimizer the reference builds in utils/utils.py:38-41.  `chunks` is a device array of `nchunks` records
- * {float* p; const float* g; float* m; float* v; int32 n; int32 pad} (tmf_adam_chunk_bytes() each, n <= 2^31-1), one block
- * per record.  `lr_dev` (1 float) and `step_dev` (1 float, the number of steps taken so far; advanced by the kernel) live
+ * {float* p; const float* g; float* m; float* v; bf16* wf; bf16* wd; int32 n, off, cout, cin, taps, pad}
+ * (tmf_adam_chunk_bytes() = 72 bytes each), one block per record.  wf != NULL marks a chunk (elements off .. off+n) of a
+ * Conv3d weight (cout,cin,k,k,k; taps = k^3) whose bf16 operand packs -- what tmf_pack_conv_weights writes -- are refreshed
+ * by the optimizer itself: the train step then has no weight-pack launches.  `lr_dev` (1 float) and `step_dev` (1 float, the number of steps taken so far; advanced by the kernel) live
  * on the device so that CUDA-graph replays see their current values; `ticket_dev` is a zero-initialised uint32 scratch. */
 int tmf_adam_chunk_bytes(void);
 int tmf_adam_step(const void* chunks, int nchunks, const float* lr_dev, float beta1, float beta2, float eps,

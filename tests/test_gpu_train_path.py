@@ -112,6 +112,31 @@ def test_one_step_of_fused_adam_equals_torch_adam_on_the_model(kind, kwargs, B, 
             assert bool((err <= 2e-7 + 2e-6 * v.abs()).all()), f"{k}: max |dp| {float(err.max()):.3e}"
 
 
+def test_fused_adam_keeps_the_conv_weight_packs_fresh():
+    """FusedAdam rewrites the bf16 operand packs of the conv weights from inside its kernel, so the
+    captured step contains no tmf_pack_conv_weights launch; the packs must equal an explicit pack of the updated weights."""
+    from transmf_ad_b200 import _lib as L
+    kind, kwargs, B, shape = CASES[0]
+    batches = _batches(B, shape, 2)
+    model = _model(kind, kwargs, seed=3)
+    opt = FusedAdam(model.parameters(), lr=LR, weight_decay=0.0)
+    step = GraphedTrainStep(model, opt, _loss, batches[0][:2], batches[0][2], warmup=3)
+    for mri, pet, label in batches:
+        step((mri, pet), label)
+    torch.cuda.synchronize()
+    for net in (model.mri_cnn, model.pet_cnn):
+        for l, (conv, _) in enumerate(net._units()):
+            if l == 0:
+                continue
+            w, pk = conv.weight.detach(), net._packs[l]
+            wf, wd = torch.empty_like(pk.wf), torch.empty_like(pk.wd)
+            L.call("tmf_pack_conv_weights", 1, L.ptrs([w]), L.ptrs([wf]), L.ptrs([wd]), w.shape[0], w.shape[1], w.shape[2])
+            assert torch.equal(wf, pk.wf) and torch.equal(wd, pk.wd), f"layer {l}"
+            assert not pk.stale(conv.weight)
+    # 99 launches per model_CNN_ad step in round 1; the 6 pack launches (and the per-layer memsets) are gone
+    assert step.launches_per_step <= 93, step.launches_per_step
+
+
 def test_fused_adam_state_dict_round_trip_matches_torch_adam():
     """a resumed FusedAdam must continue with the loaded step count (bias correction) and moments."""
     torch.manual_seed(0)

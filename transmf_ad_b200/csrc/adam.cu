@@ -9,15 +9,32 @@
 
 namespace tmf {
 
+// A chunk of a Conv3d weight (Cout,Cin,k,k,k) may carry the bf16 operand packs of the conv kernels: the updated value is
+// also written to wf[tap][Cout][Cin] (forward operand) and wd[taps-1-tap][Cin][Cout] (dgrad operand), which removes the
+// per-step tmf_pack_conv_weights launches from the train step.
 struct AdamChunk {
   float* p;
   const float* g;
   float* m;
   float* v;
+  __nv_bfloat16* wf;       // NULL: no packs
+  __nv_bfloat16* wd;       // may be NULL
   int32_t n;
+  int32_t off;             // element offset of this chunk inside its tensor (pack index arithmetic)
+  int32_t cout, cin, taps;
   int32_t pad;
 };
-static_assert(sizeof(AdamChunk) == 40, "host code packs 40-byte chunk records");
+static_assert(sizeof(AdamChunk) == 72, "host code packs 72-byte chunk records");
+
+__device__ __forceinline__ void emit_pack(const AdamChunk& c, int i, float val) {
+  const int idx = c.off + i;
+  const int t = idx % c.taps;
+  const int r = idx / c.taps;
+  const int ci = r % c.cin, co = r / c.cin;
+  const __nv_bfloat16 b = __float2bfloat16_rn(val);
+  c.wf[((size_t)t * c.cout + co) * c.cin + ci] = b;
+  if (c.wd != nullptr) c.wd[((size_t)(c.taps - 1 - t) * c.cin + ci) * c.cout + co] = b;
+}
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __restrict__ chunks, const float* __restrict__ lr_dev,
                                                          float b1, float b2, float eps, float wd, float* step_dev,
@@ -42,6 +59,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
       mp[j] = fmaf(b1, mp[j], (1.f - b1) * g);
       vp[j] = fmaf(b2, vp[j], (1.f - b2) * g * g);
       pp[j] -= step_size * (mp[j] / (sqrtf(vp[j]) * inv_sqrt_bc2 + eps));
+      if (c.wf != nullptr) emit_pack(c, 4 * i + j, pp[j]);
     }
     reinterpret_cast<float4*>(c.p)[i] = p4;
     reinterpret_cast<float4*>(c.m)[i] = m4;
@@ -53,7 +71,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
     const float v = fmaf(b2, c.v[i], (1.f - b2) * g * g);
     c.m[i] = m;
     c.v[i] = v;
-    c.p[i] -= step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+    const float pn = c.p[i] - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+    c.p[i] = pn;
+    if (c.wf != nullptr) emit_pack(c, i, pn);
   }
   __syncthreads();
   if (threadIdx.x == 0) {

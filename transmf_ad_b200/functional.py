@@ -73,14 +73,41 @@ class SNetSpec:
         self.dim = dim
 
 
+class ConvPack:
+    """bf16 operand packs of one Conv3d weight -- wf[tap][Cout][Cin] (forward) and wd[taps-1-tap][Cin][Cout] (dgrad) -- kept
+    across steps.  They are fresh while ``weight._version`` is the one they were packed from: torch in-place updates
+    (``torch.optim``, ``load_state_dict``) bump it and force a repack; ``optim.FusedAdam`` rewrites the packs from its own
+    kernel (the weight's version does not move), so a train step on FusedAdam has no pack launches at all."""
+
+    def __init__(self):
+        self.wf = self.wd = None
+        self.version, self.ptr = None, None
+
+    def stale(self, w):
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        taps = k ** 3
+        if self.wf is None or self.ptr != w.data_ptr() or self.wf.device != w.device:
+            self.wf = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
+            self.wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w.device)
+            self.version, self.ptr = None, w.data_ptr()
+        if getattr(w, "_tmf_pack_cache", None) is not self:
+            w._tmf_pack = (self.wf, self.wd, cout, cin, taps)      # optim.FusedAdam reads these
+            w._tmf_pack_cache = self
+        return self.version != w._version
+
+    def mark(self, w):
+        self.version = w._version
+
+
 class SNetRun:
     """Per-call settings of the conv stack: train / eval, whether autograd is recording (``torch.is_grad_enabled()`` at
     the call site: inside ``Function.forward`` grad mode is always off), and the hyper-parameters read from the
     ``nn.BatchNorm3d`` / ``nn.LeakyReLU`` children -- per layer (eps, momentum, negative_slope)."""
 
-    def __init__(self, training, grad_enabled, hyper=None):
+    def __init__(self, training, grad_enabled, hyper=None, packs=None):
         self.training, self.grad_enabled = bool(training), bool(grad_enabled)
         self.hyper = hyper if hyper is not None else [(BN_EPS, BN_MOMENTUM, LRELU_SLOPE)] * 7
+        self.packs = packs              # per tower: 7 ConvPack (index 0 unused: conv1.0 consumes the fp32 weight)
 
 
 def wgrad_workspace(ng, impl, B, D, H, W, cin, cout, ks, dev):
@@ -141,10 +168,19 @@ class SNetFunction(torch.autograd.Function):
                        B, Dl, Hl, Wl, cout, impl)
             else:
                 taps = ks ** 3
-                wf = [torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
-                if need_grad:
-                    wd = [torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
-                L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
+                if run.packs is not None:
+                    caches = [run.packs[t][l] for t in range(ng)]
+                    stale = [c.stale(wt) for c, wt in zip(caches, w)]
+                    wf, wd = [c.wf for c in caches], [c.wd for c in caches]
+                    if any(stale):
+                        L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
+                        for c, wt in zip(caches, w):
+                            c.mark(wt)
+                else:
+                    wf = [torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                    if need_grad:
+                        wd = [torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+                    L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs(wf), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
                        B, Dl, Hl, Wl, cin, cout, ks, impl, tag=f"tmf_conv3d_fwd@L{l}")
             coef = list(torch.empty((ng, 4 * cout), dtype=torch.float32, device=dev).unbind(0))

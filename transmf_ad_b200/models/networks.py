@@ -39,6 +39,7 @@ class sNet(nn.Module):
         self.conv3 = nn.Sequential(*_conv_unit(h, h, 3), *_conv_unit(h, dim, 3), nn.MaxPool3d(2, stride=2))
         self.conv4 = nn.Sequential(*_conv_unit(dim, dim * 2, 3), *_conv_unit(dim * 2, dim, 1), nn.AvgPool3d(2, stride=2))
         self._spec = TF.SNetSpec(dim)
+        self._packs = [TF.ConvPack() for _ in range(7)]      # cached bf16 operand packs of the conv weights
 
     def _units(self):
         """[(conv, bn)] in execution order."""
@@ -59,8 +60,22 @@ class sNet(nn.Module):
             out.append((float(bn.eps), float(bn.momentum), float(act.negative_slope)))
         return out
 
-    def _run(self):
-        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper())
+    def _run(self, other=None):
+        packs = [self._packs] if other is None else [self._packs, other._packs]
+        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs)
+
+    def pack_now(self):
+        """(Re-)pack every conv weight now, e.g. after weights were restored outside an optimizer step, so that a CUDA-graph
+        capture that follows contains no pack launches (``optim.FusedAdam`` keeps the packs fresh from then on)."""
+        from transmf_ad_b200 import _lib as L
+        for l, (conv, _) in enumerate(self._units()):
+            if l == 0 or not conv.weight.is_cuda:
+                continue
+            pk, w = self._packs[l], conv.weight
+            pk.stale(w)
+            L.call("tmf_pack_conv_weights", 1, L.ptrs([w.detach()]), L.ptrs([pk.wf]), L.ptrs([pk.wd]), w.shape[0], w.shape[1],
+                   w.shape[2])
+            pk.mark(w)
 
     def _params_and_buffers(self):
         params, bufs = [], []
@@ -81,7 +96,7 @@ def snet_pair_forward(net_a: sNet, net_b: sNet, xa, xb):
         return net_a(xa), net_b(xb)
     pa, ba = net_a._params_and_buffers()
     pb, bb = net_b._params_and_buffers()
-    return TF.SNetFunction.apply(net_a._spec, net_a._run(), [ba, bb], 2, xa, xb, *pa, *pb)
+    return TF.SNetFunction.apply(net_a._spec, net_a._run(net_b), [ba, bb], 2, xa, xb, *pa, *pb)
 
 
 def tokens_of(feat):

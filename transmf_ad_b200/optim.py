@@ -59,15 +59,26 @@ class FusedAdam(torch.optim.Optimizer):
                         st["step"].fill_(val)
                         st["seeded"] = val
                 s["step"] = st["step"]                      # one device counter shared by the group (same value for all)
+        def pack_of(p):
+            # conv weights whose bf16 operand packs are cached by the module (functional.ConvPack): the kernel refreshes them
+            pk = getattr(p, "_tmf_pack", None)
+            if pk is None or pk[0] is None or pk[0].device != p.device:
+                return (0, 0, 0, 0, 0)
+            wf, wd, cout, cin, taps = pk
+            return (wf.data_ptr(), 0 if wd is None else wd.data_ptr(), cout, cin, taps)
+
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
-                     self.state[p]["exp_avg_sq"].data_ptr(), p.numel()) for p in params)
+                     self.state[p]["exp_avg_sq"].data_ptr(), p.numel()) + pack_of(p) for p in params)
         if key != st["key"]:
             rec = int(L.load().tmf_adam_chunk_bytes())
             rows = []
-            for pp, gp, mp, vp, n in key:
+            for pp, gp, mp, vp, n, wf, wd, cout, cin, taps in key:
                 for off in range(0, n, CHUNK):
-                    rows.append((pp + 4 * off, gp + 4 * off, mp + 4 * off, vp + 4 * off, min(CHUNK, n - off), 0))
-            arr = np.array(rows, dtype=np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i4"), ("pad", "<i4")]))
+                    rows.append((pp + 4 * off, gp + 4 * off, mp + 4 * off, vp + 4 * off, wf, wd, min(CHUNK, n - off), off,
+                                 cout, cin, taps, 0))
+            arr = np.array(rows, dtype=np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("wf", "<u8"),
+                                                 ("wd", "<u8"), ("n", "<i4"), ("off", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
+                                                 ("taps", "<i4"), ("pad", "<i4")]))
             assert arr.dtype.itemsize == rec
             # pinned staging buffer + async copy: legal inside CUDA-graph capture (the captured backward hands out
             # new, then static, gradient buffers, so the table is rebuilt once while capturing)
@@ -116,4 +127,8 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             L.call("tmf_adam_step", L.ptr(st["table"]), st["n"], L.ptr(st["lr"]), float(b1), float(b2), float(group["eps"]),
                    float(group["weight_decay"]), L.ptr(st["step"]), L.ptr(st["ticket"]))
+            for p in group["params"]:                       # the kernel rewrote these parameters' packs from the new values
+                cache = getattr(p, "_tmf_pack_cache", None)
+                if cache is not None and p.grad is not None:
+                    cache.mark(p)
         return loss

@@ -113,6 +113,9 @@ class GraphedTrainStep:
                 self.optimizer.step()
             if snap is not None:
                 self._restore(snap)
+            for m in self.model.modules():                 # cached bf16 conv-weight packs follow the restored weights
+                if hasattr(m, "pack_now"):
+                    m.pack_now()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
