@@ -9,7 +9,7 @@ Tolerances.  The conv operands and the stored conv outputs are bf16 (SURVEY.md s
 reference's own numbers is measured inside the test as the distance between Oracle-A and the fp32 reference ("A:B"),
 because the BatchNorm1d heads of ``model_ad`` amplify it (measured at this size: train-mode logits A:B = 4.8e-2).
   * sNet features: <= 2e-2 rel-L2 vs Oracle-A (kernel exactness upstream of the heads; measured 6e-3);
-  * train-mode logits: vs Oracle-A <= max(3e-2, A:B), vs the fp32 reference <= max(3e-2, 1.5 * A:B); heads without
+  * train-mode logits: vs Oracle-A <= max(3e-2, A:B), vs the fp32 reference <= that + A:B (triangle inequality); heads without
     BatchNorm1d (``model_CNN_ad`` classifier): <= 2e-3;  losses <= 2e-2;  eval-mode logits <= 5e-3 (measured 7e-4);
   * gradients: whole-model cosine >= 0.95 vs Oracle-A; per tensor >= min(0.9, cos(A, fp32) - 0.05) vs Oracle-A, i.e. at least
     as aligned with Oracle-A as Oracle-A is with the fp32 reference; BatchNorm buffers <= 2e-2 relative;
@@ -47,7 +47,8 @@ def test_full_size_train_step_batch8(name):
         assert ea <= FEAT_A, f"{pfx} features vs Oracle-A: {ea}"
         assert eb <= 2 * max(ab, FEAT_A), f"{pfx} features vs fp32 reference: {eb} (Oracle-A itself: {ab})"
     ab = max(r["logit_err_A_vs_B"])                    # what bf16 operand rounding alone does to the reference's logits
-    tol_a, tol_b = max(LOGIT_TOL, ab), max(LOGIT_TOL, 1.5 * ab)
+    tol_a = max(LOGIT_TOL, ab)
+    tol_b = tol_a + ab                                 # triangle inequality through Oracle-A
     assert max(r["logit_err_A"]) <= tol_a, (r["logit_err_A"], ab)
     assert max(r["logit_err_B"]) <= tol_b, (r["logit_err_B"], ab)
     cls_tol = tol_b

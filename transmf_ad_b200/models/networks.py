@@ -64,6 +64,10 @@ class sNet(nn.Module):
         packs = [self._packs] if other is None else [self._packs, other._packs]
         return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs)
 
+    def invalidate_packs(self):
+        for pk in self._packs:
+            pk.version = None
+
     def pack_now(self):
         """(Re-)pack every conv weight now, e.g. after weights were restored outside an optimizer step, so that a CUDA-graph
         capture that follows contains no pack launches (``optim.FusedAdam`` keeps the packs fresh from then on)."""

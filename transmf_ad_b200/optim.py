@@ -17,6 +17,8 @@ CHUNK = 16384          # elements per block
 
 
 class FusedAdam(torch.optim.Optimizer):
+    emits_conv_packs = True         # the step kernel rewrites the cached bf16 conv-weight packs (functional.ConvPack)
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
         if amsgrad:
             raise ValueError("FusedAdam: amsgrad is not supported (the reference does not use it)")

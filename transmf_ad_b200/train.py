@@ -113,9 +113,16 @@ class GraphedTrainStep:
                 self.optimizer.step()
             if snap is not None:
                 self._restore(snap)
-            for m in self.model.modules():                 # cached bf16 conv-weight packs follow the restored weights
+            # Cached bf16 conv-weight packs (functional.ConvPack).  FusedAdam refreshes them inside its kernel, so they are
+            # packed once here and the captured step has no pack launches; any other optimizer updates the weights behind
+            # the cache's back during replays, so the cache is invalidated and the pack launches are captured with the forward.
+            emits = bool(getattr(self.optimizer, "emits_conv_packs", False))
+            for m in self.model.modules():
                 if hasattr(m, "pack_now"):
-                    m.pack_now()
+                    if emits:
+                        m.pack_now()
+                    else:
+                        m.invalidate_packs()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
