@@ -240,6 +240,21 @@ int tmf_token_pool_bwd(const float* dmean, const float* dmax, const int32_t* arg
  * models/gradient_reversal/functional.py:11-16 */
 int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int64_t n, void* stream);
 
+/* ---- inference (reference kfold_train_adversarial.py:144-187) ------------------------------------
+ * Eval-mode BatchNorm3d folded into the conv operands: scale = gamma*rsqrt(running_var + eps); wf (bf16
+ * [tap][Cout][Cin]; may be NULL) and / or w32 (fp32, reference layout; conv1.0) receive w*scale, bias_out receives
+ * (conv_bias - running_mean)*scale + beta.  tmf_conv3d_fwd / tmf_conv1_fwd on these operands write the post-BatchNorm
+ * value directly; tmf_bn_act_pool_fwd with identity coefficients finishes the layer (LeakyReLU + pool). */
+int tmf_fold_bn_pack(int ng, const float* const* w, const float* const* conv_bias, const float* const* gamma,
+                     const float* const* beta, const float* const* running_mean, const float* const* running_var,
+                     void* const* wf, float* const* w32, float* const* bias_out, int cout, int cin, int ksize, float eps,
+                     void* stream);
+/* val_step's metric inputs from logits[B][C]: pred (int64 arg-max, first maximum), prob_last = softmax(logits)[:, C-1]
+ * (ROC_AUC input); with labels (int64, may be NULL) and counts4 (4 x uint64, caller-zeroed, may be NULL) the confusion
+ * counts {TN, FP, FN, TP} are accumulated (C == 2). */
+int tmf_eval_head(const float* logits, const int64_t* labels, int64_t* pred, float* prob_last, void* counts4, int B, int C,
+                  void* stream);
+
 /* ---- optimizer -------------------------------------------------------------------------
  * Fused multi-tensor Adam with torch.optim.Adam arithmetic (amsgrad off): replaces the per-parameter launches of the
  * optimizer the reference builds in utils/utils.py:38-41.  `chunks` is a device array of `nchunks` records

@@ -99,15 +99,50 @@ class ConvPack:
         self.version = w._version
 
 
+# Bumped whenever parameters or BatchNorm running statistics change behind torch's version counters (FusedAdam's kernel,
+# train-mode forwards, CUDA-graph replays): the eval-mode BatchNorm folds below are rebuilt when it moves.
+_PARAM_EPOCH = [0]
+
+
+def bump_param_epoch():
+    _PARAM_EPOCH[0] += 1
+
+
+class EvalFold:
+    """Eval-mode BatchNorm3d folded into one conv layer's operands (csrc/eval_ops.cu): w*scale as the bf16 pack (or fp32 for
+    conv1.0) and b' = (b - running_mean)*scale + beta; plus the identity coefficients the LeakyReLU/pool pass then takes."""
+
+    def __init__(self):
+        self.sig = None
+        self.wf = self.w32 = self.bias = self.ident = None
+
+    def stale(self, l, tensors):
+        w = tensors[0]
+        sig = (_PARAM_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self.bias is None or self.bias.device != w.device:
+            cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+            if l == 0:
+                self.w32 = torch.empty_like(w)
+            else:
+                self.wf = torch.empty((k ** 3, cout, cin), dtype=torch.bfloat16, device=w.device)
+            self.bias = torch.empty(cout, dtype=torch.float32, device=w.device)
+            self.ident = torch.zeros(4 * cout, dtype=torch.float32, device=w.device)
+            self.ident[:cout] = 1.0
+            self.ident[3 * cout:] = 1.0
+            self.sig = None
+        return sig != self.sig, sig
+
+
 class SNetRun:
     """Per-call settings of the conv stack: train / eval, whether autograd is recording (``torch.is_grad_enabled()`` at
     the call site: inside ``Function.forward`` grad mode is always off), and the hyper-parameters read from the
     ``nn.BatchNorm3d`` / ``nn.LeakyReLU`` children -- per layer (eps, momentum, negative_slope)."""
 
-    def __init__(self, training, grad_enabled, hyper=None, packs=None):
+    def __init__(self, training, grad_enabled, hyper=None, packs=None, folds=None):
         self.training, self.grad_enabled = bool(training), bool(grad_enabled)
         self.hyper = hyper if hyper is not None else [(BN_EPS, BN_MOMENTUM, LRELU_SLOPE)] * 7
         self.packs = packs              # per tower: 7 ConvPack (index 0 unused: conv1.0 consumes the fp32 weight)
+        self.folds = folds              # per tower: 7 EvalFold (inference path: BatchNorm folded into the conv operands)
 
 
 def wgrad_workspace(ng, impl, B, D, H, W, cin, cout, ks, dev):
@@ -150,6 +185,10 @@ class SNetFunction(torch.autograd.Function):
         need_grad = run.grad_enabled and any(ctx.needs_input_grad[4 + ng:])
         impl = conv_impl()
         P = lambda t, l, k: params[(t * 7 + l) * 4 + k]
+        if not training and not need_grad and run.folds is not None and os.environ.get("TMF_EVAL_FOLD", "1") != "0":
+            return SNetFunction._eval_forward(ctx, spec, run, buffers, ng, xs, P, impl)
+        if training:
+            bump_param_epoch()                              # running statistics are about to change
         saved = []
         act = xs
         dims = (D, H, W)
@@ -211,6 +250,46 @@ class SNetFunction(torch.autograd.Function):
         ctx.params = params if need_grad else None          # references only (gradient slots of the flat DP buffer)
         ctx.impl = impl
         outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)      # logical (B,C,d,h,w), channels-last memory
+        return outs if ng > 1 else outs[0]
+
+    @staticmethod
+    def _eval_forward(ctx, spec, run, buffers, ng, xs, P, impl):
+        """Inference (val_step, reference kfold_train_adversarial.py:144-161): no statistics, no saved activations; the
+        BatchNorm of every layer is folded into the conv operands once per weight / running-statistics state."""
+        B, _, D, H, W = xs[0].shape
+        dev = xs[0].device
+        act, dims = xs, (D, H, W)
+        for l, (cin, cout, ks, pool) in enumerate(spec.layers):
+            Dl, Hl, Wl = dims
+            bn_eps, _, slope = run.hyper[l]
+            folds = [run.folds[t][l] for t in range(ng)]
+            state = [fo.stale(l, [P(t, l, 0), P(t, l, 1), P(t, l, 2), P(t, l, 3), buffers[t][l][0], buffers[t][l][1]])
+                     for t, fo in enumerate(folds)]
+            if any(st for st, _ in state):
+                L.call("tmf_fold_bn_pack", ng, L.ptrs([P(t, l, 0) for t in range(ng)]), L.ptrs([P(t, l, 1) for t in range(ng)]),
+                       L.ptrs([P(t, l, 2) for t in range(ng)]), L.ptrs([P(t, l, 3) for t in range(ng)]),
+                       L.ptrs([buffers[t][l][0] for t in range(ng)]), L.ptrs([buffers[t][l][1] for t in range(ng)]),
+                       L.ptrs([fo.wf for fo in folds]), L.ptrs([fo.w32 for fo in folds]), L.ptrs([fo.bias for fo in folds]),
+                       cout, cin, ks, float(bn_eps))
+                for fo, (_, sig) in zip(folds, state):
+                    fo.sig = sig
+            y = [torch.empty((B, Dl, Hl, Wl, cout), dtype=torch.bfloat16, device=dev) for _ in range(ng)]
+            bias = [fo.bias for fo in folds]
+            if l == 0:
+                L.call("tmf_conv1_fwd", ng, L.ptrs(act), L.ptrs([fo.w32 for fo in folds]), L.ptrs(bias), L.ptrs(y), L.ptrs(None),
+                       B, Dl, Hl, Wl, cout, impl)
+            else:
+                L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs([fo.wf for fo in folds]), L.ptrs(bias), L.ptrs(y), L.ptrs(None),
+                       B, Dl, Hl, Wl, cin, cout, ks, impl, tag=f"tmf_conv3d_fwd@L{l}")
+            last = l == len(spec.layers) - 1
+            Do, Ho, Wo = _pooled(Dl, Hl, Wl, pool)
+            out = [torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if last else torch.bfloat16, device=dev)
+                   for _ in range(ng)]
+            L.call("tmf_bn_act_pool_fwd", ng, L.ptrs(y), L.ptrs([fo.ident for fo in folds]), L.ptrs(out), int(last), B, Dl, Hl,
+                   Wl, cout, pool, slope, tag=f"tmf_bn_act_pool_fwd@L{l}")
+            act, dims = out, (Do, Ho, Wo)
+        ctx.saved = None
+        outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)
         return outs if ng > 1 else outs[0]
 
     @staticmethod

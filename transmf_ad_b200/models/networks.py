@@ -40,6 +40,7 @@ class sNet(nn.Module):
         self.conv4 = nn.Sequential(*_conv_unit(dim, dim * 2, 3), *_conv_unit(dim * 2, dim, 1), nn.AvgPool3d(2, stride=2))
         self._spec = TF.SNetSpec(dim)
         self._packs = [TF.ConvPack() for _ in range(7)]      # cached bf16 operand packs of the conv weights
+        self._folds = [TF.EvalFold() for _ in range(7)]      # eval mode: BatchNorm folded into the conv operands
 
     def _units(self):
         """[(conv, bn)] in execution order."""
@@ -62,7 +63,8 @@ class sNet(nn.Module):
 
     def _run(self, other=None):
         packs = [self._packs] if other is None else [self._packs, other._packs]
-        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs)
+        folds = [self._folds] if other is None else [self._folds, other._folds]
+        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs, folds)
 
     def invalidate_packs(self):
         for pk in self._packs:

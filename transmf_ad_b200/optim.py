@@ -129,6 +129,8 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             L.call("tmf_adam_step", L.ptr(st["table"]), st["n"], L.ptr(st["lr"]), float(b1), float(b2), float(group["eps"]),
                    float(group["weight_decay"]), L.ptr(st["step"]), L.ptr(st["ticket"]))
+            from . import functional as TF
+            TF.bump_param_epoch()                           # parameters changed behind torch's version counters
             for p in group["params"]:                       # the kernel rewrote these parameters' packs from the new values
                 cache = getattr(p, "_tmf_pack_cache", None)
                 if cache is not None and p.grad is not None:

@@ -154,6 +154,8 @@ class GraphedTrainStep:
         refresh = getattr(self.optimizer, "refresh_hyperparams", None)
         if refresh is not None:
             refresh()                                      # e.g. FusedAdam: a scheduler-changed lr reaches the device scalar
+        from . import functional as TF
+        TF.bump_param_epoch()                              # replays change parameters / running statistics without Python
         self.graph_fb.replay()
         if self.split:
             self.reducer.finish()
