@@ -255,6 +255,16 @@ int tmf_fold_bn_pack(int ng, const float* const* w, const float* const* conv_bia
 int tmf_eval_head(const float* logits, const int64_t* labels, int64_t* pred, float* prob_last, void* counts4, int B, int C,
                   void* stream);
 
+/* ---- input pipeline on the device (reference datasets/ADNI.py:59-84) -------------------------------------
+ * minmax[2*v] / [2*v+1] = min / max of volume v (ScaleIntensityd, :64). */
+int tmf_volume_minmax(const float* x, float* minmax, int nvol, int64_t voxels, void* stream);
+/* dst = scale_to_01( resample(src) ): per-volume min-max scaling fused with ONE trilinear, border-clamped affine
+ * resampling that composes RandFlipd(axis 0), RandRotated(range_x) and RandZoomd (:66-68).  params[s] = {flip, cos(theta),
+ * sin(theta), 1/zoom} per SUBJECT; consecutive groups of `vols_per_subject` volumes (MRI, PET) share a record.  Identity
+ * parameters {0,1,0,1} reproduce the test-time transform (scaling only) exactly. */
+int tmf_augment_volumes(const float* src, float* dst, const float* minmax, const float* params, int nvol,
+                        int vols_per_subject, int D, int H, int W, void* stream);
+
 /* ---- optimizer -------------------------------------------------------------------------
  * Fused multi-tensor Adam with torch.optim.Adam arithmetic (amsgrad off): replaces the per-parameter launches of the
  * optimizer the reference builds in utils/utils.py:38-41.  `chunks` is a device array of `nchunks` records

@@ -49,6 +49,8 @@ SIGNATURES = {
     "tmf_encoder_wgrad": [_pp, _vp, _vp, _vp, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_fold_bn_pack": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _f, _vp],
     "tmf_eval_head": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "tmf_volume_minmax": [_vp, _vp, _i, _i64, _vp],
+    "tmf_augment_volumes": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "tmf_token_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tmf_token_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],

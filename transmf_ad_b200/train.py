@@ -169,9 +169,12 @@ class DevicePrefetcher:
     valid until the next ``next()`` call has returned, and everything that reads it must have been enqueued on the
     current stream by then (single-threaded use)."""
 
-    def __init__(self, host_batches, device, reuse=None):
+    def __init__(self, host_batches, device, reuse=None, transform=None):
         """``reuse``: an exhausted prefetcher of the same batch shapes whose side stream and device buffers are taken over
-        (one per epoch: no cudaMalloc / stream creation after the first)."""
+        (one per epoch: no cudaMalloc / stream creation after the first).  ``transform``: a callable applied to the device
+        batch ON THE COPY STREAM right after the copy (e.g. ``data.GpuBatchTransform``: scaling + augmentation), so that
+        it overlaps the previous step like the copy itself; it must return the tuple the consumer gets."""
+        self.transform = transform
         self.it = iter(host_batches)
         self.device = torch.device(device)
         if reuse is not None:
@@ -202,8 +205,9 @@ class DevicePrefetcher:
             self.stream.wait_event(self.consumed[k])        # no-op until the slot has been handed out once
             for d, h in zip(self.slots[k], hb):
                 d.copy_(h, non_blocking=True)
+            out = self.slots[k] if self.transform is None else tuple(self.transform(self.slots[k]))
             ready = self.stream.record_event()
-        self._next = (k, ready)
+        self._next = (k, ready, out)
 
     def __iter__(self):
         return self
@@ -214,10 +218,12 @@ class DevicePrefetcher:
             self.consumed[self._last].record(cur)
         if self._next is None:
             raise StopIteration
-        k, ready = self._next
+        k, ready, batch = self._next
         cur.wait_event(ready)
         self._last = k
-        batch = self.slots[k]
+        for t in batch:                                     # transform outputs were allocated on the copy stream
+            if torch.is_tensor(t):
+                t.record_stream(cur)
         self._preload()                                     # batch i+1: H2D overlaps with the caller's work on batch i
         return batch
 
