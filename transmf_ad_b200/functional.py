@@ -492,6 +492,28 @@ def attention_core(q, kv, heads, scale):
     return AttentionCoreFunction.apply(q, kv, heads, scale)
 
 
+# Side stream for work that is off the backward pass's critical path (the encoders' weight gradients): launched there, it
+# overlaps the next encoder's dgrad chain; the launching stream waits for it when autograd finishes the backward pass
+# (engine callback), i.e. before anything can consume the gradients.  Under CUDA-graph capture this becomes a parallel branch.
+_SIDE = {}
+_SIDE_PENDING = []
+
+
+def _side_stream(device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    st = _SIDE.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE[key] = st
+    return st
+
+
+def join_side_streams():
+    """Make the current stream wait for everything launched on the side stream (idempotent)."""
+    while _SIDE_PENDING:
+        torch.cuda.current_stream().wait_event(_SIDE_PENDING.pop())
+
+
 class EncoderFunction(torch.autograd.Function):
     """One ``Transformer(depth=1)`` encoder (reference models/networks.py:215-230) with cross-attention context, as three
     forward and five backward launches (csrc/enc_fused.cu + the attention core):
@@ -549,7 +571,23 @@ class EncoderFunction(torch.autograd.Function):
         L.call("tmf_encoder_proj_bwd", L.ptr(dq), L.ptr(dkv), L.ptr(dxp), L.ptr(x3), L.ptr(ln1_w), L.ptr(mean1), L.ptr(rstd1),
                L.ptr(wq), L.ptr(wkv), L.ptr(dx), L.ptr(dctx), L.ptr(d_ln1_w), L.ptr(d_ln1_b), Mx, Mc, L.ptr(ws), nws)
         table = (ctypes_ptr_array([dq, h1, d_wq, dkv, c3, d_wkv, da, o, d_wo, d_bo, dp, h2, d_w1, d_b1, dg]))
-        L.call("tmf_encoder_wgrad", table, L.ptr(f), L.ptr(d_w2), L.ptr(d_b2), Mx, Mc, mlp, L.ptr(ws), nws)
+        if os.environ.get("TMF_ENC_SIDE", "1") != "0":
+            # all five weight gradients feed nothing downstream in this backward pass: off the critical path
+            cur = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ws2, nws2 = L.scratch(dev)                   # the side stream's own scratch buffer
+                L.call("tmf_encoder_wgrad", table, L.ptr(f), L.ptr(d_w2), L.ptr(d_b2), Mx, Mc, mlp, L.ptr(ws2), nws2)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            for t in (dq, h1, dkv, c3, da, o, dp, h2, dg, f, d_wq, d_wkv, d_wo, d_bo, d_w1, d_b1, d_w2, d_b2):
+                t.record_stream(side)
+            if not _SIDE_PENDING:
+                torch.autograd.Variable._execution_engine.queue_callback(join_side_streams)
+            _SIDE_PENDING.append(ev)
+        else:
+            L.call("tmf_encoder_wgrad", table, L.ptr(f), L.ptr(d_w2), L.ptr(d_b2), Mx, Mc, mlp, L.ptr(ws), nws)
         return (dx.reshape(x3.shape), dctx.reshape(c3.shape), None, None, None, None, None, None,
                 d_ln1_w, d_ln1_b, d_wq, d_wkv, d_wo, d_bo, d_ln2_w, d_ln2_b, d_w1, d_b1, d_w2, d_b2, d_lnf_w, d_lnf_b)
 
