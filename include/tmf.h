@@ -265,6 +265,35 @@ int tmf_volume_minmax(const float* x, float* minmax, int nvol, int64_t voxels, v
 int tmf_augment_volumes(const float* src, float* dst, const float* minmax, const float* params, int nvol,
                         int vols_per_subject, int D, int H, int W, void* stream);
 
+/* ---- MiSePyNet / Mnet baseline (reference models/MiSePyNet.py:5-163), fp32 NCDHW-contiguous tensors ------
+ * slice convolutions Conv3d(Cin, 8, (1,1,k)) along the last axis (:8,13,16,21,24,27): x [N][Cin][P][L] (P = product of the two
+ * leading spatial extents), w [8][Cin][k], y [N][8][P][L-k+1]; Cin <= 8. */
+int tmf_line_conv_fwd(const float* x, const float* w, const float* b, float* y, int N, int Cin, int64_t P, int L, int k, void* stream);
+int tmf_line_conv_dgrad(const float* dy, const float* w, float* dx, int N, int Cin, int64_t P, int L, int k, void* stream);
+/* dw [8][Cin][k], db [8] (may be NULL), both overwritten; ws: caller scratch of tmf_line_conv_wgrad_workspace_bytes (per-block
+ * partials, added in block order: deterministic) */
+int tmf_line_conv_wgrad(const float* dy, const float* x, float* dw, float* db, int N, int Cin, int64_t P, int L, int k, void* ws,
+                        size_t ws_bytes, void* stream);
+int64_t tmf_line_conv_wgrad_workspace_bytes(int Cin, int k);
+/* spatial convolutions Conv3d(Cin, Cout, (kh,kw,1), stride) on (N,C,X,Y,1) tensors (:44,48,52), no padding:
+ * x [N][Cin][X][Y], w [Cout][Cin][kh][kw], y [N][Cout][(X-kh)/s+1][(Y-kw)/s+1] */
+int tmf_conv2d_fwd(const float* x, const float* w, const float* b, float* y, int N, int Cin, int X, int Y, int Cout, int kh, int kw,
+                   int stride, void* stream);
+int tmf_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int Cin, int X, int Y, int Cout, int kh, int kw, int stride,
+                     void* stream);
+int tmf_conv2d_wgrad(const float* dy, const float* x, float* dw, float* db, int N, int Cin, int X, int Y, int Cout, int kh, int kw,
+                     int stride, void* stream);
+/* BatchNorm3d + ReLU on [N][C][S] fp32 (:9-10 ...): statistics / backward sums as partial rows double[TMF_STAT_ROWS][2C] for
+ * tmf_bn_finalize / tmf_bn_bwd_finalize (same coef / bcoef conventions as the sNet path; ReLU = LeakyReLU with slope 0) */
+int tmf_nchw_bn_stats(const float* x, double* rows, int N, int C, int64_t S, void* stream);
+int tmf_nchw_bn_relu_fwd(const float* x, const float* coef, float* out, int N, int C, int64_t S, void* stream);
+int tmf_nchw_bn_relu_bwd_reduce(const float* dout, const float* x, const float* coef, double* rows, int N, int C, int64_t S, void* stream);
+int tmf_nchw_bn_relu_bwd_apply(const float* dout, const float* x, const float* coef, const float* bcoef, float* dx, int N, int C,
+                               int64_t S, void* stream);
+/* MaxPool3d((ph,pw,1)), stride = kernel, floor mode (:47,51): x [NC][X][Y] -> y [NC][X/ph][Y/pw], idx uint8 (first maximum) */
+int tmf_maxpool2d_fwd(const float* x, float* y, void* idx, int64_t NC, int X, int Y, int ph, int pw, void* stream);
+int tmf_maxpool2d_bwd(const float* dy, const void* idx, float* dx, int64_t NC, int X, int Y, int ph, int pw, void* stream);
+
 /* ---- optimizer -------------------------------------------------------------------------
  * Fused multi-tensor Adam with torch.optim.Adam arithmetic (amsgrad off): replaces the per-parameter launches of the
  * optimizer the reference builds in utils/utils.py:38-41.  `chunks` is a device array of `nchunks` records

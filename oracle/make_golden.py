@@ -46,6 +46,8 @@ CASES = {
     "model_ad_full_b8": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 8, (91, 109, 91), 14),   # seed scanned: every train-mode margin > 0.3
     "model_cnn_ad_full_b8": ("model_CNN_ad", dict(dim=128), 8, (91, 109, 91), 9),
     "model_ad_full_b2": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 2, (91, 109, 91), 10),
+    # BASELINE configs[4]: the MiSePyNet baseline (reference models/MiSePyNet.py; its slice convolutions hard-code 91x109x91)
+    "mnet_b4": ("Mnet", dict(), 4, (91, 109, 91), 11),
 }
 GRAD_SAMPLE = 48
 
@@ -70,6 +72,8 @@ def oracle_forward(kind, sd, inputs, kwargs, training, p_drop):
         return (R.model_transformer_forward(sd, *inputs, heads=heads, training=training, p_drop=p_drop),)
     if kind == "model_transformer_res":
         return (R.model_transformer_res_forward(sd, *inputs, heads=heads, training=training, p_drop=p_drop),)
+    if kind == "Mnet":
+        return (R.mnet_forward(sd, *inputs, training=training, p_drop=p_drop),)
     raise KeyError(kind)
 
 
@@ -92,7 +96,11 @@ def set_dropout(module, p):
 
 def run_case(name, refmods, outdir):
     kind, kwargs, B, shape, wseed = CASES[name]
-    ref = getattr(refmods, kind)(**kwargs)
+    if kind == "Mnet":
+        import models.MiSePyNet as mise           # the real reference baseline
+        ref = mise.Mnet()
+    else:
+        ref = getattr(refmods, kind)(**kwargs)
     state = procedural_state(ref.state_dict(), seed=wseed)
     ref.load_state_dict(state)
     label = make_labels(B)
@@ -124,6 +132,9 @@ def run_case(name, refmods, outdir):
         assert torch.equal(total, o_total)
         ref_sd = ref.state_dict()
         for k, p in ref.named_parameters():
+            if p.grad is None:                # dead parameters (Mnet: spatial_cnn.conv2 / conv3 are never called, MiSePyNet.py:89-94)
+                assert sd[k].grad is None, k
+                continue
             assert sd[k].grad is not None, k
             assert torch.equal(p.grad, sd[k].grad), f"{name}/{tag}: grad {k} differs"
         for k, v in ref_sd.items():
@@ -132,8 +143,8 @@ def run_case(name, refmods, outdir):
     # (the p=0 results are what we store)
     gold["train_outs"] = [o.detach().clone() for o in outs]
     gold["train_losses"] = (float(ce), float(ad), float(total))
-    gold["grad_norm"] = {k: float(p.grad.norm()) for k, p in ref.named_parameters()}
-    gold["grad_sample"] = {k: sample(p.grad) for k, p in ref.named_parameters()}
+    gold["grad_norm"] = {k: float(p.grad.norm()) for k, p in ref.named_parameters() if p.grad is not None}
+    gold["grad_sample"] = {k: sample(p.grad) for k, p in ref.named_parameters() if p.grad is not None}
     gold["buffers_after"] = {k: v.clone() for k, v in ref.state_dict().items()
                              if "running" in k or "num_batches" in k}
     # ---- (B) eval-mode forward with the post-step buffers (val_step, kfold_train_adversarial.py:144-161) ----

@@ -267,6 +267,49 @@ def model_transformer_res_forward(sd, mri, pet, heads=4, training=True, rnd=None
 
 
 # --------------------------------------------------------------------------------------------------------------
+# MiSePyNet / Mnet baseline (reference models/MiSePyNet.py:5-163), pure fp32
+# --------------------------------------------------------------------------------------------------------------
+def _conv_bn_relu(sd, pfx, ci, x, training, stride=1):
+    y = F.conv3d(x, sd[f"{pfx}.{ci}.weight"], sd[f"{pfx}.{ci}.bias"], stride=stride)
+    return F.relu(batchnorm(sd, f"{pfx}.{ci + 1}", y, training))
+
+
+def slice_cnn_forward(sd, pfx, img, training):
+    """reference MiSePyNet.py:32-38: three stacks of (1,1,k) convolutions that collapse the last axis."""
+    c1 = _conv_bn_relu(sd, pfx + ".conv1", 0, img, training)
+    c2 = _conv_bn_relu(sd, pfx + ".conv2", 3, _conv_bn_relu(sd, pfx + ".conv2", 0, img, training), training)
+    c3 = _conv_bn_relu(sd, pfx + ".conv3", 0, img, training)
+    c3 = _conv_bn_relu(sd, pfx + ".conv3", 6, _conv_bn_relu(sd, pfx + ".conv3", 3, c3, training), training)
+    return c1, c2, c3
+
+
+def spatial_cnn_forward(sd, pfx, s1, s2, s3, training):
+    """reference MiSePyNet.py:89-94: ``self.conv1`` is applied to ALL three inputs (conv2 / conv3 are dead weights)."""
+    def conv1(x):
+        x = F.max_pool3d(_conv_bn_relu(sd, pfx + ".conv1", 0, x, training, stride=2), (3, 3, 1))
+        x = F.max_pool3d(_conv_bn_relu(sd, pfx + ".conv1", 4, x, training), (3, 3, 1))
+        return _conv_bn_relu(sd, pfx + ".conv1", 8, x, training)
+    return conv1(s1) + conv1(s2) + conv1(s3)
+
+
+def misepynet_forward(sd, pfx, img, training):
+    """reference MiSePyNet.py:117-136."""
+    B = img.shape[0]
+    views = (("axial", img), ("col", img.permute(0, 1, 2, 4, 3)), ("sag", img.permute(0, 1, 4, 3, 2)))
+    feats = []
+    for name, v in views:
+        s = slice_cnn_forward(sd, f"{pfx}.slice_cnn_{name}", v, training)
+        feats.append(spatial_cnn_forward(sd, f"{pfx}.spatial_cnn_{name}", *s, training).reshape(B, -1))
+    return torch.cat(feats, dim=1)
+
+
+def mnet_forward(sd, mri, pet, training=True, p_drop=0.5):
+    """reference MiSePyNet.py:155-163; fc = Linear BN1d ReLU Dropout Linear BN1d ReLU Dropout Linear (:144-153)."""
+    c = torch.cat([misepynet_forward(sd, "mri", mri, training), misepynet_forward(sd, "pet", pet, training)], dim=-1)
+    return fc_cls_transformer(sd, "fc", c, training, p_drop)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # Training step of the caller (reference kfold_train_adversarial.py:101-136, kfold_train_single.py:91-113)
 # --------------------------------------------------------------------------------------------------------------
 def adversarial_losses(logits, d_mri, d_pet, label):

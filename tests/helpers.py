@@ -57,6 +57,8 @@ def oracle_forward(kind, sd, inputs, kwargs, training, p_drop=0.0, rnd=None):
         return (R.model_transformer_forward(sd, *inputs, heads=heads, training=training, p_drop=p_drop, rnd=rnd),)
     if kind == "model_transformer_res":
         return (R.model_transformer_res_forward(sd, *inputs, heads=heads, training=training, p_drop=p_drop, rnd=rnd),)
+    if kind == "Mnet":
+        return (R.mnet_forward(sd, *inputs, training=training, p_drop=p_drop),)
     raise KeyError(kind)
 
 

@@ -9,7 +9,8 @@ from tests import helpers as H
 
 CASES = ["model_ad_h4", "model_ad_h8", "model_cnn_ad", "model_single", "model_transformer", "model_transformer_res",
          "model_cnn", "model_ad_dim64",
-         "model_ad_full_b2"]         # BASELINE configs[0]: model_ad, batch 2, 91x109x91, fwd+bwd on CPU
+         "model_ad_full_b2",         # BASELINE configs[0]: model_ad, batch 2, 91x109x91, fwd+bwd on CPU
+         "mnet_b4"]                  # BASELINE configs[4]: the MiSePyNet baseline
 TOL = 2e-4      # other host CPUs may pick different oneDNN/MKL kernels than the container that wrote the fixtures
 
 

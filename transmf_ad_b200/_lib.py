@@ -51,6 +51,18 @@ SIGNATURES = {
     "tmf_eval_head": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "tmf_volume_minmax": [_vp, _vp, _i, _i64, _vp],
     "tmf_augment_volumes": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "tmf_line_conv_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp],
+    "tmf_line_conv_dgrad": [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp],
+    "tmf_line_conv_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp, C.c_size_t, _vp],
+    "tmf_conv2d_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv2d_dgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_conv2d_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tmf_nchw_bn_stats": [_vp, _vp, _i, _i, _i64, _vp],
+    "tmf_nchw_bn_relu_fwd": [_vp, _vp, _vp, _i, _i, _i64, _vp],
+    "tmf_nchw_bn_relu_bwd_reduce": [_vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "tmf_nchw_bn_relu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "tmf_maxpool2d_fwd": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "tmf_maxpool2d_bwd": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "tmf_token_pool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "tmf_token_pool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
@@ -60,7 +72,7 @@ PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
          "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),
-         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_conv1_wgrad_workspace_bytes": (_i64, [_i] * 4), "tmf_adam_chunk_bytes": (_i, [])}
+         "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_conv1_wgrad_workspace_bytes": (_i64, [_i] * 4), "tmf_line_conv_wgrad_workspace_bytes": (_i64, [_i, _i]), "tmf_adam_chunk_bytes": (_i, [])}
 
 _lib = None
 _device_checked = False
