@@ -54,6 +54,8 @@ WORKLOADS = {
     "ad": ("model_ad", dict(dim=128, depth=3, heads=4, dim_head=32, mlp_dim=512, dropout=0.), 2,
            "model_ad (--model Transformer) adversarial train step"),
     "single": ("model_single", dict(dim=128), 1, "model_single (kfold_train_single) train step"),
+    # BASELINE configs[4] (MiSePyNet baseline, kfold_train_Mnet.py:85: SGD lr 1e-3 momentum 0.9, CE loss); not the headline
+    "mnet": ("Mnet", dict(), 2, "Mnet / MiSePyNet baseline (kfold_train_Mnet.py) train step"),
 }
 CPU_SAMPLE_BATCH = 2      # BASELINE configs[0] / the reference's default --batch_size
 
@@ -325,11 +327,17 @@ def measure(job, workload, B, steps, warmup, mode="graph", optimizer="fused", wa
     from transmf_ad_b200.synthetic import make_labels, make_volumes, procedural_state
     rank, world, dev = job.rank, job.world, job.dev
     kind, kwargs, towers, desc = WORKLOADS[workload]
-    model = getattr(M, kind)(**kwargs)
+    if kind == "Mnet":
+        from transmf_ad_b200.models.MiSePyNet import Mnet
+        model = Mnet()
+    else:
+        model = getattr(M, kind)(**kwargs)
     model.load_state_dict(procedural_state(model.state_dict(), seed=0))     # identical replicas on every rank
     model = model.to(dev).train()
     graph_mode = mode == "graph"
-    if optimizer == "fused":                                                 # utils/utils.py:38-41 (Adam branch), one launch
+    if kind == "Mnet":                                                       # kfold_train_Mnet.py:85
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    elif optimizer == "fused":                                                 # utils/utils.py:38-41 (Adam branch), one launch
         from transmf_ad_b200.optim import FusedAdam
         opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=0.0)
     else:
@@ -503,7 +511,7 @@ def measure(job, workload, B, steps, warmup, mode="graph", optimizer="fused", wa
         conv1_tags = ("tmf_conv1_fwd", "tmf_conv1_wgrad", "tmf_conv1_bwd_fused")
         gemm_ms = sum(v[0] for t, v in rec.items() if t.split("@")[0] in gemm_tags) / nprof
         conv1_ms = sum(v[0] for t, v in rec.items() if t.split("@")[0] in conv1_tags) / nprof
-        flops = conv_flops_per_subject(SHAPE, kwargs["dim"], towers, first_layer=False) * B
+        flops = 0.0 if "dim" not in kwargs else conv_flops_per_subject(SHAPE, kwargs["dim"], towers, first_layer=False) * B
         flops_all = conv_flops_per_subject(SHAPE, kwargs["dim"], towers) * B
         achieved = flops / (gemm_ms * 1e-3) / 1e12
         achieved_all = flops_all / ((gemm_ms + conv1_ms) * 1e-3) / 1e12
@@ -568,7 +576,7 @@ def main():
     B = args.batch
     head_name = "ad" if args.workload == "both" else args.workload
     head = measure(job, head_name, B, args.steps, args.warmup, args.mode, args.optimizer, want_e2e=True,
-                   want_roofline=not args.no_roofline, sample_clocks=True,
+                   want_roofline=(not args.no_roofline) and head_name != "mnet", sample_clocks=True,
                    sustained_steps=(args.sustained_steps if (world == 1 and not args.no_extras and args.mode == "graph") else 0))
     others = {}
     if args.workload == "both":

@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(256) line_conv_wgrad_kernel(const float* __res
   float* sdy = sm;                          // [8][Lo]
   float* sx = sm + LC_CO * Lo;              // [Cin][L]
   const int nw = LC_CO * Cin * k;
-  const int per = (nw + blockDim.x - 1) / blockDim.x;        // weights per thread (<= 12 for 8*8*46 / 256)
-  float acc[12];
+  const int per = (nw + blockDim.x - 1) / blockDim.x;        // weights per thread (<= 16: 8*8*55 = 3520 weights for slice_cnn(109))
+  float acc[16];
   float accb = 0.f;
 #pragma unroll
-  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   const int64_t lines = (int64_t)N * P;
   for (int64_t line = blockIdx.x; line < lines; line += gridDim.x) {
     const int n = (int)(line / P);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) line_conv_wgrad_kernel(const float* __res
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
+    for (int j = 0; j < 16; ++j) {
       const int wi = threadIdx.x + j * blockDim.x;
       if (j < per && wi < nw) {
         const int t = wi % k, ci = (wi / k) % Cin, co = wi / (k * Cin);
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) line_conv_wgrad_kernel(const float* __res
   }
   float* out = part + (size_t)blockIdx.x * (nw + LC_CO);
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
+  for (int j = 0; j < 16; ++j) {
     const int wi = threadIdx.x + j * blockDim.x;
     if (j < per && wi < nw) out[wi] = acc[j];
   }
@@ -374,7 +374,7 @@ int64_t tmf_line_conv_wgrad_workspace_bytes(int Cin, int k) { return (int64_t)si
 int tmf_line_conv_wgrad(const float* dy, const float* x, float* dw, float* db, int N, int Cin, int64_t P, int L, int k, void* ws,
                         size_t ws_bytes, void* stream) {
   TMF_REQUIRE(dy && x && dw && N > 0 && Cin >= 1 && Cin <= 8 && P > 0 && k >= 1 && k <= L, "line_conv_wgrad: bad arguments");
-  TMF_REQUIRE(LC_CO * Cin * k <= 12 * 256, "line_conv_wgrad: too many weights per output channel block");
+  TMF_REQUIRE(LC_CO * Cin * k <= 16 * 256, "line_conv_wgrad: too many weights per output channel block");
   TMF_REQUIRE(ws != nullptr && (int64_t)ws_bytes >= tmf_line_conv_wgrad_workspace_bytes(Cin, k), "line_conv_wgrad: workspace too small");
   const int64_t lines = (int64_t)N * P;
   const int nb = (int)(lines < 592 ? lines : 592);

@@ -96,14 +96,14 @@ def conv_bn_relu(x, conv, bn, training):
         raise NotImplementedError("Mnet on the B200 kernels needs biased convs and affine BatchNorm3d with running statistics")
     if any(p != 0 for p in conv.padding) or any(d != 1 for d in conv.dilation) or conv.groups != 1:
         raise NotImplementedError("Mnet conv kernels take unpadded, undilated, ungrouped convolutions (what the reference uses)")
-    if kd == 1 and kh == 1:
-        if conv.stride != (1, 1, 1) or conv.out_channels != 8 or conv.in_channels > 8:
-            raise NotImplementedError("slice convolution must be Conv3d(<=8, 8, (1,1,k)), stride 1")
-        cfg = ("line", kw, 1, bool(training), bn.eps, bn.momentum)
-    elif kw == 1:
+    if kw == 1:                                            # (kh,kw,1) spatial convolution, incl. the 1x1x1 one
         if x.shape[-1] != 1 or len(set(conv.stride)) != 1:
             raise NotImplementedError("spatial convolution expects a unit last axis and an isotropic stride")
         cfg = ("2d", (kd, kh), conv.stride[0], bool(training), bn.eps, bn.momentum)
+    elif kd == 1 and kh == 1:
+        if conv.stride != (1, 1, 1) or conv.out_channels != 8 or conv.in_channels > 8:
+            raise NotImplementedError("slice convolution must be Conv3d(<=8, 8, (1,1,k)), stride 1")
+        cfg = ("line", kw, 1, bool(training), bn.eps, bn.momentum)
     else:
         raise NotImplementedError(f"unsupported Mnet kernel size {conv.kernel_size}")
     return ConvBNReLUFunction.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
