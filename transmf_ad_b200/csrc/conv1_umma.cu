@@ -17,13 +17,8 @@ using namespace umma;
 
 constexpr int C1U_PRODUCERS = 128;                 // one im2col row (voxel) per thread; two producer groups (warps 0-3,
                                                    // 4-7) alternate tiles so global-load latency of one hides behind the other
-constexpr int C1U_THREADS = 512;                   // + warps 8-11 / 12-15: two epilogue groups alternating tiles; the first warp
-                                                   // of each group also issues the MMAs of its group's tiles (round 1 had ONE
-                                                   // epilogue group + an issuer warp: the per-tile chain accumulator -> TMEM load ->
-                                                   // pack -> stores -> statistics of a single group bounded the kernel at ~790
-                                                   // cycles per tile; a 17th warp does not fit the register file)
+constexpr int C1U_THREADS = 416;                   // + warp 8: MMA issuer / TMEM owner, warps 9-12: epilogue
 constexpr int C1U_STAGES = 4;
-constexpr int C1U_ACC = 4;                         // TMEM accumulator buffers: tile it uses buffer it & 3 (group it & 1)
 constexpr uint32_t C1U_TILE_BYTES = 128 * 64;      // one [128 x 32] bf16 operand tile
 
 struct C1UParams {
@@ -58,9 +53,9 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   const uint32_t smA = smem_base;
   const uint32_t smW = smA + C1U_STAGES * 2 * C1U_TILE_BYTES;
   const uint32_t bars = smW + 2 * 4096;
-  const uint32_t full = bars, empty = bars + 8 * C1U_STAGES, acc_full = empty + 8 * C1U_STAGES, acc_empty = acc_full + 8 * C1U_ACC;
-  const uint32_t tmem_slot = acc_empty + 8 * C1U_ACC;
-  float* stats_ptr = reinterpret_cast<float*>(gen + (tmem_slot + 16 - smem_base));        // float [8 warps][2][64]
+  const uint32_t full = bars, empty = bars + 8 * C1U_STAGES, acc_full = empty + 8 * C1U_STAGES, acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  float* stats_ptr = reinterpret_cast<float*>(gen + (tmem_slot + 16 - smem_base));        // float [4 warps][2][64]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +64,7 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C1U_STAGES; ++i) { mbar_init(full + 8 * i, C1U_PRODUCERS); mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < C1U_ACC; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     fence_barrier_init();
   }
   // weights: fp32 (Cout,27) -> bf16 hi / lo tiles, K-major rows of 32 taps (taps 27..31 zero)
@@ -174,40 +169,21 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
       mbar_arrive(full + 8 * s);
     }
-  } else {
-    // ======================================= epilogue (+ MMA issue) =================================
-    // Two groups of four warps; group eg takes the tiles it = eg, eg + 2, ... of this CTA (accumulator buffer it & 3,
-    // im2col stage it % 4: both always belong to the same group, so every barrier is waited on by threads that saw all
-    // of its earlier phases).  The group's first warp issues the MMAs of the group's tiles up to two tiles ahead:
-    // opportunistically (non-blocking barrier tests) before and after draining the current accumulator, blocking only
-    // for the tile it is about to consume.
-    // Per tile and thread (= one voxel row): TMEM -> 32 fp32 -> packed bf16 (cvt.rn.bf16x2) -> 16-byte stores; the
-    // BatchNorm sums of the STORED values accumulate in per-thread registers over the whole tile range and are
-    // reduced across lanes / warps once, at the end.  Bias is already in the accumulator (K column 27).
-    const int eg = (warp - 8) >> 2;
-    const bool lead = ((warp - 8) & 3) == 0;
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    __nv_bfloat16* yg = p.y[g];
-    const bool want_stats = p.stats[g] != nullptr;
+  } else if (warp == 8) {
+    // ======================================= MMA issuer =============================================
+    int s = 0;
+    uint32_t ph = 0;
     const uint64_t desc_hi = make_smem_desc(0, 16, 512, LAYOUT_SW64, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_const = (uint32_t)(make_smem_desc(0, 16, 512, LAYOUT_SW64, 0) & 0xFFFF0000ull);
     const uint32_t a0 = lo_const | ((smA & 0x3FFFFu) >> 4);
     const uint32_t wh = lo_const | ((smW & 0x3FFFFu) >> 4);
     const uint32_t wl = lo_const | (((smW + 4096) & 0x3FFFFu) >> 4);
-    const int nit = (p.ntiles - cta + ncta - 1) / ncta;            // tiles of this CTA: it = 0 .. nit-1
-    int next_issue = eg;                                           // next tile of this group whose MMAs are not issued yet
-    auto issue = [&](int it, bool blocking) -> bool {
-      const int s = it % C1U_STAGES;
-      const uint32_t ph = (uint32_t)(it / C1U_STAGES) & 1u;
-      const int as = it & (C1U_ACC - 1);
-      const uint32_t acc_ph = (uint32_t)(it / C1U_ACC) & 1u;
-      if (blocking) {
-        mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
-        mbar_wait(full + 8 * s, ph);
-      } else if (!(mbar_try_wait(acc_empty + 8 * as, acc_ph ^ 1u) && mbar_try_wait(full + 8 * s, ph))) {
-        return false;
-      }
+    int it = 0;
+    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
+      const int as = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
+      mbar_wait(full + 8 * s, ph);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
       const uint32_t ah = a0 + (uint32_t)s * (2 * C1U_TILE_BYTES >> 4);
@@ -224,26 +200,29 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
         mma_commit(acc_full + 8 * as);
       }
       __syncwarp();
-      return true;
-    };
-    auto top_up = [&](int it) {                                    // (lead warp only) keep tiles it and it + 2 issued
-      while (next_issue < nit && next_issue <= it + 2) {
-        if (!issue(next_issue, next_issue <= it)) break;
-        next_issue += 2;
-      }
-    };
+      if (++s == C1U_STAGES) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ======================================= epilogue ===============================================
+    // Per tile and thread (= one voxel row): TMEM -> 32 fp32 -> packed bf16 (cvt.rn.bf16x2) -> 16-byte stores; the
+    // BatchNorm sums of the STORED values accumulate in per-thread registers over the whole tile range and are
+    // reduced across lanes / warps once, at the end (no per-tile shuffles or atomics).  Bias is already in the
+    // accumulator (K column 27).
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    __nv_bfloat16* yg = p.y[g];
+    const bool want_stats = p.stats[g] != nullptr;
     float ssum[NCH][32], ssq[NCH][32];
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
       for (int j = 0; j < 32; ++j) { ssum[c][j] = 0.f; ssq[c][j] = 0.f; }
-    for (int it = eg; it < nit; it += 2) {
-      const int tile = cta + it * ncta;
+    int it = 0;
+    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
       const long long m = (long long)tile * 128 + row;
       const bool valid = m < p.M;
-      const int as = it & (C1U_ACC - 1);
-      const uint32_t acc_ph = (uint32_t)(it / C1U_ACC) & 1u;
-      if (lead) top_up(it);
+      const int as = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(acc_full + 8 * as, acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout);
@@ -256,7 +235,6 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
           if (c == NCH - 1) {                       // accumulator drained: hand the buffer back before the stores
             tc_fence_before();
             mbar_arrive(acc_empty + 8 * as);
-            if (lead) top_up(it);                   // the next tiles' MMAs overlap this tile's pack / stores / statistics
           }
           uint32_t pk[16];
 #pragma unroll
@@ -280,7 +258,6 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       }
     }
     if (want_stats) {
-      const int ew = warp - 8;                     // 0..7: one shared-memory slot per epilogue warp
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         {
@@ -298,16 +275,16 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
               ssq[c][i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
             }
           }
-          stats_ptr[ew * 128 + c * 32 + lane] = ssum[c][0];
-          stats_ptr[ew * 128 + 64 + c * 32 + lane] = ssq[c][0];
+          stats_ptr[quarter * 128 + c * 32 + lane] = ssum[c][0];
+          stats_ptr[quarter * 128 + 64 + c * 32 + lane] = ssq[c][0];
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int e = threadIdx.x - 256;             // 0..255 over the eight epilogue warps
-      if (e < p.cout) {                            // fixed-order sum over the eight warps -> this CTA's row
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 288;             // 0..127 over the four epilogue warps
+      if (e < p.cout) {                            // fixed-order sum over the four warps -> this CTA's row
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) { s1 += (double)stats_ptr[w8 * 128 + e]; s2 += (double)stats_ptr[w8 * 128 + 64 + e]; }
+        for (int w4 = 0; w4 < 4; ++w4) { s1 += (double)stats_ptr[w4 * 128 + e]; s2 += (double)stats_ptr[w4 * 128 + 64 + e]; }
         stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, e, s1);
         stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, p.cout + e, s2);
       }
@@ -525,7 +502,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   p.M = (long long)B * D * H * W;
   p.ntiles = (int)((p.M + 127) / 128);
   p.idesc = make_idesc_bf16(128, cout, 0, 0);
-  p.tmem_cols = (cout == 32) ? 128 : 256;          // four accumulator buffers
+  p.tmem_cols = (cout == 32) ? 64 : 128;
   {
     const char* e = getenv("TMF_C1U_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -538,7 +515,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
     p.y[g] = (__nv_bfloat16*)y[g];
     p.stats[g] = stats ? stats[g] : nullptr;
   }
-  const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES + 2 * C1U_ACC) + 64 + 4096 + 64;
+  const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 2048 + 64;
   static bool attr_done = false;
   if (!attr_done) {
     TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
