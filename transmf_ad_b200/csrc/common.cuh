@@ -117,6 +117,33 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* ticket, unsigned nb
 constexpr size_t TMF_WS_TICKET_BYTES = 16384;                 // 4096 tickets: [0,1024) LayerNorm, [1024,3072) GEMM tiles, [3072,4096) column sums
 constexpr size_t TMF_WS_BYTES = (size_t)16 << 20;
 
+// Packed fp32 pairs in one 64-bit register (sm_100: FADD2 / FFMA2 issue two fp32 operations per slot).
+__device__ __forceinline__ uint64_t pair_u32(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pair_f32(float lo, float hi) { return pair_u32(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ uint32_t lo_u32(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ uint32_t hi_u32(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return hi;
+}
+__device__ __forceinline__ uint64_t add2_f32(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2_f32(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -243,51 +243,48 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
     __nv_bfloat16* yg = p.y[g];
     const bool want_stats = p.stats[g] != nullptr;
     const bool no_shift = (p.debug & 1) != 0, no_store = (p.debug & 2) != 0;
-    float acc_s[CC_CO], acc_q[CC_CO];
+    const bool has_bias = p.bias[g] != nullptr;
+    // Packed fp32 pairs (FADD2 / FFMA2): the epilogue is bound by issue slots and dependent-issue latency of its 8 warps, not
+    // by TMEM or memory (TMF_COL_DEBUG=32: issuers of the Cin = 32 layers wait 35 % of the time for a free accumulator).
+    uint64_t acc_s[CC_CO / 2], acc_q[CC_CO / 2];
 #pragma unroll
-    for (int j = 0; j < CC_CO; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
-    const float4* bias4 = reinterpret_cast<const float4*>(bias_ptr);
+    for (int j = 0; j < CC_CO / 2; ++j) { acc_s[j] = 0ull; acc_q[j] = 0ull; }
+    const uint64_t m_in = pair_f32(lane < 31 ? 1.f : 0.f, lane < 31 ? 1.f : 0.f);   // rows whose +1 neighbour is in this warp
+    const uint64_t m_31 = pair_f32(lane == 31 ? 1.f : 0.f, lane == 31 ? 1.f : 0.f);
+    const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(bias_ptr);
     long long t_epi = 0;
     const long long t_epi0 = clock64();
     uint32_t xb = 0;                              // exchange buffer parity
     int it = eg;
-    for (int s = s_begin + eg; s < s_end; s += 2, it += 2) {
-      const int d = s % p.D, col = s / p.D;
-      const int c = col % p.NC, n = col / p.NC;
+    int s = s_begin + eg;
+    int d = s % p.D, col = s / p.D;
+    bool new_col = true, valid = false;
+    const int64_t dstride = (int64_t)p.H * p.W * p.cout;
+    __nv_bfloat16* ycol = yg;
+    for (; s < s_end; s += 2, it += 2) {
+      if (new_col) {                              // (every D / 2 outputs: the divisions stay out of the per-output path)
+        const int c = col % p.NC, n = col / p.NC;
+        const int q = c * CC_TILE_OUT + row;
+        const int h = q / p.Wp, w = q - h * p.Wp;
+        valid = (row < CC_TILE_OUT) && (h < p.H) && (w < p.W) && !no_store;
+        ycol = yg + (((int64_t)n * p.D * p.H + h) * p.W + w) * p.cout + co_off;
+        new_col = false;
+      }
+      __nv_bfloat16* yrow = ycol + d * dstride;
+      d += 2;
+      while (d >= p.D) { d -= p.D; ++col; new_col = true; }
       const int as = it & (CC_NBUF - 1);
       mbar_wait_t(acc_full + 8 * as, (uint32_t)(it / CC_NBUF) & 1u, t_epi, prof);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * CC_NSTACK);
-      // ---- phase A: publish the rows the previous lane quarter needs (D1 of row 0; D2 of rows 0 and 1)
-      float4* xw = reinterpret_cast<float4*>(xchg_ptr + (((xb * 2 + eg) * 4 + quarter) * 3) * 32);
-      const float4* xr = reinterpret_cast<const float4*>(xchg_ptr + (((xb * 2 + eg) * 4 + ((quarter + 1) & 3)) * 3) * 32);
+      // Every accumulator value is read from TMEM once.  Per 16-channel half: load D0, D1, D2; lane 0 publishes its D1 / D2
+      // and lane 1 its D2 for the previous lane quarter; the two-row shift is done with shuffles -- rows 30 / 31 of a quarter
+      // lack the terms of the next quarter -- both halves stay in registers, ONE group barrier, then rows 30 / 31 add the
+      // published terms and everybody stores.   T[r] = D1[r] + D2[r+1];  y[r] = D0[r] + T[r+1].
+      float* xw = xchg_ptr + (((xb * 2 + eg) * 4 + quarter) * 3) * 32;                       // [D1 row0 | D2 row0 | D2 row1][32]
+      const float* xr = xchg_ptr + (((xb * 2 + eg) * 4 + ((quarter + 1) & 3)) * 3) * 32;
       xb ^= 1u;
-      if (!no_shift) {
-        uint32_t b1[32], b2[32];
-        tmem_ld32(taddr + CC_CO, b1);
-        tmem_ld32(taddr + 2 * CC_CO, b2);
-        tmem_ld_wait();
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            xw[j] = make_float4(__uint_as_float(b1[4 * j]), __uint_as_float(b1[4 * j + 1]), __uint_as_float(b1[4 * j + 2]),
-                                __uint_as_float(b1[4 * j + 3]));
-            xw[8 + j] = make_float4(__uint_as_float(b2[4 * j]), __uint_as_float(b2[4 * j + 1]), __uint_as_float(b2[4 * j + 2]),
-                                    __uint_as_float(b2[4 * j + 3]));
-          }
-        } else if (lane == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            xw[16 + j] = make_float4(__uint_as_float(b2[4 * j]), __uint_as_float(b2[4 * j + 1]), __uint_as_float(b2[4 * j + 2]),
-                                     __uint_as_float(b2[4 * j + 3]));
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-      }
-      // ---- phase B: 16 channels at a time
-      const int q = c * CC_TILE_OUT + row;
-      const int h = q / p.Wp, w = q - h * p.Wp;
-      const bool valid = (row < CC_TILE_OUT) && (h < p.H) && (w < p.W) && !no_store;
-      __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout + co_off;
+      uint64_t v[2][8];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t r0[16], r1[16], r2[16];
@@ -300,55 +297,63 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + 8 * as);
         }
-        float v[16];
         if (no_shift) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) + __uint_as_float(r2[j]);
+          for (int j = 0; j < 8; ++j)
+            v[hf][j] = add2_f32(pair_u32(r0[2 * j], r0[2 * j + 1]), add2_f32(pair_u32(r1[2 * j], r1[2 * j + 1]), pair_u32(r2[2 * j], r2[2 * j + 1])));
         } else {
-          // T[r] = D1[r] + D2[r+1];  y[r] = D0[r] + T[r+1]
-          float tt[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            tt[j] = __uint_as_float(r1[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);
-          if (lane == 31) {
+          if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 n2 = xr[8 + hf * 4 + j];           // D2 of the next quarter's row 0
-              tt[4 * j] = __uint_as_float(r1[4 * j]) + n2.x;
-              tt[4 * j + 1] = __uint_as_float(r1[4 * j + 1]) + n2.y;
-              tt[4 * j + 2] = __uint_as_float(r1[4 * j + 2]) + n2.z;
-              tt[4 * j + 3] = __uint_as_float(r1[4 * j + 3]) + n2.w;
+              reinterpret_cast<uint4*>(xw + hf * 16)[j] = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+              reinterpret_cast<uint4*>(xw + 32 + hf * 16)[j] = make_uint4(r2[4 * j], r2[4 * j + 1], r2[4 * j + 2], r2[4 * j + 3]);
             }
-          }
+          } else if (lane == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __shfl_down_sync(0xffffffffu, tt[j], 1);
-          if (lane == 31) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 n1 = xr[hf * 4 + j];               // D1 of the next quarter's row 0
-              const float4 n2 = xr[16 + hf * 4 + j];          // D2 of the next quarter's row 1
-              v[4 * j] = __uint_as_float(r0[4 * j]) + (n1.x + n2.x);
-              v[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + (n1.y + n2.y);
-              v[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + (n1.z + n2.z);
-              v[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + (n1.w + n2.w);
-            }
-          }
-        }
-        if (valid) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = bias4[hf * 4 + j];                 // shared-memory broadcast
-            pk[2 * j] = pack_bf16(v[4 * j] + b4.x, v[4 * j + 1] + b4.y);
-            pk[2 * j + 1] = pack_bf16(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<uint4*>(xw + 64 + hf * 16)[j] = make_uint4(r2[4 * j], r2[4 * j + 1], r2[4 * j + 2], r2[4 * j + 3]);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float f0 = bf16_lo(pk[j]), f1 = bf16_hi(pk[j]);
-            acc_s[hf * 16 + 2 * j] += f0;
-            acc_q[hf * 16 + 2 * j] = fmaf(f0, f0, acc_q[hf * 16 + 2 * j]);
-            acc_s[hf * 16 + 2 * j + 1] += f1;
-            acc_q[hf * 16 + 2 * j + 1] = fmaf(f1, f1, acc_q[hf * 16 + 2 * j + 1]);
+            const uint32_t da = __shfl_down_sync(0xffffffffu, r2[2 * j], 1), db = __shfl_down_sync(0xffffffffu, r2[2 * j + 1], 1);
+            const uint64_t tt = fma2_f32(pair_u32(da, db), m_in, pair_u32(r1[2 * j], r1[2 * j + 1]));
+            const uint32_t ta = __shfl_down_sync(0xffffffffu, lo_u32(tt), 1), tb = __shfl_down_sync(0xffffffffu, hi_u32(tt), 1);
+            v[hf][j] = fma2_f32(pair_u32(ta, tb), m_in, pair_u32(r0[2 * j], r0[2 * j + 1]));
+          }
+        }
+      }
+      if (!no_shift) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+        if (lane >= 30) {
+          // row 30: y += D2next[0];   row 31: y += D1next[0] + D2next[1]   (same instructions, different addresses)
+          const ulonglong2* pa = reinterpret_cast<const ulonglong2*>(xr + (lane == 31 ? 0 : 32));
+          const ulonglong2* pb = reinterpret_cast<const ulonglong2*>(xr + 64);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const ulonglong2 a2 = pa[hf * 4 + j], b2 = pb[hf * 4 + j];
+              v[hf][2 * j] = add2_f32(v[hf][2 * j], fma2_f32(b2.x, m_31, a2.x));
+              v[hf][2 * j + 1] = add2_f32(v[hf][2 * j + 1], fma2_f32(b2.y, m_31, a2.y));
+            }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t o = has_bias ? add2_f32(v[hf][j], bias2[hf * 8 + j]) : v[hf][j];     // shared-memory broadcast
+            pk[j] = pack_bf16(__uint_as_float(lo_u32(o)), __uint_as_float(hi_u32(o)));
+          }
+          if (want_stats) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t f = pair_u32(pk[j] << 16, pk[j] & 0xffff0000u);        // the stored (rounded) values
+              acc_s[hf * 8 + j] = add2_f32(acc_s[hf * 8 + j], f);
+              acc_q[hf * 8 + j] = fma2_f32(f, f, acc_q[hf * 8 + j]);
+            }
           }
           // one 256-bit store: a thread writes whole 32-byte sectors
           asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + hf * 16), "r"(pk[0]), "r"(pk[1]),
@@ -363,8 +368,9 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
       // deterministic: shuffle tree per warp -> one slot per warp -> fixed-order sum -> this CTA's row of the buffer
 #pragma unroll
       for (int j = 0; j < CC_CO; ++j) {
-        const float ssum = warp_sum(acc_s[j]);
-        const float qsum = warp_sum(acc_q[j]);
+        const uint64_t ps = acc_s[j >> 1], pq = acc_q[j >> 1];
+        const float ssum = warp_sum(__uint_as_float((j & 1) ? hi_u32(ps) : lo_u32(ps)));
+        const float qsum = warp_sum(__uint_as_float((j & 1) ? hi_u32(pq) : lo_u32(pq)));
         if (lane == 0) {
           stats_ptr[ew * 64 + j] = ssum;
           stats_ptr[ew * 64 + 32 + j] = qsum;
