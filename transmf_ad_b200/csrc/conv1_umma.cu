@@ -17,8 +17,10 @@ using namespace umma;
 
 constexpr int C1U_PRODUCERS = 128;                 // one im2col row (voxel) per thread; two producer groups (warps 0-3,
                                                    // 4-7) alternate tiles so global-load latency of one hides behind the other
-constexpr int C1U_THREADS = 416;                   // + warp 8: MMA issuer / TMEM owner, warps 9-12: epilogue
-constexpr int C1U_STAGES = 4;
+constexpr int C1U_THREADS = 640;                   // + warps 8, 14: MMA issuers (8 owns TMEM), 9-12 and 16-19: epilogue, 13: image loader
+constexpr int C1U_STAGES = 8;                      // im2col tile pairs in flight (16 KB each)
+constexpr int C1U_ACC = 4;                         // TMEM accumulator buffers
+constexpr int C1U_XS = 8;                          // staged image slots (tiles in flight ahead of the producers)
 constexpr uint32_t C1U_TILE_BYTES = 128 * 64;      // one [128 x 32] bf16 operand tile
 
 struct C1UParams {
@@ -31,12 +33,22 @@ struct C1UParams {
   long long M;
   int ntiles;
   uint32_t idesc, tmem_cols;
+  int xs_seg;         // STAGED: floats per staged window (one per kd): 2 W + 130 + alignment slack, multiple of 4
   int debug;          // timing-only bring-up switches (TMF_C1U_DEBUG): 1 = one MMA pair instead of three, 2 = no stores,
-                      // 4 = no image loads.  Results are wrong with any of them set.
+                      // 4 = no image loads (unstaged path), 32 = role timing printed by block 0.
+                      // Results are wrong with 1 / 2 / 4 set.
 };
 
 // byte offset of 16-byte chunk j of row r inside a K-major, 64-byte-row, 64B-swizzled tile (tile base 1024-aligned)
 __device__ __forceinline__ uint32_t sw64_off(int r, int j) { return (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4); }
+
+// bring-up instrumentation (debug & 32): cycles a role spends blocked on one kind of barrier
+__device__ __forceinline__ void c1u_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 
 __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
   hi = round_bf16(v);
@@ -44,7 +56,16 @@ __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
 }
 
 // NCH = Cout / 32 (1 for dim 128, the benchmark path; 2 for dim 256 -- that variant spills some statistics registers)
-template <int NCH>
+//
+// STAGED (the normal path): the 27 taps of a tile's 128 consecutive voxels live in three contiguous windows of the flat
+// image, one per kd:  [m0 - 1 - W + (kd-1) H W,  + 2 W + 130).  Three lanes of a loader warp copy the windows of every tile
+// into shared memory with cp.async.bulk (completion on an mbarrier, C1U_XS tiles ahead) and the producers read their taps
+// with shared-memory loads: ncu of the unstaged producers (27 __ldg per voxel, one tile ahead) showed 50 % of all stall
+// samples on the first use of those loads (profiles/r2_conv1_notes.md).  The kernel is bound by instruction issue
+// (2200 warp instructions per tile), so the copies must not cost the producers instructions: issuing them as 16-byte
+// cp.async from the producer threads themselves (+30 instructions per thread and tile) was measured SLOWER than no staging.
+// !STAGED keeps the direct loads for images whose base address is not 16-byte aligned or whose rows are too wide.
+template <int NCH, bool STAGED>
 __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __grid_constant__ C1UParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -53,9 +74,12 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   const uint32_t smA = smem_base;
   const uint32_t smW = smA + C1U_STAGES * 2 * C1U_TILE_BYTES;
   const uint32_t bars = smW + 2 * 4096;
-  const uint32_t full = bars, empty = bars + 8 * C1U_STAGES, acc_full = empty + 8 * C1U_STAGES, acc_empty = acc_full + 16;
-  const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t full = bars, empty = bars + 8 * C1U_STAGES, acc_full = empty + 8 * C1U_STAGES, acc_empty = acc_full + 8 * C1U_ACC;
+  const uint32_t tmem_slot = acc_empty + 8 * C1U_ACC;
   float* stats_ptr = reinterpret_cast<float*>(gen + (tmem_slot + 16 - smem_base));        // float [4 warps][2][64]
+  const uint32_t xfull = tmem_slot + 16 + 2048, xempty = xfull + 8 * C1U_XS;
+  const uint32_t xs_sm = xempty + 8 * C1U_XS;                                               // float [C1U_XS][3][xs_seg]
+  const uint32_t xs_slot_bytes = 3u * (uint32_t)p.xs_seg * 4u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,7 +88,8 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C1U_STAGES; ++i) { mbar_init(full + 8 * i, C1U_PRODUCERS); mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < C1U_ACC; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 256); }
+    for (int i = 0; i < C1U_XS; ++i) { mbar_init(xfull + 8 * i, 3); mbar_init(xempty + 8 * i, C1U_PRODUCERS); }
     fence_barrier_init();
   }
   // weights: fp32 (Cout,27) -> bf16 hi / lo tiles, K-major rows of 32 taps (taps 27..31 zero)
@@ -90,6 +115,9 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool prof = (p.debug & 32) != 0;
+  const long long t_start = clock64();
+  long long t_w0 = 0, t_w1 = 0, t_w2 = 0;
 
   if (warp < 8) {
     // ======================================= im2col producers =======================================
@@ -107,13 +135,27 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
     const unsigned st_w = stride % W, st_t = stride / W, st_h = st_t % H, st_d = (st_t / H) % D;
     unsigned m = (unsigned)(cta + grp * ncta) * 128u + (unsigned)r;
     unsigned wq = m % W, hq = (m / W) % H, dq = (m / (W * H)) % D;
-    float nxt[28];
-    auto load_row = [&](float (&v)[28]) {
+    // STAGED: word offset of tap (kd, kh, kw = 0) of row 0 inside a staging slot (warp-uniform).  The window of kd starts
+    // at the aligned-down flat index of voxel (row 0, kh = 0, kw = 0); tiles start at multiples of 128, so the alignment
+    // remainder is the same for every tile.
+    int uoff[9];
+    if (STAGED) {
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) uoff[kd * 3 + kh] = kd * p.xs_seg + ((-1 - sW + (kd - 1) * sH) & 3) + kh * sW;
+    }
+    auto tap_mask = [&](bool (&dok)[3], bool (&hok)[3], bool (&wok)[3]) {
       const bool in_range = m < M32;
-      v[27] = in_range ? 1.f : 0.f;                   // bias column; rows past the end stay all-zero
-      const bool dok[3] = {in_range && dq > 0, in_range, in_range && dq + 1 < D};
-      const bool hok[3] = {hq > 0, true, hq + 1 < H};
-      const bool wok[3] = {wq > 0, true, wq + 1 < W};
+      dok[0] = in_range && dq > 0; dok[1] = in_range; dok[2] = in_range && dq + 1 < D;
+      hok[0] = hq > 0; hok[1] = true; hok[2] = hq + 1 < H;
+      wok[0] = wq > 0; wok[1] = true; wok[2] = wq + 1 < W;
+      return in_range;
+    };
+    float nxt[28];
+    auto load_row = [&](float (&v)[28]) {            // !STAGED: straight from global memory
+      bool dok[3], hok[3], wok[3];
+      v[27] = tap_mask(dok, hok, wok) ? 1.f : 0.f;   // bias column; rows past the end stay all-zero
       const float* xp = xg + m;
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd)
@@ -124,6 +166,24 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
             const bool ok = dok[kd] && hok[kh] && wok[kw];
             v[(kd * 3 + kh) * 3 + kw] = (ok && !(p.debug & 4)) ? __ldg(xp + (kd - 1) * sH + (kh - 1) * sW + (kw - 1)) : 0.f;
           }
+    };
+    // Unconditional shared-memory loads (every tap address lies inside the slot), then the boundary masks as AND words:
+    // 27 LDS + 27 LOP3 instead of 27 predicated loads with their predicate logic, address arithmetic and zero-initialisation.
+    auto load_row_staged = [&](uint32_t (&v)[28], uint32_t slot_sm) {
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(gen + (slot_sm - smem_base)) + r;
+      const bool in_range = m < M32;
+      const uint32_t md[3] = {(in_range && dq > 0) ? ~0u : 0u, in_range ? ~0u : 0u, (in_range && dq + 1 < D) ? ~0u : 0u};
+      const uint32_t mh[3] = {hq > 0 ? ~0u : 0u, ~0u, hq + 1 < H ? ~0u : 0u};
+      const uint32_t mw[3] = {wq > 0 ? ~0u : 0u, ~0u, wq + 1 < W ? ~0u : 0u};
+      v[27] = md[1] & 0x3f800000u;                   // bias column (1.0f); rows past the end stay all-zero
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t mdh = md[kd] & mh[kh];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) v[(kd * 3 + kh) * 3 + kw] = sp[uoff[kd * 3 + kh] + kw] & mdh & mw[kw];
+        }
     };
     auto advance = [&]() {
       m += stride;
@@ -138,26 +198,34 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
     };
     int it = grp;
     int tile = cta + grp * ncta;
-    if (tile < p.ntiles) load_row(nxt);
+    if (!STAGED && tile < p.ntiles) load_row(nxt);
     for (; tile < p.ntiles; tile += 2 * ncta, it += 2) {
       const int s = it % C1U_STAGES;
       const uint32_t ph = (uint32_t)(it / C1U_STAGES) & 1u;
-      float in[28];
+      const int xs = it % C1U_XS;
+      uint32_t in[28];
+      if (STAGED) {
+        c1u_wait_t(xfull + 8 * xs, (uint32_t)(it / C1U_XS) & 1u, t_w0, prof);
+        load_row_staged(in, xs_sm + (uint32_t)xs * xs_slot_bytes);
+        advance();
+      } else {
 #pragma unroll
-      for (int t = 0; t < 28; ++t) in[t] = nxt[t];
-      advance();
-      if (tile + 2 * ncta < p.ntiles) load_row(nxt);
-      // bf16 hi / lo split, two elements per cvt.rn.bf16x2:  hi = bf16(v), lo = bf16(v - hi)
+        for (int t = 0; t < 28; ++t) in[t] = __float_as_uint(nxt[t]);
+        advance();
+        if (tile + 2 * ncta < p.ntiles) load_row(nxt);
+      }
+      // bf16 hi / lo split, two elements per instruction:  hi = bf16(v) (cvt.rn.bf16x2), lo = bf16(v - hi) (FADD2 + cvt)
       uint32_t phi[16], plo[16];
 #pragma unroll
       for (int j = 0; j < 14; ++j) {
-        const float a = in[2 * j], b = in[2 * j + 1];
-        const uint32_t h2 = pack_bf16(a, b);
+        const uint32_t h2 = pack_bf16(__uint_as_float(in[2 * j]), __uint_as_float(in[2 * j + 1]));
+        const uint64_t l2 = sub2_f32(pair_u32(in[2 * j], in[2 * j + 1]), pair_u32(h2 << 16, h2 & 0xffff0000u));
         phi[j] = h2;
-        plo[j] = pack_bf16(a - bf16_lo(h2), b - bf16_hi(h2));
+        plo[j] = pack_bf16(__uint_as_float(lo_u32(l2)), __uint_as_float(hi_u32(l2)));
       }
       phi[14] = phi[15] = plo[14] = plo[15] = 0u;
-      mbar_wait(empty + 8 * s, ph ^ 1u);
+      if (STAGED) mbar_arrive(xempty + 8 * xs);                 // every staged value has been consumed
+      c1u_wait_t(empty + 8 * s, ph ^ 1u, t_w1, prof);
       uint8_t* a_hi = gen + (smA - smem_base) + (size_t)s * 2 * C1U_TILE_BYTES;
       uint8_t* a_lo = a_hi + C1U_TILE_BYTES;
 #pragma unroll
@@ -169,26 +237,78 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
       fence_proxy_async();                           // generic-proxy smem writes -> visible to the tensor core
       mbar_arrive(full + 8 * s);
     }
-  } else if (warp == 8) {
-    // ======================================= MMA issuer =============================================
-    int s = 0;
-    uint32_t ph = 0;
+    if (prof && blockIdx.x == 0 && (threadIdx.x & 127) == 0)
+      printf("c1u prof: producer group %d: total %lld cyc, waiting for staged image %lld, for a free A stage %lld\n", grp,
+             clock64() - t_start, t_w0, t_w1);
+  } else if (warp == 13) {
+    // ======================================= image loader (STAGED) ==================================
+    // lane kd copies window kd of every tile.  Interior tiles: one aligned bulk copy of xs_seg floats.  At the two ends of the
+    // image the window is clipped to whole 16-byte chunks inside [0, total) (the destination shifts with it) and the up to
+    // three floats of a ragged tail are stored by hand; whatever stays unwritten is only ever read under a false tap mask.
+    // (one cp.async.bulk keeps the issuing thread busy for ~280 cycles, so twelve lanes work on four consecutive tiles)
+    if (STAGED && lane < 12) {
+      const int kdl = lane % 3, sub = lane / 3;
+      const float* xg = p.x[g];
+      const int total = (int)p.M, seg = p.xs_seg;
+      const int c_kd = (-1 - p.W + (kdl - 1) * p.W * p.H) & ~3;            // aligned-down window start relative to the tile
+      const uint32_t dst_kd = (uint32_t)kdl * (uint32_t)seg * 4u;
+      int it = sub;
+      for (int tile = cta + sub * ncta; tile < p.ntiles; tile += 4 * ncta, it += 4) {
+        const int xs = it % C1U_XS;
+        const uint32_t bar = xfull + 8 * xs;
+        const uint32_t slot_sm = xs_sm + (uint32_t)xs * xs_slot_bytes + dst_kd;
+        int a = tile * 128 + c_kd;
+        c1u_wait_t(xempty + 8 * xs, ((uint32_t)(it / C1U_XS) & 1u) ^ 1u, t_w0, prof);
+        if (a >= 0 && a + seg <= total) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_expect_tx(bar, (uint32_t)seg * 4u);
+          const long long t1 = prof ? clock64() : 0;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot_sm),
+                       "l"(xg + a), "r"((uint32_t)seg * 4u), "r"(bar)
+                       : "memory");
+          if (prof) { const long long t2 = clock64(); t_w1 += t1 - t0; t_w2 += t2 - t1; }
+        } else {
+          int d0 = 0, n = seg;
+          if (a < 0) { d0 = -a; n += a; a = 0; }                           // (-a is a multiple of 4: destination stays aligned)
+          if (a + n > total) {
+            const int keep = (total - a) > 0 ? ((total - a) & ~3) : 0;
+            float* slot_ptr = reinterpret_cast<float*>(gen + (slot_sm - smem_base));
+            for (int i = a + keep; i < total; ++i) slot_ptr[d0 + (i - a)] = xg[i];      // <= 3 floats
+            n = keep;
+          }
+          n = n > 0 ? n : 0;
+          mbar_expect_tx(bar, (uint32_t)n * 4u);                           // (the arrive also releases the tail stores)
+          if (n > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             slot_sm + (uint32_t)d0 * 4u),
+                         "l"(xg + a), "r"((uint32_t)n * 4u), "r"(bar)
+                         : "memory");
+        }
+      }
+      if (prof && blockIdx.x == 0 && lane == 0)
+        printf("c1u prof: loader: total %lld cyc, waiting for a free staging slot %lld, in expect_tx %lld, in cp.async.bulk %lld\n",
+               clock64() - t_start, t_w0, t_w1, t_w2);
+    }
+  } else if (warp == 8 || warp == 14) {
+    // ======================================= MMA issuers ============================================
+    // Two issuers (one elected lane each) alternate tiles: with one, the serial chain  wait(accumulator) -> wait(A stage) ->
+    // 6 MMAs -> 2 commits  took 700 cycles per tile and the producers waited 37 % of the time for a free A stage.
+    const int iss = (warp == 8) ? 0 : 1;
     const uint64_t desc_hi = make_smem_desc(0, 16, 512, LAYOUT_SW64, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_const = (uint32_t)(make_smem_desc(0, 16, 512, LAYOUT_SW64, 0) & 0xFFFF0000ull);
     const uint32_t a0 = lo_const | ((smA & 0x3FFFFu) >> 4);
     const uint32_t wh = lo_const | ((smW & 0x3FFFFu) >> 4);
     const uint32_t wl = lo_const | (((smW + 4096) & 0x3FFFFu) >> 4);
-    int it = 0;
-    for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
-      const int as = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
-      mbar_wait(full + 8 * s, ph);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
-      const uint32_t ah = a0 + (uint32_t)s * (2 * C1U_TILE_BYTES >> 4);
-      const uint32_t al = ah + (C1U_TILE_BYTES >> 4);
-      if (elect_one()) {
+    if (elect_one()) {
+      int it = iss;
+      for (int tile = cta + iss * ncta; tile < p.ntiles; tile += 2 * ncta, it += 2) {
+        const int as = it % C1U_ACC, s = it % C1U_STAGES;
+        c1u_wait_t(acc_empty + 8 * as, ((uint32_t)(it / C1U_ACC) & 1u) ^ 1u, t_w0, prof);
+        c1u_wait_t(full + 8 * s, (uint32_t)(it / C1U_STAGES) & 1u, t_w1, prof);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.cout);
+        const uint32_t ah = a0 + (uint32_t)s * (2 * C1U_TILE_BYTES >> 4);
+        const uint32_t al = ah + (C1U_TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(ah + 2u * k), desc_hi | (uint64_t)(wh + 2u * k), p.idesc, k ? 1u : 0u);
@@ -199,89 +319,102 @@ __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __
         mma_commit(empty + 8 * s);
         mma_commit(acc_full + 8 * as);
       }
-      __syncwarp();
-      if (++s == C1U_STAGES) { s = 0; ph ^= 1u; }
+      if (prof && blockIdx.x == 0)
+        printf("c1u prof: issuer %d: total %lld cyc, waiting for a free accumulator %lld, for a full A stage %lld\n", iss,
+               clock64() - t_start, t_w0, t_w1);
     }
-  } else {
+    __syncwarp();
+  } else if (warp != 15) {
     // ======================================= epilogue ===============================================
-    // Per tile and thread (= one voxel row): TMEM -> 32 fp32 -> packed bf16 (cvt.rn.bf16x2) -> 16-byte stores; the
-    // BatchNorm sums of the STORED values accumulate in per-thread registers over the whole tile range and are
-    // reduced across lanes / warps once, at the end (no per-tile shuffles or atomics).  Bias is already in the
-    // accumulator (K column 27).
+    // Two groups of four warps (9-12, 16-19) work on EVERY tile: group h owns channels [16 h, 16 h + 16) of each 32-channel
+    // slice, so a thread (= one voxel row) does TMEM -> 16 fp32 -> packed bf16 -> one 32-byte store, and keeps the
+    // BatchNorm sums of the stored values of its 16 channels in registers over the whole tile range (no per-tile
+    // shuffles or atomics).  One group of four warps with all 32 channels took 730 cycles per tile and held the issuers
+    // back 62 % of the time; a thread with 32 channels also needs 128 registers.  Bias is already in the accumulator
+    // (K column 27).
+    const int half = (warp >= 16) ? 1 : 0;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     __nv_bfloat16* yg = p.y[g];
     const bool want_stats = p.stats[g] != nullptr;
-    float ssum[NCH][32], ssq[NCH][32];
+    uint64_t ssum2[NCH][8], ssq2[NCH][8];            // packed fp32 pairs (FADD2 / FFMA2)
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { ssum[c][j] = 0.f; ssq[c][j] = 0.f; }
+      for (int j = 0; j < 8; ++j) { ssum2[c][j] = 0ull; ssq2[c][j] = 0ull; }
     int it = 0;
     for (int tile = cta; tile < p.ntiles; tile += ncta, ++it) {
       const long long m = (long long)tile * 128 + row;
       const bool valid = m < p.M;
-      const int as = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(acc_full + 8 * as, acc_ph);
+      const int as = it % C1U_ACC;
+      const uint32_t acc_ph = (uint32_t)(it / C1U_ACC) & 1u;
+      c1u_wait_t(acc_full + 8 * as, acc_ph, t_w0, prof);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.cout + half * 16);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        {
-          uint32_t raw[32];
-          tmem_ld32(taddr + (uint32_t)(c * 32), raw);
-          tmem_ld_wait();
-          if (c == NCH - 1) {                       // accumulator drained: hand the buffer back before the stores
-            tc_fence_before();
-            mbar_arrive(acc_empty + 8 * as);
-          }
-          uint32_t pk[16];
+        uint32_t raw[16];
+        tmem_ld16(taddr + (uint32_t)(c * 32), raw);
+        tmem_ld_wait();
+        if (c == NCH - 1) {                         // accumulator drained: hand the buffer back before the stores
+          tc_fence_before();
+          mbar_arrive(acc_empty + 8 * as);
+        }
+        uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
-          if (valid && !(p.debug & 2)) {
-            uint4* yrow = reinterpret_cast<uint4*>(yg + m * p.cout + c * 32);
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+        if (valid && !(p.debug & 2))                // 256-bit store: a thread writes one whole 32-byte sector
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yg + m * p.cout + c * 32 + half * 16),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        if (want_stats) {                           // rows past the end are exact zeros (all-zero im2col row)
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) yrow[qd] = make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-          }
-          if (want_stats) {                         // rows past the end are exact zeros (all-zero im2col row)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
-              ssum[c][2 * j] += lo;
-              ssum[c][2 * j + 1] += hi;
-              ssq[c][2 * j] = fmaf(lo, lo, ssq[c][2 * j]);
-              ssq[c][2 * j + 1] = fmaf(hi, hi, ssq[c][2 * j + 1]);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t f = pair_u32(pk[j] << 16, pk[j] & 0xffff0000u);      // the stored (rounded) values
+            ssum2[c][j] = add2_f32(ssum2[c][j], f);
+            ssq2[c][j] = fma2_f32(f, f, ssq2[c][j]);
           }
         }
       }
     }
+    if (prof && blockIdx.x == 0 && lane == 0 && quarter == 0)
+      printf("c1u prof: epilogue group %d: total %lld cyc, waiting for a finished accumulator %lld\n", half, clock64() - t_start, t_w0);
     if (want_stats) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        {
-          // transpose-reduce: lane l ends with the warp total of column c*32 + l
+        float ssum[16], ssq[16];
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
+        for (int j = 0; j < 8; ++j) {
+          ssum[2 * j] = __uint_as_float(lo_u32(ssum2[c][j])); ssum[2 * j + 1] = __uint_as_float(hi_u32(ssum2[c][j]));
+          ssq[2 * j] = __uint_as_float(lo_u32(ssq2[c][j])); ssq[2 * j + 1] = __uint_as_float(hi_u32(ssq2[c][j]));
+        }
+        // fold lanes l and l ^ 16, then transpose-reduce: lanes l and l + 16 end with the warp total of column l (l < 16)
 #pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float s_send = upper ? ssum[c][i] : ssum[c][i + off];
-              const float s_keep = upper ? ssum[c][i + off] : ssum[c][i];
-              ssum[c][i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
-              const float q_send = upper ? ssq[c][i] : ssq[c][i + off];
-              const float q_keep = upper ? ssq[c][i + off] : ssq[c][i];
-              ssq[c][i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
-            }
+        for (int i = 0; i < 16; ++i) {
+          ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+          ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+        }
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float s_send = upper ? ssum[i] : ssum[i + off];
+            const float s_keep = upper ? ssum[i + off] : ssum[i];
+            ssum[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+            const float q_send = upper ? ssq[i] : ssq[i + off];
+            const float q_keep = upper ? ssq[i + off] : ssq[i];
+            ssq[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
           }
-          stats_ptr[quarter * 128 + c * 32 + lane] = ssum[c][0];
-          stats_ptr[quarter * 128 + 64 + c * 32 + lane] = ssq[c][0];
+        }
+        if (lane < 16) {
+          stats_ptr[quarter * 128 + c * 32 + half * 16 + lane] = ssum[0];
+          stats_ptr[quarter * 128 + 64 + c * 32 + half * 16 + lane] = ssq[0];
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 288;             // 0..127 over the four epilogue warps
-      if (e < p.cout) {                            // fixed-order sum over the four warps -> this CTA's row
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int e = threadIdx.x - 288;             // 0..127 over the first group's four warps
+      if (e >= 0 && e < p.cout) {                  // fixed-order sum over the four lane quarters -> this CTA's row
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4) { s1 += (double)stats_ptr[w4 * 128 + e]; s2 += (double)stats_ptr[w4 * 128 + 64 + e]; }
@@ -502,7 +635,7 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   p.M = (long long)B * D * H * W;
   p.ntiles = (int)((p.M + 127) / 128);
   p.idesc = make_idesc_bf16(128, cout, 0, 0);
-  p.tmem_cols = (cout == 32) ? 64 : 128;
+  p.tmem_cols = (cout == 32) ? 128 : 256;          // C1U_ACC accumulators of Cout columns
   {
     const char* e = getenv("TMF_C1U_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -515,11 +648,20 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
     p.y[g] = (__nv_bfloat16*)y[g];
     p.stats[g] = stats ? stats[g] : nullptr;
   }
-  const uint32_t smem = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 64 + 2048 + 64;
+  // staged image windows (see the kernel): needs 16-byte aligned images and rows that fit the staging buffers
+  p.xs_seg = (2 * W + 133 + 3) & ~3;
+  bool staged = getenv("TMF_C1U_UNSTAGED") == nullptr;
+  for (int g = 0; g < ng; ++g) staged = staged && (reinterpret_cast<uintptr_t>(x[g]) & 15u) == 0;
+  const uint32_t smem_fixed = 1024 + C1U_STAGES * 2 * C1U_TILE_BYTES + 2 * 4096 + 8 * (2 * C1U_STAGES) + 16 * C1U_ACC + 32 + 2048 + 16 * C1U_XS;
+  const uint32_t smem_max = 227 * 1024;
+  staged = staged && smem_fixed + (uint32_t)C1U_XS * 3 * p.xs_seg * 4 + 64 <= smem_max;
+  const uint32_t smem = smem_fixed + (staged ? (uint32_t)C1U_XS * 3 * p.xs_seg * 4 : 0u) + 64;
   static bool attr_done = false;
   if (!attr_done) {
-    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    TMF_CUDA(cudaFuncSetAttribute(conv1_umma_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_done = true;
   }
   int dev = 0, sms = 148;
@@ -529,8 +671,11 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   if (per_group > p.ntiles) per_group = p.ntiles;
   if (per_group < 1) per_group = 1;
   if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;
-  if (cout == 32) conv1_umma_fwd_kernel<1><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
-  else conv1_umma_fwd_kernel<2><<<dim3(per_group * ng), C1U_THREADS, smem, st>>>(p);
+  const dim3 grid(per_group * ng);
+  if (cout == 32 && staged) conv1_umma_fwd_kernel<1, true><<<grid, C1U_THREADS, smem, st>>>(p);
+  else if (cout == 32) conv1_umma_fwd_kernel<1, false><<<grid, C1U_THREADS, smem, st>>>(p);
+  else if (staged) conv1_umma_fwd_kernel<2, true><<<grid, C1U_THREADS, smem, st>>>(p);
+  else conv1_umma_fwd_kernel<2, false><<<grid, C1U_THREADS, smem, st>>>(p);
   TMF_LAUNCH_CHECK();
   return 0;
 }

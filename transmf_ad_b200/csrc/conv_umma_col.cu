@@ -64,15 +64,6 @@ struct alignas(64) ColConvParams {
   int debug;                      // bring-up switches (TMF_COL_DEBUG): 1 no shift, 2 no stores/stats, 8 no MMAs, 32 role timing
 };
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 
 // bring-up instrumentation (debug & 32): cycles a role spends blocked on one kind of barrier
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
