@@ -199,8 +199,11 @@ int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float
 /* ---- fused Transformer(depth=1) encoder (reference models/networks.py:114-175, 215-230; :272-281 for the caller) -------------
  * One encoder  y = LNf( FF(LN2(a)) + a ) [+ x],  a = Attn(LN1(x), ctx) + x  in 3 forward and 5 backward launches: the
  * projections (proj), the attention core (tmf_attn_fwd / tmf_attn_bwd above) and the row-local chain behind it (chain),
- * plus one launch for all weight gradients (wgrad).  GEMMs on the tensor cores with the 3-pass TF32 split (fp32-level
- * accuracy).  dim = heads*dim_head = 128, mlp_dim a multiple of 128 (tmf_encoder_supported); x rows Mx = B*Nq, ctx rows
+ * plus one launch for all weight gradients (wgrad).  The forward / input-gradient GEMMs run on the tensor cores as a
+ * three-MMA bf16 hi/lo split (x*w ~= xh*wh + xl*wh + xh*wl, ~2^-16 relative) from a per-step bf16 hi/lo copy of the five
+ * weight matrices: tmf_encoder_pack_weights writes it (tmf_encoder_pack_bytes(mlp) bytes, 16-byte aligned) and the four
+ * panel entry points take it as `pack`; pack == NULL selects the three-MMA TF32 split straight from the fp32 weights
+ * (~2^-22, slower; the weight gradients always use it).  dim = heads*dim_head = 128, mlp_dim a multiple of 128 (tmf_encoder_supported); x rows Mx = B*Nq, ctx rows
  * Mc = B*Nk; all tensors fp32 row-major; `ws` is the scratch buffer described at tmf_scratch_bytes().
  *   proj_fwd : h1 = LN1(x) (saved with mean1 / rstd1), q = h1 Wq^T [Mx,128], kv = ctx Wkv^T [Mc,256]
  *   chain_fwd: a = o Wo^T + bo + x; h2 = LN2(a); pre = h2 W1^T + b1; f = GELU(pre); g = f W2^T + b2 + a;
@@ -209,22 +212,26 @@ int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float
  *   proj_bwd : dx = dxp + LN1'(dq Wq), dctx = dkv Wkv, LN1 parameter gradients
  *   wgrad    : t = {dq,h1,dWq, dkv,ctx,dWkv, da,o,dWo,dbo, dp,h2,dW1,db1, dg}; dW2 = dg^T f, db2 (all overwritten) */
 int tmf_encoder_supported(int dim, int inner, int mlp);
+size_t tmf_encoder_pack_bytes(int mlp);
+int tmf_encoder_pack_weights(const float* wq, const float* wkv, const float* wo, const float* w1, const float* w2, int mlp,
+                             void* pack, void* stream);
 int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, const float* ln_b, const float* wq,
                          const float* wkv, float* h1, float* mean1, float* rstd1, float* q, float* kv, int Mx, int Mc,
-                         float eps, void* stream);
+                         float eps, const void* pack, void* stream);
 int tmf_encoder_chain_fwd(const float* o, const float* x, const float* wo, const float* bo, const float* ln2_w,
                           const float* ln2_b, const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* lnf_w, const float* lnf_b, float* a, float* h2, float* mean2, float* rstd2,
                           float* pre, float* f, float* g, float* meanf, float* rstdf, float* y, int M, int mlp,
-                          int add_input, float eps2, float epsf, void* stream);
+                          int add_input, float eps2, float epsf, const void* pack, void* stream);
 int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const float* pre, const float* wo,
                           const float* w1, const float* w2, const float* ln2_w, const float* lnf_w, const float* mean2,
                           const float* rstd2, const float* meanf, const float* rstdf, float* dg, float* dp, float* da,
                           float* dout, float* dxp, float* dlnf_w, float* dlnf_b, float* dln2_w, float* dln2_b, int M,
-                          int mlp, int add_input, void* ws, size_t ws_bytes, void* stream);
+                          int mlp, int add_input, const void* pack, void* ws, size_t ws_bytes, void* stream);
 int tmf_encoder_proj_bwd(const float* dq, const float* dkv, const float* dxp, const float* x, const float* ln_w,
                          const float* mean1, const float* rstd1, const float* wq, const float* wkv, float* dx, float* dctx,
-                         float* dln_w, float* dln_b, int Mx, int Mc, void* ws, size_t ws_bytes, void* stream);
+                         float* dln_w, float* dln_b, int Mx, int Mc, const void* pack, void* ws, size_t ws_bytes,
+                         void* stream);
 int tmf_encoder_wgrad(const void* const* t, const float* f, float* dw2, float* db2, int Mx, int Mc, int mlp, void* ws,
                       size_t ws_bytes, void* stream);
 

@@ -42,10 +42,11 @@ SIGNATURES = {
     "tmf_gelu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "tmf_attn_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "tmf_attn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
-    "tmf_encoder_proj_fwd": [_vp] * 11 + [_i, _i, _f, _vp],
-    "tmf_encoder_chain_fwd": [_vp] * 22 + [_i, _i, _i, _f, _f, _vp],
-    "tmf_encoder_chain_bwd": [_vp] * 22 + [_i, _i, _i, _vp, C.c_size_t, _vp],
-    "tmf_encoder_proj_bwd": [_vp] * 13 + [_i, _i, _vp, C.c_size_t, _vp],
+    "tmf_encoder_pack_weights": [_vp] * 5 + [_i, _vp, _vp],
+    "tmf_encoder_proj_fwd": [_vp] * 11 + [_i, _i, _f, _vp, _vp],
+    "tmf_encoder_chain_fwd": [_vp] * 22 + [_i, _i, _i, _f, _f, _vp, _vp],
+    "tmf_encoder_chain_bwd": [_vp] * 22 + [_i, _i, _i, _vp, _vp, C.c_size_t, _vp],
+    "tmf_encoder_proj_bwd": [_vp] * 13 + [_i, _i, _vp, _vp, C.c_size_t, _vp],
     "tmf_encoder_wgrad": [_pp, _vp, _vp, _vp, _i, _i, _i, _vp, C.c_size_t, _vp],
     "tmf_fold_bn_pack": [_i, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _pp, _i, _i, _i, _f, _vp],
     "tmf_eval_head": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
@@ -68,7 +69,7 @@ SIGNATURES = {
     "tmf_scale": [_vp, _vp, _f, _vp, _i64, _vp],
     "tmf_adam_step": [_vp, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp],
 }
-PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []), "tmf_stat_rows": (_i, []), "tmf_scratch_bytes": (_i64, []), "tmf_encoder_supported": (_i, [_i, _i, _i]),
+PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check_device": (_i, []), "tmf_stat_rows": (_i, []), "tmf_scratch_bytes": (_i64, []), "tmf_encoder_supported": (_i, [_i, _i, _i]), "tmf_encoder_pack_bytes": (C.c_size_t, [_i]),
          "tmf_launch_count": (_i64, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
          "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),

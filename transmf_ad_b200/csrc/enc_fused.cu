@@ -28,7 +28,8 @@ namespace enc {
 
 constexpr int THREADS = 256;
 constexpr int PR = 16;                       // panel rows
-constexpr int WT_FLOATS = 128 * 36;          // one weight stage: [128][32+4] (B_NK) or [32][128+8] (B_KN)
+constexpr int WT_FLOATS = 5120;              // one weight stage (20480 B): fp32 [128][32+4] (B_NK) / [32][128+8] (B_KN), or the bf16
+                                             // hi + lo tiles [2][128][32+8] (B_NK) / [2][32][128+8] (B_KN) of the split-weight path
 constexpr int NSTAGE = 4;
 constexpr int LD128 = 132;                   // panel pitch for 128 columns (== 4 mod 32: conflict-free A fragments)
 
@@ -59,32 +60,74 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level; 14 instructions against libdevice erff's
+// 30): the GELU epilogue of the W1 GEMM was 10 k of the 45 k cycles of enc_chain_fwd_kernel (TMF_ENC_PROF).
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  return copysignf(fmaf(-p, __expf(-ax * ax), 1.f), x);
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
 
-// one weight stage: B_NK: rows n0..n0+127 of W (pitch ldw), columns k0..k0+31 -> Ws[r*36 + c]
-//                   B_KN: rows k0..k0+31 of W (pitch ldw; rows >= kvalid read as zero), columns n0..n0+127 -> Ws[r*136 + c]
-template <int MODE>
-__device__ __forceinline__ void stage_w(float* Ws, const float* __restrict__ W, int ldw, int n0, int k0, int kvalid) {
-  if (MODE == B_NK) {
-#pragma unroll
-    for (int c = threadIdx.x; c < 1024; c += THREADS) {
-      const int r = c >> 3, q = c & 7;
-      cp_async16(Ws + r * 36 + 4 * q, W + (size_t)(n0 + r) * ldw + k0 + 4 * q, true);
-    }
-  } else {
-#pragma unroll
-    for (int c = threadIdx.x; c < 1024; c += THREADS) {
-      const int r = c >> 5, q = c & 31;
-      const bool ok = k0 + r < kvalid;
-      cp_async16(Ws + r * 136 + 4 * q, W + (size_t)(ok ? k0 + r : 0) * ldw + n0 + 4 * q, ok);
+// One weight stage is [128][32+4] floats (B_NK: rows n0..n0+127 of W, columns k0..k0+31 -> Ws[r*36 + c]) or [32][128+8]
+// (B_KN: rows k0..k0+31 of W, rows >= kvalid read as zero, columns n0..n0+127 -> Ws[r*136 + c]); 1024 16-byte chunks, chunk
+// c = thread + TH * u.  The per-thread source pointer / destination offset of u = 0 are computed once per GEMM and the stages
+// are issued in order, so a stage costs one pointer update plus the cp.async themselves (the address arithmetic of the
+// straightforward version was 11 % of all instructions of enc_chain_fwd_kernel, profiles/r2_encoder.md).
+template <int MODE, int TH>
+struct WeightStager {
+  const float* src;          // W + r0 * ldw + 4 q           (u = 0 chunk of stage 0)
+  uint32_t dst;              // shared address of chunk u = 0 inside stage slot 0
+  size_t ustride;            // floats between a thread's consecutive chunks
+  int ldw, nk, kvalid, r0;
+  int nb, kc, slot;          // next stage to issue
+  __device__ __forceinline__ WeightStager(float* wstage, const float* W, int ldw_, int nk_, int kvalid_)
+      : ldw(ldw_), nk(nk_), kvalid(kvalid_), nb(0), kc(0), slot(0) {
+    if (MODE == B_NK) {
+      r0 = threadIdx.x >> 3;
+      const int q = threadIdx.x & 7;
+      src = W + (size_t)r0 * ldw + 4 * q;
+      dst = (uint32_t)__cvta_generic_to_shared(wstage + r0 * 36 + 4 * q);
+      ustride = (size_t)(TH >> 3) * ldw;
+    } else {
+      r0 = threadIdx.x >> 5;
+      const int q = threadIdx.x & 31;
+      src = W + (size_t)r0 * ldw + 4 * q;
+      dst = (uint32_t)__cvta_generic_to_shared(wstage + r0 * 136 + 4 * q);
+      ustride = (size_t)(TH >> 5) * ldw;
     }
   }
-}
+  __device__ __forceinline__ void issue() {
+    const uint32_t d = dst + (uint32_t)slot * (WT_FLOATS * 4);
+    if (MODE == B_NK) {
+      const float* g = src + (size_t)nb * 128 * ldw + kc * 32;
+#pragma unroll
+      for (int u = 0; u < 1024 / TH; ++u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)u * ((TH >> 3) * 36 * 4)), "l"(g + u * ustride) : "memory");
+    } else {
+      const float* g = src + (size_t)kc * 32 * ldw + nb * 128;
+#pragma unroll
+      for (int u = 0; u < 1024 / TH; ++u) {
+        const bool ok = kc * 32 + r0 + u * (TH >> 5) < kvalid;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (uint32_t)u * ((TH >> 5) * 136 * 4)),
+                     "l"(ok ? g + u * ustride : src), "r"(ok ? 16 : 0)
+                     : "memory");
+      }
+    }
+    if (++kc == nk) { kc = 0; ++nb; }
+    if (++slot == NSTAGE) slot = 0;
+  }
+};
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -107,12 +150,10 @@ __device__ __forceinline__ void panel_gemm(const float* As, const float* __restr
   const int nk = K / 32;
   const int total = (N / 128) * nk;          // weight stages of the whole GEMM: ONE continuous pipeline over all column blocks
   const float* arow = As + (mt * 16 + g) * LDA + t;
-  auto issue = [&](int s) {
-    stage_w<MODE>(wstage + (s % NSTAGE) * WT_FLOATS, W, ldw, (s / nk) * 128, (s % nk) * 32, kvalid);
-  };
+  WeightStager<MODE, THREADS> stager(wstage, W, ldw, nk, kvalid);
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
-    if (s < total) issue(s);
+    if (s < total) stager.issue();
     cp_async_commit();
   }
   uint32_t a_hi_addr = 0, a_lo_addr = 0;
@@ -138,7 +179,7 @@ __device__ __forceinline__ void panel_gemm(const float* As, const float* __restr
   for (int s = 0; s < total; ++s) {
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
-    if (s + NSTAGE - 1 < total) issue(s + NSTAGE - 1);
+    if (s + NSTAGE - 1 < total) stager.issue();
     cp_async_commit();
     const int kc = s % nk;
     if (kc == 0) {
@@ -195,18 +236,225 @@ __device__ __forceinline__ void panel_gemm(const float* As, const float* __restr
   __syncthreads();
 }
 
+// =====================================================================================================================
+// bf16x3 panel GEMM (the default for the forward / input-gradient GEMMs):  x = xh + xl with xh = bf16(x), xl = bf16(x - xh)
+// (16-17 significant bits), x*w ~= xh*wh + xl*wh + xh*wl on mma.sync.m16n8k16 with fp32 accumulation: ~2^-16 relative,
+// 200x below the bf16 noise of the conv towers that feed the encoder.  Against the 3xTF32 GEMM above it halves the MMA count
+// (k16 instead of k8) and -- the point -- removes the operand handling from the inner loop: the weights are split ONCE per
+// step into bf16 hi / lo arrays (tmf_encoder_pack_weights), stream through the cp.async ring as they are, and both operands
+// reach the registers with ldmatrix.x4; per warp and 32-k stage that is 8 ldmatrix + 12 MMA instead of 8 ldmatrix + 32 LDS +
+// 64 ALU + 24 MMA.  Measured (TMF_ENC_PROF): a stage of enc_chain_fwd took 1200-1400 cycles with 3xTF32.
+// =====================================================================================================================
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// hi / lo bf16 pairs of two fp32 values
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(a, b);
+  const uint64_t l2 = sub2_f32(pair_f32(a, b), pair_u32(hi << 16, hi & 0xffff0000u));
+  lo = pack_bf16(__uint_as_float(lo_u32(l2)), __uint_as_float(hi_u32(l2)));
+}
+
+__device__ int g_enc_prof = 0;              // TMF_ENC_PROF: block 0 prints where the stage loop of the bf16 GEMM spends its cycles
+
+constexpr int WB_NK_PITCH = 80;              // bytes per row of a B_NK stage tile: 32 bf16 + 16 B pad (conflict-free ldmatrix)
+constexpr int WB_KN_PITCH = 272;             // bytes per row of a B_KN stage tile: 128 bf16 + 16 B pad
+constexpr int WB_NK_PLANE = 128 * WB_NK_PITCH, WB_KN_PLANE = 32 * WB_KN_PITCH;
+
+// Weight stages of the split-weight path: `whi` / `whi + wnumel` are the bf16 hi / lo copies of W (same [rows][ldw] layout).
+template <int MODE>
+struct WeightStagerB {
+  const __nv_bfloat16* src;  // chunk u = 0 of stage 0
+  uint32_t dst;
+  size_t lo_off;             // elements between the hi and the lo array
+  int ldw, nk, nb, kc, slot;
+  __device__ __forceinline__ WeightStagerB(float* wstage, const __nv_bfloat16* whi, size_t wnumel, int ldw_, int nk_)
+      : lo_off(wnumel), ldw(ldw_), nk(nk_), nb(0), kc(0), slot(0) {
+    if (MODE == B_NK) {      // chunk c = thread + 256 u: plane u >> 1, row (thread >> 2) + 64 (u & 1), 16-byte column thread & 3
+      const int r0 = threadIdx.x >> 2, q = threadIdx.x & 3;
+      src = whi + (size_t)r0 * ldw + 8 * q;
+      dst = (uint32_t)__cvta_generic_to_shared(wstage) + r0 * WB_NK_PITCH + q * 16;
+    } else {                 // plane u >> 1, row (thread >> 4) + 16 (u & 1), 16-byte column thread & 15
+      const int r0 = threadIdx.x >> 4, q = threadIdx.x & 15;
+      src = whi + (size_t)r0 * ldw + 8 * q;
+      dst = (uint32_t)__cvta_generic_to_shared(wstage) + r0 * WB_KN_PITCH + q * 16;
+    }
+  }
+  __device__ __forceinline__ void issue() {
+    const uint32_t d = dst + (uint32_t)slot * (WT_FLOATS * 4);
+    if (MODE == B_NK) {
+      const __nv_bfloat16* g = src + (size_t)nb * 128 * ldw + kc * 32;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (u >> 1) * WB_NK_PLANE + (u & 1) * 64 * WB_NK_PITCH),
+                     "l"(g + (u >> 1) * lo_off + (size_t)(u & 1) * 64 * ldw)
+                     : "memory");
+    } else {
+      const __nv_bfloat16* g = src + (size_t)kc * 32 * ldw + nb * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (u >> 1) * WB_KN_PLANE + (u & 1) * 16 * WB_KN_PITCH),
+                     "l"(g + (u >> 1) * lo_off + (size_t)(u & 1) * 16 * ldw)
+                     : "memory");
+    }
+    if (++kc == nk) { kc = 0; ++nb; }
+    if (++slot == NSTAGE) slot = 0;
+  }
+};
+
+// C[16][N] = A[16][K] . op(W):  A fp32 in shared memory (pitch LDA floats), W given as its bf16 hi / lo arrays; warp w owns
+// columns [16w, 16w+16) of every 128-column block.  `asplit` receives the bf16 hi / lo planes of A ([2][16][K+8] bf16).
+// B_NK: W is [N][K] (ldw = K); B_KN: W is [K][N] (ldw = N).  epi as in panel_gemm.  Ends with __syncthreads().
+template <int MODE, int LDA, int K, typename Epi>
+__device__ __forceinline__ void panel_gemm_bf16(const float* As, const __nv_bfloat16* whi, size_t wnumel, int ldw, int N,
+                                                float* wstage, float* asplit, Epi epi) {
+  static_assert(THREADS == 256, "chunk mapping of WeightStagerB assumes 256 threads");
+  constexpr int AP = (K + 8) * 2;                      // bytes per row of an A plane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cbase = warp * 16;
+  constexpr int nk = K / 32;
+  const int total = (N / 128) * nk;
+  WeightStagerB<MODE> stager(wstage, whi, wnumel, ldw, nk);
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < total) stager.issue();
+    cp_async_commit();
+  }
+  // split the panel once (the first __syncthreads of the loop below orders it before any fragment load)
+  uint8_t* ap = reinterpret_cast<uint8_t*>(asplit);
+  for (int i = threadIdx.x; i < PR * (K >> 2); i += THREADS) {
+    const int r = i / (K >> 2), c = i - r * (K >> 2);
+    const float4 v = *reinterpret_cast<const float4*>(As + r * LDA + 4 * c);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(ap + r * AP + 8 * c) = h;
+    *reinterpret_cast<uint2*>(ap + PR * AP + r * AP + 8 * c) = l;
+  }
+  // ldmatrix lane addresses.  A: matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7), (rows 0-7, k 8-15), (rows 8-15, k 8-15)
+  const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(ap) + ((lane & 7) + 8 * ((lane >> 3) & 1)) * AP + 16 * (lane >> 4);
+  const uint32_t a_lo = a_hi + PR * AP;
+  // B: matrices (n-tile 0, k 0-7), (n-tile 0, k 8-15), (n-tile 1, k 0-7), (n-tile 1, k 8-15)
+  const uint32_t b_off = (MODE == B_NK)
+                             ? (uint32_t)((cbase + (lane & 7) + 8 * (lane >> 4)) * WB_NK_PITCH + 16 * ((lane >> 3) & 1))
+                             : (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * WB_KN_PITCH + (cbase + 8 * (lane >> 4)) * 2);
+  const uint32_t w_sm = (uint32_t)__cvta_generic_to_shared(wstage);
+  float acc[2][4], acl[2][4];          // hi*hi products and the two small cross terms accumulate in separate chains
+  const bool prof = g_enc_prof != 0 && blockIdx.x == 0;
+  long long t_wait = 0, t_bar = 0, t_issue = 0, t_all = prof ? clock64() : 0;
+  for (int s = 0; s < total; ++s) {
+    long long t0 = prof ? clock64() : 0;
+    cp_async_wait<NSTAGE - 2>();
+    long long t1 = prof ? clock64() : 0;
+    __syncthreads();
+    long long t2 = prof ? clock64() : 0;
+    if (s + NSTAGE - 1 < total) stager.issue();
+    cp_async_commit();
+    if (prof) { const long long t3 = clock64(); t_wait += t1 - t0; t_bar += t2 - t1; t_issue += t3 - t2; }
+    const int kc = s % nk;
+    if (kc == 0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f;
+        acl[j][0] = 0.f; acl[j][1] = 0.f; acl[j][2] = 0.f; acl[j][3] = 0.f;
+      }
+    }
+    const uint32_t ws = w_sm + (uint32_t)(s % NSTAGE) * (WT_FLOATS * 4) + b_off;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t ah[4], al[4], bh[4], bl[4];
+      const uint32_t koff = (uint32_t)(kc * 32 + kk * 16) * 2u;
+      ldmatrix_x4(ah, a_hi + koff);
+      ldmatrix_x4(al, a_lo + koff);
+      if (MODE == B_NK) {
+        ldmatrix_x4(bh, ws + kk * 32);
+        ldmatrix_x4(bl, ws + WB_NK_PLANE + kk * 32);
+      } else {
+        ldmatrix_x4_trans(bh, ws + kk * 16 * WB_KN_PITCH);
+        ldmatrix_x4_trans(bl, ws + WB_KN_PLANE + kk * 16 * WB_KN_PITCH);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        mma_bf16(acl[j], al, bh[2 * j], bh[2 * j + 1]);
+        mma_bf16(acc[j], ah, bh[2 * j], bh[2 * j + 1]);
+        mma_bf16(acl[j], ah, bl[2 * j], bl[2 * j + 1]);
+      }
+    }
+    if (kc == nk - 1) {
+      const int nb = (s / nk) * 128;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = nb + cbase + j * 8 + 2 * t;
+        epi(g, col, acc[j][0] + acl[j][0], acc[j][1] + acl[j][1]);
+        epi(g + 8, col, acc[j][2] + acl[j][2], acc[j][3] + acl[j][3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (prof && (threadIdx.x == 0 || threadIdx.x == 255))
+    printf("bf16 gemm N=%d K=%d thread %d: %d stages, total %lld cyc: cp.async wait %lld, barrier %lld, issue %lld\n", N, K,
+           (int)threadIdx.x, total, clock64() - t_all, t_wait, t_bar, t_issue);
+}
+
+// One GEMM of a panel kernel: split-weight bf16x3 path when the caller passed a weight pack, 3xTF32 from the fp32 weights
+// otherwise (cross-check / TMF_ENC_BF16=0).  `woff` = element offset of this matrix inside the pack (hi array; lo follows).
+template <int MODE, int LDA, int K, typename Epi>
+__device__ __forceinline__ void panel_gemm_any(const float* As, const float* __restrict__ W, const __nv_bfloat16* pack, size_t woff,
+                                               size_t wnumel, int ldw, int N, float* wstage, float* asplit, Epi epi) {
+  if (pack != nullptr) panel_gemm_bf16<MODE, LDA, K>(As, pack + woff, wnumel, ldw, N, wstage, asplit, epi);
+  else panel_gemm<1, MODE, LDA>(As, W, ldw, N, K, 1 << 30, wstage, asplit, epi);
+}
+
+// element offsets of the five weight matrices inside a pack ([hi | lo] per matrix): Wq, Wkv, Wo, W1, W2
+__host__ __device__ constexpr size_t pack_off_wq() { return 0; }
+__host__ __device__ constexpr size_t pack_off_wkv() { return 2 * 128 * 128; }
+__host__ __device__ constexpr size_t pack_off_wo() { return pack_off_wkv() + 2 * 256 * 128; }
+__host__ __device__ constexpr size_t pack_off_w1() { return pack_off_wo() + 2 * 128 * 128; }
+__host__ __device__ constexpr size_t pack_off_w2(int mlp) { return pack_off_w1() + (size_t)2 * mlp * 128; }
+__host__ __device__ constexpr size_t pack_elems(int mlp) { return pack_off_w2(mlp) + (size_t)2 * 128 * mlp; }
+
+struct PackArgs {
+  const float* w[5];
+  int numel[5];
+  size_t off[5];
+  __nv_bfloat16* pack;
+};
+__global__ void __launch_bounds__(256) enc_pack_kernel(PackArgs p) {
+  const int m = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(p.w[m]);
+  uint2* hi = reinterpret_cast<uint2*>(p.pack + p.off[m]);
+  uint2* lo = reinterpret_cast<uint2*>(p.pack + p.off[m] + p.numel[m]);
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < (p.numel[m] >> 2); i += gridDim.x * 256) {
+    const float4 v = __ldg(src + i);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---- panel <-> global helpers (all 256 threads; float4, rows >= nvalid read as zero / are not written) ----------------
-__device__ __forceinline__ void load_panel(float* Ps, int lds, const float* __restrict__ src, int ld, int nvalid, int rows,
-                                           int cols) {
-  const int c4 = cols >> 2;
+template <int COLS>
+__device__ __forceinline__ void load_panel(float* Ps, int lds, const float* __restrict__ src, int ld, int nvalid, int rows) {
+  constexpr int c4 = COLS >> 2;                 // (a power of two: the index split below compiles to shifts)
   for (int i = threadIdx.x; i < rows * c4; i += THREADS) {
     const int r = i / c4, c = i - r * c4;
     const float4 v = (r < nvalid) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)r * ld) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(Ps + r * lds + 4 * c) = v;
   }
 }
-__device__ __forceinline__ void store_panel(float* __restrict__ dst, int ld, const float* Ps, int lds, int nvalid, int cols) {
-  const int c4 = cols >> 2;
+template <int COLS>
+__device__ __forceinline__ void store_panel(float* __restrict__ dst, int ld, const float* Ps, int lds, int nvalid) {
+  constexpr int c4 = COLS >> 2;
   for (int i = threadIdx.x; i < nvalid * c4; i += THREADS) {
     const int r = i / c4, c = i - r * c4;
     reinterpret_cast<float4*>(dst + (size_t)r * ld)[c] = *reinterpret_cast<const float4*>(Ps + r * lds + 4 * c);
@@ -268,15 +516,19 @@ __device__ __forceinline__ void panel_layernorm_bwd(const float* dys, const floa
   }
 }
 
-// Block-level column sums of per-lane float4 accumulators (8 warps, lane owns columns 4*lane..): the warps add into
-// red[128] one after the other (deterministic), result left in red.
-__device__ __forceinline__ void block_colsum128(float* red, const float4& v) {
+// Block-level column sums of NV per-lane float4 accumulators (8 warps, lane owns columns 4*lane..): the warps add into
+// red[NV][128] one after the other (deterministic), result left in red.
+template <int NV>
+__device__ __forceinline__ void block_colsum128(float* red, const float4 (&v)[NV]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int w = 0; w < 8; ++w) {
+  for (int w = 0; w < THREADS / 32; ++w) {
     if (warp == w) {
-      float4* p = reinterpret_cast<float4*>(red) + lane;
-      if (w == 0) *p = v;
-      else { float4 a = *p; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; *p = a; }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4* p = reinterpret_cast<float4*>(red + 128 * i) + lane;
+        if (w == 0) *p = v[i];
+        else { float4 a = *p; a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w; *p = a; }
+      }
     }
     __syncthreads();
   }
@@ -301,6 +553,7 @@ struct ProjFwdArgs {
   float *h1, *mean1, *rstd1, *q, *kv;
   int Mx, Mc, nbx;
   float eps;
+  const __nv_bfloat16* pack;          // bf16 hi / lo copies of the weights (tmf_encoder_pack_weights), or null: 3xTF32
 };
 
 __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
@@ -311,23 +564,23 @@ __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
   float* wst = spl + 2 * PR * LD128;
   if ((int)blockIdx.x < p.nbx) {
     const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
-    load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
+    load_panel<128>(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR);
     __syncthreads();
     panel_layernorm(P0, P0, LD128, p.ln_w, p.ln_b, p.eps, p.mean1, p.rstd1, row0, nv);
     __syncthreads();
-    store_panel(p.h1 + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
-    panel_gemm<1, B_NK, LD128>(P0, p.wq, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+    store_panel<128>(p.h1 + (size_t)row0 * 128, 128, P0, LD128, nv);
+    panel_gemm_any<B_NK, LD128, 128>(P0, p.wq, p.pack, pack_off_wq(), 128 * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
-    store_panel(p.q + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+    store_panel<128>(p.q + (size_t)row0 * 128, 128, P1, LD128, nv);
   } else {
     const int row0 = (blockIdx.x - p.nbx) * PR, nv = min(PR, p.Mc - row0);
-    load_panel(P0, LD128, p.ctx + (size_t)row0 * 128, 128, nv, PR, 128);
+    load_panel<128>(P0, LD128, p.ctx + (size_t)row0 * 128, 128, nv, PR);
     __syncthreads();
-    panel_gemm<1, B_NK, LD128>(P0, p.wkv, 128, 256, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+    panel_gemm_any<B_NK, LD128, 128>(P0, p.wkv, p.pack, pack_off_wkv(), 256 * 128, 128, 256, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * 260 + c) = make_float2(v0, v1);
     });
-    store_panel(p.kv + (size_t)row0 * 256, 256, P1, 260, nv, 256);
+    store_panel<256>(p.kv + (size_t)row0 * 256, 256, P1, 260, nv);
   }
 }
 
@@ -337,8 +590,9 @@ __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
 struct ChainFwdArgs {
   const float *o, *x, *wo, *bo, *ln2_w, *ln2_b, *w1, *b1, *w2, *b2, *lnf_w, *lnf_b;
   float *a, *h2, *mean2, *rstd2, *pre, *f, *g, *meanf, *rstdf, *y;
-  int M, mlp, add_input;
+  int M, mlp, add_input, prof;
   float eps2, epsf;
+  const __nv_bfloat16* pack;
 };
 
 template <int MLP>
@@ -352,36 +606,39 @@ __global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) 
   float* spl = PF + PR * ldf;               // [2][16][mlp+4] hi / lo planes of the current GEMM's A panel
   float* wst = spl + 2 * PR * ldf;
   const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
-  load_panel(P0, LD128, p.o + (size_t)row0 * 128, 128, nv, PR, 128);
-  load_panel(P2, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);     // x parked in P2 until LN2 overwrites it
+  long long tk[10]; int ntk = 0;
+#define TK() do { if (p.prof) { __syncthreads(); tk[ntk++] = clock64(); } } while (0)
+  TK();
+  load_panel<128>(P0, LD128, p.o + (size_t)row0 * 128, 128, nv, PR);
+  load_panel<128>(P2, LD128, p.x + (size_t)row0 * 128, 128, nv, PR);     // x parked in P2 until LN2 overwrites it
   __syncthreads();
+  TK();
   // a = o Wo^T + bo + x
-  panel_gemm<1, B_NK, LD128>(P0, p.wo, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+  panel_gemm_any<B_NK, LD128, 128>(P0, p.wo, p.pack, pack_off_wo(), 128 * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
     const float2 xb = *reinterpret_cast<const float2*>(P2 + r * LD128 + c);
     *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0 + __ldg(p.bo + c) + xb.x, v1 + __ldg(p.bo + c + 1) + xb.y);
   });
-  store_panel(p.a + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  TK();
+  store_panel<128>(p.a + (size_t)row0 * 128, 128, P1, LD128, nv);
   panel_layernorm(P1, P2, LD128, p.ln2_w, p.ln2_b, p.eps2, p.mean2, p.rstd2, row0, nv);
   __syncthreads();
-  store_panel(p.h2 + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
-  // pre = h2 W1^T + b1
-  panel_gemm<1, B_NK, LD128>(P2, p.w1, 128, MLP, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
-    *reinterpret_cast<float2*>(PF + r * ldf + c) = make_float2(v0 + __ldg(p.b1 + c), v1 + __ldg(p.b1 + c + 1));
+  store_panel<128>(p.h2 + (size_t)row0 * 128, 128, P2, LD128, nv);
+  TK();
+  // pre = h2 W1^T + b1 (saved for the backward pass straight from the accumulator registers);  f = GELU(pre) -> PF
+  panel_gemm_any<B_NK, LD128, 128>(P2, p.w1, p.pack, pack_off_w1(), MLP * 128, 128, MLP, wst, spl, [&](int r, int c, float v0, float v1) {
+    const float2 pre = make_float2(v0 + __ldg(p.b1 + c), v1 + __ldg(p.b1 + c + 1));
+    if (r < nv) *reinterpret_cast<float2*>(p.pre + (size_t)(row0 + r) * MLP + c) = pre;
+    *reinterpret_cast<float2*>(PF + r * ldf + c) = make_float2(gelu_exact(pre.x), gelu_exact(pre.y));
   });
-  store_panel(p.pre + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
-  __syncthreads();
-  for (int i = threadIdx.x; i < PR * MLP; i += THREADS) {
-    const int r = i / MLP, c = i - r * MLP;
-    PF[r * ldf + c] = gelu_exact(PF[r * ldf + c]);
-  }
-  __syncthreads();
-  store_panel(p.f + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
+  TK();
+  store_panel<MLP>(p.f + (size_t)row0 * MLP, MLP, PF, ldf, nv);
   // g = f W2^T + b2 + a
-  panel_gemm<1, B_NK, MLP + 4>(PF, p.w2, MLP, 128, MLP, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+  panel_gemm_any<B_NK, MLP + 4, MLP>(PF, p.w2, p.pack, pack_off_w2(MLP), 128 * MLP, MLP, 128, wst, spl, [&](int r, int c, float v0, float v1) {
     const float2 ab = *reinterpret_cast<const float2*>(P1 + r * LD128 + c);
     *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0 + __ldg(p.b2 + c) + ab.x, v1 + __ldg(p.b2 + c + 1) + ab.y);
   });
-  store_panel(p.g + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
+  TK();
+  store_panel<128>(p.g + (size_t)row0 * 128, 128, P0, LD128, nv);
   // y = LNf(g) (+ x)
   panel_layernorm(P0, P2, LD128, p.lnf_w, p.lnf_b, p.epsf, p.meanf, p.rstdf, row0, nv);
   __syncthreads();
@@ -394,8 +651,13 @@ __global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) 
       reinterpret_cast<float4*>(p.y + (size_t)(row0 + r) * 128)[c] = v;
     }
   } else {
-    store_panel(p.y + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
+    store_panel<128>(p.y + (size_t)row0 * 128, 128, P2, LD128, nv);
   }
+  TK();
+  if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("enc_chain_fwd phases (cycles): load %lld | gemm_o %lld | store a, LN2, store h2 %lld | gemm_1 %lld | store f %lld+gemm_2 %lld | LNf, store y %lld\n", tk[1]-tk[0], tk[2]-tk[1], tk[3]-tk[2], tk[4]-tk[3], 0ll, tk[5]-tk[4], tk[6]-tk[5]);
+  }
+#undef TK
 }
 
 // =====================================================================================================================
@@ -408,6 +670,7 @@ struct ChainBwdArgs {
   float* part;                                      // [gridDim.x][4][128]
   unsigned* ticket;
   int M, mlp, add_input;
+  const __nv_bfloat16* pack;
 };
 
 template <int MLP>
@@ -424,32 +687,32 @@ __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) 
   const int row0 = blockIdx.x * PR, nv = min(PR, p.M - row0);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 agf = z4, abf = z4, ag2 = z4, ab2 = z4;
-  load_panel(P0, LD128, p.dy + (size_t)row0 * 128, 128, nv, PR, 128);
-  load_panel(P1, LD128, p.g + (size_t)row0 * 128, 128, nv, PR, 128);
+  load_panel<128>(P0, LD128, p.dy + (size_t)row0 * 128, 128, nv, PR);
+  load_panel<128>(P1, LD128, p.g + (size_t)row0 * 128, 128, nv, PR);
   __syncthreads();
   // dg = LNf'(dy)  -> P2
   panel_layernorm_bwd(P0, P1, P2, nullptr, LD128, p.lnf_w, p.meanf, p.rstdf, row0, nv, agf, abf);
   __syncthreads();
-  store_panel(p.dg + (size_t)row0 * 128, 128, P2, LD128, nv, 128);
+  store_panel<128>(p.dg + (size_t)row0 * 128, 128, P2, LD128, nv);
   // dp = (dg W2) * GELU'(pre)  -> PF        (W2 is [128][mlp]: reduction over its rows)
-  load_panel(PF, ldf, p.pre + (size_t)row0 * MLP, MLP, nv, PR, MLP);
+  load_panel<MLP>(PF, ldf, p.pre + (size_t)row0 * MLP, MLP, nv, PR);
   __syncthreads();
-  panel_gemm<1, B_KN, LD128>(P2, p.w2, MLP, MLP, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+  panel_gemm_any<B_KN, LD128, 128>(P2, p.w2, p.pack, pack_off_w2(MLP), 128 * MLP, MLP, MLP, wst, spl, [&](int r, int c, float v0, float v1) {
     float2* q = reinterpret_cast<float2*>(PF + r * ldf + c);
     const float2 pr = *q;
     *q = make_float2(v0 * gelu_grad(pr.x), v1 * gelu_grad(pr.y));
   });
-  store_panel(p.dp + (size_t)row0 * MLP, MLP, PF, ldf, nv, MLP);
+  store_panel<MLP>(p.dp + (size_t)row0 * MLP, MLP, PF, ldf, nv);
   // dh2 = dp W1  -> P0                       (W1 is [mlp][128])
-  panel_gemm<1, B_KN, MLP + 4>(PF, p.w1, 128, 128, MLP, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+  panel_gemm_any<B_KN, MLP + 4, MLP>(PF, p.w1, p.pack, pack_off_w1(), MLP * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
     *reinterpret_cast<float2*>(P0 + r * LD128 + c) = make_float2(v0, v1);
   });
   // da = dg + LN2'(dh2)  -> P0
-  load_panel(P1, LD128, p.a + (size_t)row0 * 128, 128, nv, PR, 128);
+  load_panel<128>(P1, LD128, p.a + (size_t)row0 * 128, 128, nv, PR);
   __syncthreads();
   panel_layernorm_bwd(P0, P1, P0, P2, LD128, p.ln2_w, p.mean2, p.rstd2, row0, nv, ag2, ab2);
   __syncthreads();
-  store_panel(p.da + (size_t)row0 * 128, 128, P0, LD128, nv, 128);
+  store_panel<128>(p.da + (size_t)row0 * 128, 128, P0, LD128, nv);
   // dxp = da (+ dy: outer residual)
   for (int i = threadIdx.x; i < nv * 32; i += THREADS) {
     const int r = i >> 5, c = i & 31;
@@ -461,15 +724,13 @@ __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) 
     reinterpret_cast<float4*>(p.dxp + (size_t)(row0 + r) * 128)[c] = v;
   }
   // do = da Wo  -> P1                        (Wo is [128][128])
-  panel_gemm<1, B_KN, LD128>(P0, p.wo, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+  panel_gemm_any<B_KN, LD128, 128>(P0, p.wo, p.pack, pack_off_wo(), 128 * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
     *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
   });
-  store_panel(p.dout + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+  store_panel<128>(p.dout + (size_t)row0 * 128, 128, P1, LD128, nv);
   // LayerNorm parameter gradients: block partials, then the last block adds them in order
-  block_colsum128(red, agf);
-  block_colsum128(red + 128, abf);
-  block_colsum128(red + 256, ag2);
-  block_colsum128(red + 384, ab2);
+  const float4 sums[4] = {agf, abf, ag2, ab2};
+  block_colsum128<4>(red, sums);
   for (int i = threadIdx.x; i < 512; i += THREADS) p.part[(size_t)blockIdx.x * 512 + i] = red[i];
   float* outs[4] = {p.dlnf_w, p.dlnf_b, p.dln2_w, p.dln2_b};
   finish_ln_partials(p.part, 4, outs, p.ticket);
@@ -484,6 +745,7 @@ struct ProjBwdArgs {
   float* part;                                      // [nbx][2][128]
   unsigned* ticket;
   int Mx, Mc, nbx;
+  const __nv_bfloat16* pack;
 };
 
 __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
@@ -496,31 +758,31 @@ __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
   float* red = wst + NSTAGE * WT_FLOATS;    // [2][128]
   if ((int)blockIdx.x < p.nbx) {
     const int row0 = blockIdx.x * PR, nv = min(PR, p.Mx - row0);
-    load_panel(P0, LD128, p.dq + (size_t)row0 * 128, 128, nv, PR, 128);
+    load_panel<128>(P0, LD128, p.dq + (size_t)row0 * 128, 128, nv, PR);
     __syncthreads();
     // dh1 = dq Wq  -> P1
-    panel_gemm<1, B_KN, LD128>(P0, p.wq, 128, 128, 128, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+    panel_gemm_any<B_KN, LD128, 128>(P0, p.wq, p.pack, pack_off_wq(), 128 * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
-    load_panel(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR, 128);
-    load_panel(P2, LD128, p.dxp + (size_t)row0 * 128, 128, nv, PR, 128);
+    load_panel<128>(P0, LD128, p.x + (size_t)row0 * 128, 128, nv, PR);
+    load_panel<128>(P2, LD128, p.dxp + (size_t)row0 * 128, 128, nv, PR);
     __syncthreads();
     float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
     panel_layernorm_bwd(P1, P0, P1, P2, LD128, p.ln_w, p.mean1, p.rstd1, row0, nv, ag, ab);
     __syncthreads();
-    store_panel(p.dx + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
-    block_colsum128(red, ag);
-    block_colsum128(red + 128, ab);
+    store_panel<128>(p.dx + (size_t)row0 * 128, 128, P1, LD128, nv);
+    const float4 sums[2] = {ag, ab};
+    block_colsum128<2>(red, sums);
     for (int i = threadIdx.x; i < 256; i += THREADS) p.part[(size_t)blockIdx.x * 256 + i] = red[i];
   } else {
     const int row0 = (blockIdx.x - p.nbx) * PR, nv = min(PR, p.Mc - row0);
-    load_panel(P0, 260, p.dkv + (size_t)row0 * 256, 256, nv, PR, 256);
+    load_panel<256>(P0, 260, p.dkv + (size_t)row0 * 256, 256, nv, PR);
     __syncthreads();
     // dctx = dkv Wkv                          (Wkv is [256][128])
-    panel_gemm<1, B_KN, 260>(P0, p.wkv, 128, 128, 256, 1 << 30, wst, spl, [&](int r, int c, float v0, float v1) {
+    panel_gemm_any<B_KN, 260, 256>(P0, p.wkv, p.pack, pack_off_wkv(), 256 * 128, 128, 128, wst, spl, [&](int r, int c, float v0, float v1) {
       *reinterpret_cast<float2*>(P1 + r * LD128 + c) = make_float2(v0, v1);
     });
-    store_panel(p.dctx + (size_t)row0 * 128, 128, P1, LD128, nv, 128);
+    store_panel<128>(p.dctx + (size_t)row0 * 128, 128, P1, LD128, nv);
   }
   // every block takes part in the rendezvous; only the x blocks hold partials
   if (!last_block_arrives(p.ticket, gridDim.x)) return;
@@ -652,12 +914,30 @@ int tmf_encoder_supported(int dim, int inner, int mlp) {
   return (dim == 128 && inner == 128 && (mlp == 128 || mlp == 256 || mlp == 512)) ? 1 : 0;
 }
 
+size_t tmf_encoder_pack_bytes(int mlp) { return pack_elems(mlp) * sizeof(__nv_bfloat16); }
+
+int tmf_encoder_pack_weights(const float* wq, const float* wkv, const float* wo, const float* w1, const float* w2, int mlp,
+                             void* pack, void* stream) {
+  TMF_REQUIRE(wq && wkv && wo && w1 && w2 && pack, "encoder_pack_weights: NULL pointer");
+  TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_pack_weights: mlp_dim %d not supported", mlp);
+  TMF_REQUIRE(((uintptr_t)pack & 15) == 0, "encoder_pack_weights: pack must be 16-byte aligned");
+  PackArgs p{};
+  const float* w[5] = {wq, wkv, wo, w1, w2};
+  const int numel[5] = {128 * 128, 256 * 128, 128 * 128, mlp * 128, 128 * mlp};
+  const size_t off[5] = {pack_off_wq(), pack_off_wkv(), pack_off_wo(), pack_off_w1(), pack_off_w2(mlp)};
+  for (int i = 0; i < 5; ++i) { p.w[i] = w[i]; p.numel[i] = numel[i]; p.off[i] = off[i]; }
+  p.pack = (__nv_bfloat16*)pack;
+  enc_pack_kernel<<<dim3(16, 5), 256, 0, (cudaStream_t)stream>>>(p);
+  TMF_LAUNCH_CHECK();
+  return 0;
+}
+
 int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, const float* ln_b, const float* wq,
                          const float* wkv, float* h1, float* mean1, float* rstd1, float* q, float* kv, int Mx, int Mc,
-                         float eps, void* stream) {
+                         float eps, const void* pack, void* stream) {
   TMF_REQUIRE(x && ctx && ln_w && ln_b && wq && wkv && h1 && mean1 && rstd1 && q && kv, "encoder_proj_fwd: NULL pointer");
   TMF_REQUIRE(Mx > 0 && Mc > 0, "encoder_proj_fwd: empty input");
-  ProjFwdArgs p{x, ctx, ln_w, ln_b, wq, wkv, h1, mean1, rstd1, q, kv, Mx, Mc, ceil_div(Mx, PR), eps};
+  ProjFwdArgs p{x, ctx, ln_w, ln_b, wq, wkv, h1, mean1, rstd1, q, kv, Mx, Mc, ceil_div(Mx, PR), eps, (const __nv_bfloat16*)pack};
   const size_t smem = sizeof(float) * (PR * LD128 + PR * 260 + 2 * PR * LD128 + NSTAGE * WT_FLOATS);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_proj_fwd_kernel, smem)) return 2; done = true; }
@@ -670,12 +950,17 @@ int tmf_encoder_chain_fwd(const float* o, const float* x, const float* wo, const
                           const float* ln2_b, const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* lnf_w, const float* lnf_b, float* a, float* h2, float* mean2, float* rstd2,
                           float* pre, float* f, float* g, float* meanf, float* rstdf, float* y, int M, int mlp,
-                          int add_input, float eps2, float epsf, void* stream) {
+                          int add_input, float eps2, float epsf, const void* pack, void* stream) {
   TMF_REQUIRE(o && x && wo && bo && ln2_w && ln2_b && w1 && b1 && w2 && b2 && lnf_w && lnf_b && a && h2 && mean2 && rstd2 &&
                   pre && f && g && meanf && rstdf && y, "encoder_chain_fwd: NULL pointer");
   TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_chain_fwd: mlp_dim %d not supported", mlp);
+  {
+    const int on = getenv("TMF_ENC_PROF") != nullptr ? 1 : 0;
+    static int cur = -1;
+    if (on != cur) { cudaMemcpyToSymbol(g_enc_prof, &on, sizeof(int)); cur = on; }
+  }
   ChainFwdArgs p{o, x, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf, y,
-                 M, mlp, add_input, eps2, epsf};
+                 M, mlp, add_input, getenv("TMF_ENC_PROF") != nullptr ? 1 : 0, eps2, epsf, (const __nv_bfloat16*)pack};
   const size_t smem = sizeof(float) * (3 * PR * LD128 + 3 * PR * (mlp + 4) + NSTAGE * WT_FLOATS);
 #define TMF_LAUNCH_CHAIN_FWD(MLPV)                                                                                 \
   do {                                                                                                            \
@@ -695,7 +980,7 @@ int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const
                           const float* w1, const float* w2, const float* ln2_w, const float* lnf_w, const float* mean2,
                           const float* rstd2, const float* meanf, const float* rstdf, float* dg, float* dp, float* da,
                           float* dout, float* dxp, float* dlnf_w, float* dlnf_b, float* dln2_w, float* dln2_b, int M,
-                          int mlp, int add_input, void* ws, size_t ws_bytes, void* stream) {
+                          int mlp, int add_input, const void* pack, void* ws, size_t ws_bytes, void* stream) {
   TMF_REQUIRE(dy && g && a && pre && wo && w1 && w2 && ln2_w && lnf_w && mean2 && rstd2 && meanf && rstdf && dg && dp && da &&
                   dout && dxp && dlnf_w && dlnf_b && dln2_w && dln2_b, "encoder_chain_bwd: NULL pointer");
   TMF_REQUIRE(tmf_encoder_supported(128, 128, mlp), "encoder_chain_bwd: mlp_dim %d not supported", mlp);
@@ -703,7 +988,7 @@ int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const
   const int nb = ceil_div(M, PR);
   TMF_REQUIRE((size_t)nb * 512 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_chain_bwd: too many rows");
   ChainBwdArgs p{dy, g, a, pre, wo, w1, w2, ln2_w, lnf_w, mean2, rstd2, meanf, rstdf, dg, dp, da, dout, dxp,
-                 dlnf_w, dlnf_b, dln2_w, dln2_b, enc_partials(ws), enc_tickets(ws, 0), M, mlp, add_input};
+                 dlnf_w, dlnf_b, dln2_w, dln2_b, enc_partials(ws), enc_tickets(ws, 0), M, mlp, add_input, (const __nv_bfloat16*)pack};
   const size_t smem = sizeof(float) * (3 * PR * LD128 + 3 * PR * (mlp + 4) + NSTAGE * WT_FLOATS + 512);
 #define TMF_LAUNCH_CHAIN_BWD(MLPV)                                                                                 \
   do {                                                                                                            \
@@ -721,12 +1006,12 @@ int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const
 
 int tmf_encoder_proj_bwd(const float* dq, const float* dkv, const float* dxp, const float* x, const float* ln_w,
                          const float* mean1, const float* rstd1, const float* wq, const float* wkv, float* dx, float* dctx,
-                         float* dln_w, float* dln_b, int Mx, int Mc, void* ws, size_t ws_bytes, void* stream) {
+                         float* dln_w, float* dln_b, int Mx, int Mc, const void* pack, void* ws, size_t ws_bytes, void* stream) {
   TMF_REQUIRE(dq && dkv && dxp && x && ln_w && mean1 && rstd1 && wq && wkv && dx && dctx && dln_w && dln_b,
               "encoder_proj_bwd: NULL pointer");
   if (enc_check_ws("encoder_proj_bwd", ws, ws_bytes)) return 1;
   ProjBwdArgs p{dq, dkv, dxp, x, ln_w, mean1, rstd1, wq, wkv, dx, dctx, dln_w, dln_b, enc_partials(ws), enc_tickets(ws, 1),
-                Mx, Mc, ceil_div(Mx, PR)};
+                Mx, Mc, ceil_div(Mx, PR), (const __nv_bfloat16*)pack};
   TMF_REQUIRE((size_t)p.nbx * 256 * sizeof(float) <= TMF_WS_BYTES - TMF_WS_TICKET_BYTES, "encoder_proj_bwd: too many rows");
   const size_t smem = sizeof(float) * (PR * 260 + 2 * PR * LD128 + 2 * PR * 260 + NSTAGE * WT_FLOATS + 256);
   static bool done = false;

@@ -530,8 +530,14 @@ class EncoderFunction(torch.autograd.Function):
         dev = x3.device
         E = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         h1, mean1, rstd1, q, kv = E(Mx, dim), E(Mx), E(Mx), E(B, Nq, dim), E(B, Nk, 2 * dim)
+        # bf16 hi / lo copies of the five weight matrices for the split-weight GEMMs (one launch; the backward pass reuses
+        # them).  TMF_ENC_BF16=0: three-pass TF32 straight from the fp32 weights (pack = NULL).
+        pack = None
+        if os.environ.get("TMF_ENC_BF16", "1") != "0":
+            pack = torch.empty(int(L.load().tmf_encoder_pack_bytes(int(mlp))) // 2, dtype=torch.bfloat16, device=dev)
+            L.call("tmf_encoder_pack_weights", L.ptr(wq), L.ptr(wkv), L.ptr(wo), L.ptr(w1), L.ptr(w2), mlp, L.ptr(pack))
         L.call("tmf_encoder_proj_fwd", L.ptr(x3), L.ptr(c3), L.ptr(ln1_w), L.ptr(ln1_b), L.ptr(wq), L.ptr(wkv), L.ptr(h1),
-               L.ptr(mean1), L.ptr(rstd1), L.ptr(q), L.ptr(kv), Mx, Mc, float(eps1))
+               L.ptr(mean1), L.ptr(rstd1), L.ptr(q), L.ptr(kv), Mx, Mc, float(eps1), L.ptr(pack))
         o, lse = E(B, Nq, dim), E(B, heads, Nq)
         L.call("tmf_attn_fwd", L.ptr(q), L.ptr(kv), L.ptr(o), L.ptr(lse), B, Nq, Nk, heads, dim // heads, float(scale))
         a, h2, mean2, rstd2, pre, f, g = E(Mx, dim), E(Mx, dim), E(Mx), E(Mx), E(Mx, mlp), E(Mx, mlp), E(Mx, dim)
@@ -539,9 +545,10 @@ class EncoderFunction(torch.autograd.Function):
         L.call("tmf_encoder_chain_fwd", L.ptr(o), L.ptr(x3), L.ptr(wo), L.ptr(bo), L.ptr(ln2_w), L.ptr(ln2_b), L.ptr(w1),
                L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(lnf_w), L.ptr(lnf_b), L.ptr(a), L.ptr(h2), L.ptr(mean2), L.ptr(rstd2),
                L.ptr(pre), L.ptr(f), L.ptr(g), L.ptr(meanf), L.ptr(rstdf), L.ptr(y), Mx, mlp, int(add_input), float(eps2),
-               float(epsf))
+               float(epsf), L.ptr(pack))
         ctx.save_for_backward(x3, c3, h1, mean1, rstd1, q, kv, o, lse, a, h2, mean2, rstd2, pre, f, g, meanf, rstdf,
                               ln1_w, wq, wkv, wo, ln2_w, w1, w2, lnf_w)
+        ctx.pack = pack
         ctx.param_refs = params                              # references only: gradient slots of the flat DP buffer
         ctx.cfg = (heads, float(scale), bool(add_input), B, Nq, Nk, dim, mlp)
         return y.reshape(x.shape)
@@ -563,13 +570,14 @@ class EncoderFunction(torch.autograd.Function):
         L.call("tmf_encoder_chain_bwd", L.ptr(dy2), L.ptr(g), L.ptr(a), L.ptr(pre), L.ptr(wo), L.ptr(w1), L.ptr(w2), L.ptr(ln2_w),
                L.ptr(lnf_w), L.ptr(mean2), L.ptr(rstd2), L.ptr(meanf), L.ptr(rstdf), L.ptr(dg), L.ptr(dp), L.ptr(da),
                L.ptr(dout), L.ptr(dxp), L.ptr(d_lnf_w), L.ptr(d_lnf_b), L.ptr(d_ln2_w), L.ptr(d_ln2_b), Mx, mlp,
-               int(add_input), L.ptr(ws), nws)
+               int(add_input), L.ptr(ctx.pack), L.ptr(ws), nws)
         dq, dkv = E(B, Nq, dim), E(B, Nk, 2 * dim)
         L.call("tmf_attn_bwd", L.ptr(dout), L.ptr(q), L.ptr(kv), L.ptr(o), L.ptr(lse), L.ptr(dq), L.ptr(dkv), B, Nq, Nk, heads,
                dim // heads, scale)
         dx, dctx = E(B, Nq, dim), E(B, Nk, dim)
         L.call("tmf_encoder_proj_bwd", L.ptr(dq), L.ptr(dkv), L.ptr(dxp), L.ptr(x3), L.ptr(ln1_w), L.ptr(mean1), L.ptr(rstd1),
-               L.ptr(wq), L.ptr(wkv), L.ptr(dx), L.ptr(dctx), L.ptr(d_ln1_w), L.ptr(d_ln1_b), Mx, Mc, L.ptr(ws), nws)
+               L.ptr(wq), L.ptr(wkv), L.ptr(dx), L.ptr(dctx), L.ptr(d_ln1_w), L.ptr(d_ln1_b), Mx, Mc, L.ptr(ctx.pack),
+               L.ptr(ws), nws)
         table = (ctypes_ptr_array([dq, h1, d_wq, dkv, c3, d_wkv, da, o, d_wo, d_bo, dp, h2, d_w1, d_b1, dg]))
         if os.environ.get("TMF_ENC_SIDE", "1") != "0":
             # all five weight gradients feed nothing downstream in this backward pass: off the critical path
