@@ -52,6 +52,10 @@ int tmf_version(void);
 int tmf_check_device(void);
 /* number of kernel launches issued through this library by the calling process so far */
 int64_t tmf_launch_count(void);
+/* programmatic dependent launch of the train-step kernels (default off; TMF_PDL=1 in the environment turns it on): each
+ * kernel waits for its stream predecessors before its first global access, so results are identical either way */
+int tmf_set_pdl(int on);
+int tmf_get_pdl(void);
 /* TMF_STAT_ROWS, for callers that size statistics buffers without the header */
 int tmf_stat_rows(void);
 

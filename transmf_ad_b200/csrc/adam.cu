@@ -39,6 +39,7 @@ __device__ __forceinline__ void emit_pack(const AdamChunk& c, int i, float val) 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __restrict__ chunks, const float* __restrict__ lr_dev,
                                                          float b1, float b2, float eps, float wd, float* step_dev,
                                                          unsigned* ticket) {
+  pdl_entry();
   const AdamChunk c = chunks[blockIdx.x];
   const float t = step_dev[0] + 1.f;              // step_dev is only advanced after every block has read it (ticket below)
   const float lr = lr_dev[0];
@@ -100,7 +101,7 @@ int tmf_adam_step(const void* chunks, int nchunks, const float* lr_dev, float be
               "adam_step: NULL device pointer");
   TMF_REQUIRE(nchunks > 0, "adam_step: empty chunk table");
   TMF_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_step: bad hyper-parameters");
-  adam_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, lr_dev, beta1, beta2, eps,
+  launch_k(adam_multi_kernel, nchunks, 256, 0, (cudaStream_t)stream, (const AdamChunk*)chunks, lr_dev, beta1, beta2, eps,
                                                                weight_decay, step_dev, (unsigned*)ticket_dev);
   TMF_LAUNCH_CHECK();
   return 0;

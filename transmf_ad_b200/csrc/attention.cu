@@ -64,6 +64,7 @@ __device__ __forceinline__ void stage_rows_t(float* dst, const float* src, int64
 // ---------------------------------------------------------------------------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(TA_THREADS) attn_tiled_fwd_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   constexpr int Np = 32 * NPL;
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_fwd_kernel(AttnArgs p) 
 // ---------------------------------------------------------------------------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dq_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   constexpr int Np = 32 * NPL;
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dq_kernel(AttnArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(TA_THREADS) attn_tiled_dkv_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   constexpr int Np = 32 * NPL;
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
@@ -325,7 +328,7 @@ static bool tiled_enabled() {
 template <typename K>
 static int launch_tiled(K kernel, const AttnArgs& p, dim3 grid, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel<<<grid, TA_THREADS, smem, st>>>(p);
+  launch_k(kernel, grid, TA_THREADS, smem, st, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }

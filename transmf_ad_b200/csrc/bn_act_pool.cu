@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) bn_finalize_kernel(GroupPtr<co
                                    GroupPtr<const float> beta, GroupPtr<float> rmean, GroupPtr<float> rvar,
                                    GroupPtr<int64_t> nbt, GroupPtr<float> coef, int C, double count, float momentum,
                                    float eps, int training) {
+  pdl_entry();
   const int g = blockIdx.z;
   double t1, t2;
   sum_stat_rows(stats.p[g], C, training != 0, t1, t2);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) bn_finalize_kernel(GroupPtr<co
 __global__ void __launch_bounds__(32 * FIN_WARPS) bn_bwd_finalize_kernel(GroupPtr<const double> sums, GroupPtr<const float> coef, GroupPtr<float> dgamma,
                                        GroupPtr<float> dbeta, GroupPtr<float> dbias, GroupPtr<float> bcoef, int C,
                                        double count, int training) {
+  pdl_entry();
   const int g = blockIdx.z;
   double s1, s2;
   sum_stat_rows(sums.p[g], C, true, s1, s2);
@@ -140,6 +142,7 @@ __device__ __forceinline__ void store8f(void* base, int64_t elem_off, int fp32, 
 // block 1 re-read 925 MB per step for two per-channel sums.
 template <bool KEEP>
 __global__ void __launch_bounds__(256, KEEP ? 3 : 4) bn_act_pool_fwd_kernel(ActPoolArgs p) {
+  pdl_entry();
   const int g = blockIdx.z;
   const int CQ = p.C >> 3;
   const __nv_bfloat16* yg = p.y.p[g];
@@ -249,6 +252,7 @@ __device__ __forceinline__ void block_channel_sums(float* red, double* rows, int
 //    A = scale*(m2*invstd*mean - m1),  Bc = -scale*m2*invstd.
 template <bool APPLY, int POOL>
 __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_pool_bwd_kernel(ActPoolArgs p) {
+  pdl_entry();
   const int g = blockIdx.z;
   extern __shared__ float red[];  // [16][256] (REDUCE only)
   const int CQ = p.C >> 3;
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
 // Max-pool backward reduction from ymax (see bn_act_pool_fwd_kernel<true>): sum dz, sum dz*xhat over the pooled
 // positions;  dz = dout * LeakyReLU'(scale*ymax + shift),  xhat = (ymax - mean) * invstd.
 __global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
+  pdl_entry();
   const int g = blockIdx.z;
   extern __shared__ float red[];  // [16][256]
   const int CQ = p.C >> 3;
@@ -418,9 +423,9 @@ __global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_reduce_kept_kernel(ActP
 
 template <bool APPLY>
 static void launch_bwd(const ActPoolArgs& p, dim3 grid, size_t smem, cudaStream_t st) {
-  if (p.pool == TMF_POOL_MAX) bn_act_pool_bwd_kernel<APPLY, TMF_POOL_MAX><<<grid, 256, smem, st>>>(p);
-  else if (p.pool == TMF_POOL_AVG) bn_act_pool_bwd_kernel<APPLY, TMF_POOL_AVG><<<grid, 256, smem, st>>>(p);
-  else bn_act_pool_bwd_kernel<APPLY, TMF_POOL_NONE><<<grid, 256, smem, st>>>(p);
+  if (p.pool == TMF_POOL_MAX) launch_k(bn_act_pool_bwd_kernel<APPLY, TMF_POOL_MAX>, grid, 256, smem, st, p);
+  else if (p.pool == TMF_POOL_AVG) launch_k(bn_act_pool_bwd_kernel<APPLY, TMF_POOL_AVG>, grid, 256, smem, st, p);
+  else launch_k(bn_act_pool_bwd_kernel<APPLY, TMF_POOL_NONE>, grid, 256, smem, st, p);
 }
 
 static int fill_args(ActPoolArgs& p, int B, int D, int H, int W, int C, int pool, float slope, int fp32io) {
@@ -483,7 +488,7 @@ int tmf_bn_finalize(int ng, const double* const* stats, const float* const* gamm
     return 1;
   TMF_REQUIRE(count > 0, "bn_finalize: count must be positive");
   dim3 grid(ceil_div(C, 32), 1, ng);
-  bn_finalize_kernel<<<grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream>>>(gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
+  launch_k(bn_finalize_kernel, grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream, gs, gg, gb, grm, grv, gn, gc, C, (double)count, momentum,
                                                              eps, training);
   TMF_LAUNCH_CHECK();
   return 0;
@@ -498,7 +503,7 @@ int tmf_bn_act_pool_fwd(int ng, const void* const* y, const float* const* coef, 
       !load_group(p.out, (void* const*)out, ng, true, "out"))
     return 1;
   dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 8, &p.nch, &p.hcr), 1, ng);
-  bn_act_pool_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  launch_k(bn_act_pool_fwd_kernel<false>, grid, 256, 0, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -514,7 +519,7 @@ int tmf_bn_act_pool_fwd_keepmax(int ng, const void* const* y, const float* const
       !load_group(p.ymax, (__nv_bfloat16* const*)ymax, ng, true, "ymax"))
     return 1;
   dim3 grid(plan_units(B, p.Do, p.Ho, 148 * 8, &p.nch, &p.hcr), 1, ng);
-  bn_act_pool_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  launch_k(bn_act_pool_fwd_kernel<true>, grid, 256, 0, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -537,7 +542,7 @@ int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp3
   if (blocks > 148) blocks = 148;                                  // one statistics row per block (<= TMF_STAT_ROWS); with two
                                                                    // towers that is 2 blocks of <= 128 registers per SM
   if (blocks < 1) blocks = 1;
-  bn_maxpool_bwd_reduce_kept_kernel<<<dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st>>>(p, (int)npos);
+  launch_k(bn_maxpool_bwd_reduce_kept_kernel, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -570,7 +575,7 @@ int tmf_bn_bwd_finalize(int ng, const double* const* sums, const float* const* c
       !load_group(gdbias, dbias, ng, false, "dbias") || !load_group(gbc, bcoef, ng, true, "bcoef"))
     return 1;
   dim3 grid(ceil_div(C, 32), 1, ng);
-  bn_bwd_finalize_kernel<<<grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream>>>(gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
+  launch_k(bn_bwd_finalize_kernel, grid, 32 * FIN_WARPS, 0, (cudaStream_t)stream, gs, gc, gdg, gdb, gdbias, gbc, C, (double)count,
                                                                  training);
   TMF_LAUNCH_CHECK();
   return 0;

@@ -50,6 +50,7 @@ struct alignas(64) C1BParams {
 // fp32 image (B*D*H rows of W) -> six bf16 rows of pitch P per image row: x6[row][hl*3+kw][k] = hl-part of x[k+kw-1]
 // (zero outside [0,W)); hl = 0: bf16(x), hl = 1: bf16(x - bf16(x)).
 __global__ void conv1_split_x_kernel(GroupPtr<const float> x, GroupPtr<__nv_bfloat16> x6, int rows, int W, int P) {
+  pdl_entry();
   const int g = blockIdx.z;
   const int chunks = P >> 3;
   const unsigned total = (unsigned)rows * (unsigned)chunks;
@@ -74,6 +75,7 @@ __global__ void conv1_split_x_kernel(GroupPtr<const float> x, GroupPtr<__nv_bflo
 }
 
 __global__ void __launch_bounds__(C1B_THREADS, 1) conv1_bwd_fused_kernel(const __grid_constant__ C1BParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(C1B_THREADS, 1) conv1_bwd_fused_kernel(const _
 
 // dw[co][tap] = sum over CTAs of part[cta][co*27+tap], fixed order
 __global__ void conv1_bwd_reduce_kernel(GroupPtr<const float> part, GroupPtr<float> dw, int ncta) {
+  pdl_entry();
   const int g = blockIdx.z;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 32 * 27) return;
@@ -467,7 +470,7 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
     const int rows = B * D * H;
     const long long total = (long long)rows * (pl.P / 8);
     dim3 grid((unsigned)min((long long)148 * 8, (total + 255) / 256), 1, ng);
-    conv1_split_x_kernel<<<grid, 256, 0, st>>>(gx, gx6, rows, W, pl.P);
+    launch_k(conv1_split_x_kernel, grid, 256, 0, st, gx, gx6, rows, W, pl.P);
     TMF_LAUNCH_CHECK();
   }
   static bool attr_done = false;
@@ -475,9 +478,9 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
     TMF_CUDA(cudaFuncSetAttribute(conv1_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  conv1_bwd_fused_kernel<<<dim3(pl.ncta * ng), C1B_THREADS, pl.smem_bytes, st>>>(p);
+  launch_k(conv1_bwd_fused_kernel, dim3(pl.ncta * ng), C1B_THREADS, pl.smem_bytes, st, p);
   TMF_LAUNCH_CHECK();
-  conv1_bwd_reduce_kernel<<<dim3(ceil_div(32 * 27, 256), 1, ng), 256, 0, st>>>(gpart, gdw, pl.ncta);
+  launch_k(conv1_bwd_reduce_kernel, dim3(ceil_div(32 * 27, 256), 1, ng), 256, 0, st, gpart, gdw, pl.ncta);
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -67,6 +67,7 @@ __device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
 // !STAGED keeps the direct loads for images whose base address is not 16-byte aligned or whose rows are too wide.
 template <int NCH, bool STAGED>
 __global__ void __launch_bounds__(C1U_THREADS, 1) conv1_umma_fwd_kernel(const __grid_constant__ C1UParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -458,6 +459,7 @@ struct alignas(64) C1WParams {
 };
 
 __global__ void __launch_bounds__(C1W_U_THREADS, 1) conv1_umma_wgrad_kernel(const __grid_constant__ C1WParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -608,6 +610,7 @@ __global__ void __launch_bounds__(C1W_U_THREADS, 1) conv1_umma_wgrad_kernel(cons
 }
 
 __global__ void conv1_wgrad_reduce_kernel(GroupPtr<const float> part, GroupPtr<float> dw, int ncta, int n) {
+  pdl_entry();
   const int g = blockIdx.z;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -672,10 +675,10 @@ int tmf_conv1_fwd_umma(int ng, const float* const* x, const float* const* w, con
   if (per_group < 1) per_group = 1;
   if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;
   const dim3 grid(per_group * ng);
-  if (cout == 32 && staged) conv1_umma_fwd_kernel<1, true><<<grid, C1U_THREADS, smem, st>>>(p);
-  else if (cout == 32) conv1_umma_fwd_kernel<1, false><<<grid, C1U_THREADS, smem, st>>>(p);
-  else if (staged) conv1_umma_fwd_kernel<2, true><<<grid, C1U_THREADS, smem, st>>>(p);
-  else conv1_umma_fwd_kernel<2, false><<<grid, C1U_THREADS, smem, st>>>(p);
+  if (cout == 32 && staged) launch_k(conv1_umma_fwd_kernel<1, true>, grid, C1U_THREADS, smem, st, p);
+  else if (cout == 32) launch_k(conv1_umma_fwd_kernel<1, false>, grid, C1U_THREADS, smem, st, p);
+  else if (staged) launch_k(conv1_umma_fwd_kernel<2, true>, grid, C1U_THREADS, smem, st, p);
+  else launch_k(conv1_umma_fwd_kernel<2, false>, grid, C1U_THREADS, smem, st, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -745,12 +748,12 @@ int tmf_conv1_wgrad_umma(int ng, const void* const* dy, const float* const* x, f
   if (per_group > p.ntiles) per_group = p.ntiles;
   if (per_group > 148) per_group = 148;
   if (per_group < 1) per_group = 1;
-  conv1_umma_wgrad_kernel<<<dim3(per_group * ng), C1W_U_THREADS, smem, st>>>(p);
+  launch_k(conv1_umma_wgrad_kernel, dim3(per_group * ng), C1W_U_THREADS, smem, st, p);
   TMF_LAUNCH_CHECK();
   GroupPtr<const float> gpart;
   GroupPtr<float> gdw;
   for (int g = 0; g < TMF_MAX_GROUPS; ++g) { gpart.p[g] = g < ng ? p.part[g] : nullptr; gdw.p[g] = g < ng ? dw[g] : nullptr; }
-  conv1_wgrad_reduce_kernel<<<dim3(ceil_div(27 * cout, 128), 1, ng), 128, 0, st>>>(gpart, gdw, per_group, 27 * cout);
+  launch_k(conv1_wgrad_reduce_kernel, dim3(ceil_div(27 * cout, 128), 1, ng), 128, 0, st, gpart, gdw, per_group, 27 * cout);
   TMF_LAUNCH_CHECK();
   return 0;
 }

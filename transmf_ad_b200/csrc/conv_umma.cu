@@ -62,6 +62,7 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
 // stage s always belongs to issuer s % 2: SB is even), each into its own TMEM accumulator; the epilogue adds the two.
 template <int KSTEPS, int KS, bool RES, int NISS>
 __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const __grid_constant__ UmmaConvParams p) {
+  pdl_entry();
   static_assert(NISS == 1 || !RES, "two issuers only with the streamed weight ring");
   constexpr int NTHREADS = 32 * (5 + NISS);
   constexpr int EPI0 = 32 * (1 + NISS);             // first epilogue thread
@@ -520,6 +521,9 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                         void* const* y, double* const* stats, int B, int D, int H, int W, int cin, int cout, int ksize,
                         void* stream) {
   TMF_CHECK_NG(ng);
+  // A 1x1x1 convolution is a plain GEMM over the B*D*H*W voxel rows: drop the plane structure (one "plane" of M rows of
+  // width 1) so that every 128-row tile is full -- conv4.3: 99 tiles per tower instead of 176 tiles of 143 valid rows.
+  if (ksize == 1 && (int64_t)B * D * H * W < (1ll << 31)) { H = B * D * H * W; B = 1; D = 1; W = 1; }
   const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize, B, ng);
   TMF_REQUIRE(pl.ok, "conv3d_fwd_umma: unsupported problem");
   EncodeTiledFn encode = get_encode_fn();
@@ -589,7 +593,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UC_SMEM_BUDGET));            \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    conv3d_umma_kernel<KST, KSZ, RES, NI><<<grid, 32 * (5 + NI), pl.smem_bytes, st>>>(p);                          \
+    launch_k(conv3d_umma_kernel<KST, KSZ, RES, NI>, grid, 32 * (5 + NI), pl.smem_bytes, st, p);                          \
   } while (0)
   if (ksteps == 4 && ksize == 3 && pl.b_resident) TMF_LAUNCH_CONV(4, 3, true, 1);
   else if (ksteps == 4 && ksize == 3 && pl.niss == 2) TMF_LAUNCH_CONV(4, 3, false, 2);

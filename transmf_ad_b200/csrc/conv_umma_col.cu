@@ -76,6 +76,7 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
 // KSTEPS = Cin / 16 (2 or 4)
 template <int KSTEPS>
 __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __grid_constant__ ColConvParams p) {
+  pdl_entry();
   constexpr uint32_t PITCH = KSTEPS * 32u;          // bytes per smem row (= Cin * 2)
   constexpr uint32_t ROW_UNITS = PITCH >> 4;
   constexpr uint32_t SBO = 8u * PITCH;
@@ -515,7 +516,7 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
                                     (int)CC_SMEM_BUDGET));                                                              \
       attr_done = true;                                                                                                 \
     }                                                                                                                   \
-    conv3d_umma_col_kernel<KST><<<grid, CC_THREADS, pl.smem_bytes, st>>>(p);                                            \
+    launch_k(conv3d_umma_col_kernel<KST>, grid, CC_THREADS, pl.smem_bytes, st, p);                                            \
   } while (0)
   if (cin == 32) TMF_LAUNCH_COL(2);
   else TMF_LAUNCH_COL(4);

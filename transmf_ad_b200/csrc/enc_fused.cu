@@ -428,6 +428,7 @@ struct PackArgs {
   __nv_bfloat16* pack;
 };
 __global__ void __launch_bounds__(256) enc_pack_kernel(PackArgs p) {
+  pdl_entry();
   const int m = blockIdx.y;
   const float4* src = reinterpret_cast<const float4*>(p.w[m]);
   uint2* hi = reinterpret_cast<uint2*>(p.pack + p.off[m]);
@@ -557,6 +558,7 @@ struct ProjFwdArgs {
 };
 
 __global__ void __launch_bounds__(THREADS) enc_proj_fwd_kernel(ProjFwdArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* P0 = sm;                           // [16][132] input panel
   float* P1 = P0 + PR * LD128;              // [16][260] output panel
@@ -597,6 +599,7 @@ struct ChainFwdArgs {
 
 template <int MLP>
 __global__ void __launch_bounds__(THREADS) enc_chain_fwd_kernel(ChainFwdArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   constexpr int ldf = MLP + 4;
   float* P0 = sm;                           // o, later g
@@ -675,6 +678,7 @@ struct ChainBwdArgs {
 
 template <int MLP>
 __global__ void __launch_bounds__(THREADS) enc_chain_bwd_kernel(ChainBwdArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   constexpr int ldf = MLP + 4;
   float* P0 = sm;
@@ -749,6 +753,7 @@ struct ProjBwdArgs {
 };
 
 __global__ void __launch_bounds__(THREADS) enc_proj_bwd_kernel(ProjBwdArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* P0 = sm;                           // [16][260]
   float* P1 = P0 + PR * 260;                // [16][132]
@@ -816,6 +821,7 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(THREADS) enc_wgrad_kernel(WgradArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* At = sm;                           // [32][WG_LDA]: dY^T chunk
   float* wst = At + 32 * WG_LDA;
@@ -927,7 +933,7 @@ int tmf_encoder_pack_weights(const float* wq, const float* wkv, const float* wo,
   const size_t off[5] = {pack_off_wq(), pack_off_wkv(), pack_off_wo(), pack_off_w1(), pack_off_w2(mlp)};
   for (int i = 0; i < 5; ++i) { p.w[i] = w[i]; p.numel[i] = numel[i]; p.off[i] = off[i]; }
   p.pack = (__nv_bfloat16*)pack;
-  enc_pack_kernel<<<dim3(16, 5), 256, 0, (cudaStream_t)stream>>>(p);
+  launch_k(enc_pack_kernel, dim3(16, 5), 256, 0, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -941,7 +947,7 @@ int tmf_encoder_proj_fwd(const float* x, const float* ctx, const float* ln_w, co
   const size_t smem = sizeof(float) * (PR * LD128 + PR * 260 + 2 * PR * LD128 + NSTAGE * WT_FLOATS);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_proj_fwd_kernel, smem)) return 2; done = true; }
-  enc_proj_fwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  launch_k(enc_proj_fwd_kernel, p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -966,7 +972,7 @@ int tmf_encoder_chain_fwd(const float* o, const float* x, const float* wo, const
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) { if (set_smem((const void*)enc_chain_fwd_kernel<MLPV>, smem)) return 2; done = true; }            \
-    enc_chain_fwd_kernel<MLPV><<<ceil_div(M, PR), THREADS, smem, (cudaStream_t)stream>>>(p);                      \
+    launch_k(enc_chain_fwd_kernel<MLPV>, ceil_div(M, PR), THREADS, smem, (cudaStream_t)stream, p);                      \
   } while (0)
   if (mlp == 128) TMF_LAUNCH_CHAIN_FWD(128);
   else if (mlp == 256) TMF_LAUNCH_CHAIN_FWD(256);
@@ -994,7 +1000,7 @@ int tmf_encoder_chain_bwd(const float* dy, const float* g, const float* a, const
   do {                                                                                                            \
     static bool done = false;                                                                                     \
     if (!done) { if (set_smem((const void*)enc_chain_bwd_kernel<MLPV>, smem)) return 2; done = true; }            \
-    enc_chain_bwd_kernel<MLPV><<<nb, THREADS, smem, (cudaStream_t)stream>>>(p);                                   \
+    launch_k(enc_chain_bwd_kernel<MLPV>, nb, THREADS, smem, (cudaStream_t)stream, p);                                   \
   } while (0)
   if (mlp == 128) TMF_LAUNCH_CHAIN_BWD(128);
   else if (mlp == 256) TMF_LAUNCH_CHAIN_BWD(256);
@@ -1016,7 +1022,7 @@ int tmf_encoder_proj_bwd(const float* dq, const float* dkv, const float* dxp, co
   const size_t smem = sizeof(float) * (PR * 260 + 2 * PR * LD128 + 2 * PR * 260 + NSTAGE * WT_FLOATS + 256);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_proj_bwd_kernel, smem)) return 2; done = true; }
-  enc_proj_bwd_kernel<<<p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream>>>(p);
+  launch_k(enc_proj_bwd_kernel, p.nbx + ceil_div(Mc, PR), THREADS, smem, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -1051,7 +1057,7 @@ int tmf_encoder_wgrad(const void* const* t, const float* f, float* dw2, float* d
   const size_t smem = sizeof(float) * (32 * WG_LDA + NSTAGE * WT_FLOATS);
   static bool done = false;
   if (!done) { if (set_smem((const void*)enc_wgrad_kernel, smem)) return 2; done = true; }
-  enc_wgrad_kernel<<<tiles * p.nsplit, THREADS, smem, (cudaStream_t)stream>>>(p);
+  launch_k(enc_wgrad_kernel, tiles * p.nsplit, THREADS, smem, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }

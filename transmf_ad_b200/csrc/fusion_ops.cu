@@ -47,6 +47,7 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + 
 // These GEMMs are tiny (M = B*150 rows, K, N <= 512): what matters is latency, so the global loads of tile k+1 are
 // issued before the FMAs of tile k (register double buffering), and long-K problems are split over blockIdx.z.
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
+  pdl_entry();
   __shared__ __align__(16) float As[G_TK][G_TM + G_PAD];
   __shared__ __align__(16) float Bs[G_TK][G_TN + G_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
 // block of a column group adds them in index order (deterministic; no atomics, nothing to zero).
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int rows_per_block,
                               float* __restrict__ partbuf, unsigned* __restrict__ tickets) {
+  pdl_entry();
   __shared__ float part[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r = threadIdx.x >> 5;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ residual, float* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, int dim, float eps) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int nv = dim >> 2;
   for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
@@ -204,6 +207,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim, int accumulate,
                      float* __restrict__ partbuf, unsigned* __restrict__ ticket) {
+  pdl_entry();
   extern __shared__ float sm[];  // [2][dim]
   for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -279,6 +283,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gelu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ pre, float4* __restrict__ dx,
                                 int64_t n4) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 g = dy[i], x = pre[i];
     float4 o;
@@ -297,6 +302,7 @@ __global__ void gelu_bwd_kernel(const float4* __restrict__ dy, const float4* __r
 
 __global__ void scale_kernel(const float* __restrict__ x, float* __restrict__ y, float alpha,
                              const float* __restrict__ alpha_dev, int64_t n) {
+  pdl_entry();
   if (alpha_dev != nullptr) alpha *= alpha_dev[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = alpha * x[i];
@@ -310,6 +316,7 @@ constexpr int AT_ROWS = 32;  // rows per block
 
 // smem: Ks[Nk][dh+1], Vs[Nk][dh+1], sc[AT_WARPS][Nk], qs[AT_WARPS][dh]
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ float sm[];
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
   float* Ks = sm;
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(AttnArgs p) {
 
 // dq: same staging as forward.  extra smem: dos[AT_WARPS][dh]
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dq_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ float sm[];
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
   float* Ks = sm;
@@ -410,6 +418,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dq_kernel(AttnArgs p) 
 
 // dk, dv: smem Qs[Nq][dh+1], dOs[Nq][dh+1], lses[Nq], Ds[Nq], pw[AT_WARPS][Nq], dsw[AT_WARPS][Nq], ks/vs[AT_WARPS][dh]
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dkv_kernel(AttnArgs p) {
+  pdl_entry();
   extern __shared__ float sm[];
   const int dh = p.dh, ld = dh + 1, inner = p.heads * dh;
   float* Qs = sm;
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_dkv_kernel(AttnArgs p)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void token_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ mx,
                                       int32_t* __restrict__ amax, int B, int N, int C) {
+  pdl_entry();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C) return;
   const int b = idx / C, c = idx % C;
@@ -492,6 +502,7 @@ __global__ void token_pool_fwd_kernel(const float* __restrict__ x, float* __rest
 __global__ void token_pool_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ dmax,
                                       const int32_t* __restrict__ amax, float* __restrict__ dx, int B, int N, int C,
                                       int accumulate) {
+  pdl_entry();
   const int64_t total = (int64_t)B * N * C;
   const float invn = 1.f / N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -535,6 +546,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <bool AKF, bool BKF>
 __global__ void __launch_bounds__(F_THREADS) gemm_pipe_kernel(GemmArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float fsm[];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * F_TM, n0 = blockIdx.x * F_TN;
@@ -678,6 +690,7 @@ constexpr int V_RED_PITCH = 36;
 
 template <bool AKF, bool BKF>
 __global__ void __launch_bounds__(V_THREADS) gemm_ksplit_kernel(GemmArgs p) {
+  pdl_entry();
   extern __shared__ __align__(16) float fsm[];
   const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63, tx = t & 7, ty = t >> 3;
   const int m0 = blockIdx.y * V_TM, n0 = blockIdx.x * V_TN;
@@ -841,7 +854,7 @@ static int launch_gemm(GemmArgs& p, cudaStream_t st) {
       TMF_CUDA(cudaFuncSetAttribute(gemm_ksplit_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    gemm_ksplit_kernel<AK, BK><<<grid, V_THREADS, smem, st>>>(p);                                                   \
+    launch_k(gemm_ksplit_kernel<AK, BK>, grid, V_THREADS, smem, st, p);                                                   \
   } while (0)
     if (akf && bkf) TMF_LAUNCH_KS(true, true);
     else if (akf) TMF_LAUNCH_KS(true, false);
@@ -862,7 +875,7 @@ static int launch_gemm(GemmArgs& p, cudaStream_t st) {
       TMF_CUDA(cudaFuncSetAttribute(gemm_pipe_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    gemm_pipe_kernel<AK, BK><<<grid, F_THREADS, smem, st>>>(p);                                                     \
+    launch_k(gemm_pipe_kernel<AK, BK>, grid, F_THREADS, smem, st, p);                                                     \
   } while (0)
     if (akf && bkf) TMF_LAUNCH_PIPE(true, true);
     else if (akf) TMF_LAUNCH_PIPE(true, false);
@@ -873,7 +886,7 @@ static int launch_gemm(GemmArgs& p, cudaStream_t st) {
     return 0;
   }
   dim3 grid(ceil_div(p.N, G_TN), ceil_div(p.M, G_TM), p.kchunk ? ceil_div(p.K, p.kchunk) : 1);
-  gemm_kernel<<<grid, 256, 0, st>>>(p);
+  launch_k(gemm_kernel, grid, 256, 0, st, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -958,7 +971,7 @@ int tmf_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, i
     dim3 grid(ceil_div(N, 32), ceil_div(M, rows), 1);
     TMF_REQUIRE(grid.x <= 1024, "linear_wgrad: N=%d too wide for the column-sum tickets", N);
     // (runs after the GEMM in stream order, so it may reuse the partial area)
-    colsum_kernel<<<grid, 256, 0, st>>>(dy, dbias, M, N, rows, partials, tickets + 3072);
+    launch_k(colsum_kernel, grid, 256, 0, st, dy, dbias, M, N, rows, partials, tickets + 3072);
     TMF_LAUNCH_CHECK();
   }
   return 0;
@@ -971,7 +984,7 @@ int tmf_layernorm_fwd(const float* x, const float* gamma, const float* beta, con
   TMF_REQUIRE(dim % 4 == 0 && dim <= 128 * LN_MAXV, "layernorm: dim must be a multiple of 4 and <= %d (got %d)",
               128 * LN_MAXV, dim);
   const int grid = max(1, min(ceil_div(rows, 8), 148 * 8));
-  layernorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, residual, y, mean, rstd, rows, dim, eps);
+  launch_k(layernorm_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, x, gamma, beta, residual, y, mean, rstd, rows, dim, eps);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -983,7 +996,7 @@ int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
               128 * LN_MAXV, dim);
   if (check_ws("layernorm_bwd", ws, ws_bytes)) return 1;
   const int grid = max(1, min(ceil_div(rows, 8 * 4), 148));
-  layernorm_bwd_kernel<<<grid, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+  launch_k(layernorm_bwd_kernel, grid, 256, 2 * dim * sizeof(float), (cudaStream_t)stream, 
       dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, dim, accumulate,
       reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + TMF_WS_TICKET_BYTES), reinterpret_cast<unsigned*>(ws));
   TMF_LAUNCH_CHECK();
@@ -993,14 +1006,14 @@ int tmf_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 int tmf_gelu_bwd(const float* dy, const float* pre, float* dx, int64_t n, void* stream) {
   TMF_REQUIRE(n % 4 == 0, "gelu_bwd: n must be a multiple of 4");
   const int grid = max(1, min(ceil_div(n / 4, 256), 148 * 8));
-  gelu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)pre, (float4*)dx, n / 4);
+  launch_k(gelu_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, (const float4*)dy, (const float4*)pre, (float4*)dx, n / 4);
   TMF_LAUNCH_CHECK();
   return 0;
 }
 
 int tmf_scale(const float* x, float* y, float alpha, const float* alpha_dev, int64_t n, void* stream) {
   const int grid = max(1, min(ceil_div(n, 256), 148 * 8));
-  scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, alpha, alpha_dev, n);
+  launch_k(scale_kernel, grid, 256, 0, (cudaStream_t)stream, x, y, alpha, alpha_dev, n);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -1023,7 +1036,7 @@ int tmf_attn_fwd(const float* q, const float* kv, float* out, float* lse, int B,
   const size_t smem = sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)AT_WARPS * dh);
   if (attn_smem_check(smem, (const void*)attn_fwd_kernel)) return 2;
   dim3 grid(B * heads, ceil_div(Nq, AT_ROWS), 1);
-  attn_fwd_kernel<<<grid, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+  launch_k(attn_fwd_kernel, grid, AT_WARPS * 32, smem, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -1041,20 +1054,20 @@ int tmf_attn_bwd(const float* dout, const float* q, const float* kv, const float
       sizeof(float) * ((size_t)2 * Nk * (dh + 1) + (size_t)AT_WARPS * Nk + (size_t)2 * AT_WARPS * dh);
   if (attn_smem_check(smem1, (const void*)attn_bwd_dq_kernel)) return 2;
   dim3 grid1(B * heads, ceil_div(Nq, AT_ROWS), 1);
-  attn_bwd_dq_kernel<<<grid1, AT_WARPS * 32, smem1, (cudaStream_t)stream>>>(p);
+  launch_k(attn_bwd_dq_kernel, grid1, AT_WARPS * 32, smem1, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   const size_t smem2 = sizeof(float) * ((size_t)2 * Nq * (dh + 1) + (size_t)2 * Nq + (size_t)2 * AT_WARPS * Nq +
                                         (size_t)2 * AT_WARPS * dh);
   if (attn_smem_check(smem2, (const void*)attn_bwd_dkv_kernel)) return 2;
   dim3 grid2(B * heads, ceil_div(Nk, AT_ROWS), 1);
-  attn_bwd_dkv_kernel<<<grid2, AT_WARPS * 32, smem2, (cudaStream_t)stream>>>(p);
+  launch_k(attn_bwd_dkv_kernel, grid2, AT_WARPS * 32, smem2, (cudaStream_t)stream, p);
   TMF_LAUNCH_CHECK();
   return 0;
 }
 
 int tmf_token_pool_fwd(const float* x, float* mean, float* max, int32_t* argmax, int B, int N, int C, void* stream) {
   TMF_REQUIRE(max == nullptr || argmax != nullptr, "token_pool_fwd: argmax buffer required with max");
-  token_pool_fwd_kernel<<<ceil_div((int64_t)B * C, 128), 128, 0, (cudaStream_t)stream>>>(x, mean, max, argmax, B, N, C);
+  launch_k(token_pool_fwd_kernel, ceil_div((int64_t)B * C, 128), 128, 0, (cudaStream_t)stream, x, mean, max, argmax, B, N, C);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -1063,7 +1076,7 @@ int tmf_token_pool_bwd(const float* dmean, const float* dmax, const int32_t* arg
                        int accumulate, void* stream) {
   const int64_t total = (int64_t)B * N * C;
   const int grid = max(1, min(ceil_div(total, 256), 148 * 8));
-  token_pool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dmean, dmax, argmax, dx, B, N, C, accumulate);
+  launch_k(token_pool_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dmean, dmax, argmax, dx, B, N, C, accumulate);
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -58,6 +58,7 @@ struct alignas(64) WgradParams {
 
 template <int KSTEPS>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + (uint32_t)p.stages * p.stage_bytes;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_umma_kernel(const 
 // dw[co][ci][tap] = sum_split ws[split][tap][ci][co]   (fixed order -> deterministic)
 __global__ void wgrad_reduce_kernel(GroupPtr<const float> ws, GroupPtr<float> dw, int nsplit, int taps, int cin,
                                     int cout) {
+  pdl_entry();
   const int g = blockIdx.z;
   const int64_t total = (int64_t)taps * cin * cout;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -380,7 +382,7 @@ int tmf_wgrad_reduce(int ng, float* const* ws, float* const* dw, int nsplit, int
   for (int g = 0; g < ng; ++g) { gws.p[g] = ws[g]; gdw.p[g] = dw[g]; }
   const int64_t total = (int64_t)taps * cin * cout;
   dim3 rgrid(min(ceil_div(total, 256), 148 * 4), 1, ng);
-  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(gws, gdw, nsplit, taps, cin, cout);
+  launch_k(wgrad_reduce_kernel, rgrid, 256, 0, (cudaStream_t)stream, gws, gdw, nsplit, taps, cin, cout);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -408,6 +410,8 @@ int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, f
   WgradParams p{};
   uint32_t smem = 0;
   CUtensorMapSwizzle swx, swy;
+  // 1x1x1: a plain GEMM over the voxel rows -- flatten the volume so that every K tile of 128 voxels is full
+  if (ksize == 1 && (int64_t)B * D * H * W < (1ll << 31)) { H = B * D * H * W; B = 1; D = 1; W = 1; }
   TMF_REQUIRE(build_wgrad_plan(p, ng, B, D, H, W, cin, cout, ksize, device_sms(), &smem, &swx, &swy),
               "conv3d_wgrad_umma: unsupported problem");
   const size_t per_tower = (size_t)p.nsplit * p.taps * cin * cout * sizeof(float);
@@ -455,14 +459,14 @@ int tmf_conv3d_wgrad_umma(int ng, const void* const* dy, const void* const* a, f
                                     (int)WG_SMEM_BUDGET));                                                       \
       attr_done = true;                                                                                          \
     }                                                                                                            \
-    conv3d_wgrad_umma_kernel<KST><<<grid, WG_THREADS, smem, st>>>(p);                                            \
+    launch_k(conv3d_wgrad_umma_kernel<KST>, grid, WG_THREADS, smem, st, p);                                            \
   } while (0)
   if (p.TK == 128) TMF_LAUNCH_WG(8); else TMF_LAUNCH_WG(4);
 #undef TMF_LAUNCH_WG
   TMF_LAUNCH_CHECK();
   const int64_t total = (int64_t)p.taps * cin * cout;
   dim3 rgrid(min(ceil_div(total, 256), 148 * 4), 1, ng);
-  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(gws, gdw, p.nsplit, p.taps, cin, cout);
+  launch_k(wgrad_reduce_kernel, rgrid, 256, 0, st, gws, gdw, p.nsplit, p.taps, cin, cout);
   TMF_LAUNCH_CHECK();
   return 0;
 }

@@ -43,6 +43,7 @@ struct alignas(64) WgColParams {
 };
 
 __global__ void __launch_bounds__(WC_THREADS, 1) conv3d_wgrad_col_kernel(const __grid_constant__ WgColParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smX = smem_base;
@@ -340,7 +341,7 @@ int tmf_conv3d_wgrad_col(int ng, const void* const* dy, const void* const* a, fl
     attr_done = true;
   }
   dim3 grid(pl.ngv * pl.nsplit, 1, 1);
-  conv3d_wgrad_col_kernel<<<grid, WC_THREADS, pl.smem, st>>>(p);
+  launch_k(conv3d_wgrad_col_kernel, grid, WC_THREADS, pl.smem, st, p);
   TMF_LAUNCH_CHECK();
   return tmf_wgrad_reduce(ng, wsp, dw, pl.nsplit, 27, cin, cout, stream);
 }
