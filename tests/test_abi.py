@@ -50,8 +50,8 @@ def test_sass_is_sm100a_only():
 def test_streamed_weight_conv_plans_for_the_bench_layers(built_lib):
     """Host-only introspection of the generic tcgen05 forward/dgrad kernel's launch plan: at the
     bench shape (B = 8, two towers) conv3.3 dgrad applies each weight box to three 128-row tiles with two issuer warps
-    and one accumulator set, conv4.0 dgrad to two tiles, and conv4.0 forward keeps one tile per pass (wave
-    quantisation); the 1x1x1 layer keeps its weights resident."""
+    and one accumulator set, conv4.0 forward / dgrad tile the stacked planes of a sample; the 1x1x1 layer keeps its
+    weights resident."""
     import ctypes as C
     out = (C.c_int * 8)()
 
@@ -62,10 +62,11 @@ def test_streamed_weight_conv_plans_for_the_bench_layers(built_lib):
 
     p = plan(22, 27, 22, 128, 64, 3)
     assert (p["mt"], p["issuers"], p["acc_sets"], p["resident"]) == (3, 2, 1, 0) and p["b_stages"] % 2 == 0
+    # conv4.0 (planes of 13 x 13 padded rows = 1.3 tiles): plane-stack tiling, 17 tiles per sample instead of 22
     p = plan(11, 13, 11, 256, 128, 3)
-    assert (p["mt"], p["acc_sets"], p["resident"]) == (2, 2, 0)
+    assert (p["mt"], p["acc_sets"], p["resident"], p["tiles_per_plane"]) == (1, 2, 2, 17)      # resident bit 1 = plane-stack mode
     p = plan(11, 13, 11, 128, 256, 3)
-    assert (p["mt"], p["issuers"], p["resident"]) == (1, 1, 0)
+    assert (p["mt"], p["issuers"], p["resident"], p["tiles_per_plane"]) == (1, 1, 2, 17)
     p = plan(11, 13, 11, 256, 128, 1)
     assert p["resident"] == 1 and p["mt"] == 1
     # every plan respects the 512-column TMEM budget

@@ -49,6 +49,12 @@ struct alignas(64) UmmaConvParams {
   int tma_lanes;                  // producer lanes that issue TMA boxes round-robin
   int mt;                         // 128-row M tiles per weight pass ("super-tile" = 128*mt consecutive positions)
   int nbuf;                       // accumulator sets in TMEM: 2 = epilogue overlaps the next super-tile, 1 = it does not
+  // Plane-stack mode (small planes, e.g. conv4.0 at 11x13x11: a plane is 169 padded rows = 1.3 tiles, so per-plane tiling
+  // leaves 44 % of the MMA rows empty): the positions of a whole SAMPLE are linearised, q = d*Pp + h*Wp + w' with the plane
+  // pitch Pp = (H + 2*hw) * Wp, and a tile is any 128 consecutive q.  Its A slab for (kd, chunk) is ONE box of NP whole padded
+  // planes starting at plane q0/Pp + kd - hw (out-of-bounds planes / rows / columns zero-filled = the padding); tap shifts
+  // stay row offsets because every plane carries its own halo rows.  QT = tiles per sample, mt = 1.
+  int stack, Pp, NP;
 };
 
 __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
@@ -118,12 +124,12 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta) {
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
-        const int d = r % p.D;
-        const int n = r / p.D;
-        const int h0 = (qt * UC_TILE_M * p.mt) / p.Wp;
+        const int d = p.stack ? (qt * UC_TILE_M) / p.Pp : r % p.D;          // stack: first plane the tile touches
+        const int n = p.stack ? r : r / p.D;
+        const int h0 = p.stack ? 0 : (qt * UC_TILE_M * p.mt) / p.Wp;
         for (int kd = 0; kd < p.ks; ++kd) {
           const int dd = d + kd - p.hw;
-          if (dd < 0 || dd >= p.D) continue;
+          if (dd + p.NP - 1 < 0 || dd >= p.D) continue;
           if (p.b_resident && !((kd_loaded >> kd) & 1u)) {     // all (tap, chunk) boxes of this plane, once per CTA
             kd_loaded |= 1u << kd;
             for (int t = 0; t < taps2; ++t)
@@ -182,8 +188,9 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
       for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
         int r = tile;
         const int qt = r % p.QT; r /= p.QT;
-        const int d = r % p.D;
-        const uint32_t qoff_units = (uint32_t)((qt * UC_TILE_M * p.mt) % p.Wp) * ROW_UNITS;
+        const int d = p.stack ? (qt * UC_TILE_M) / p.Pp : r % p.D;
+        const uint32_t qoff_units =
+            (uint32_t)(p.stack ? (qt * UC_TILE_M) % p.Pp : (qt * UC_TILE_M * p.mt) % p.Wp) * ROW_UNITS;
         const int as = (p.nbuf == 2) ? (it & 1) : 0;
         const uint32_t acc_ph = (uint32_t)((p.nbuf == 2) ? (it >> 1) : it) & 1u;
         mbar_wait(acc_empty + 8 * as, acc_ph ^ 1u);
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
 #pragma unroll 1
         for (int kd = 0; kd < KS; ++kd) {
           const int dd = d + kd - p.hw;
-          if (dd < 0 || dd >= p.D) continue;
+          if (dd + p.NP - 1 < 0 || dd >= p.D) continue;
           if (RES && !((kd_ready >> kd) & 1u)) {
             for (int i = 0; i < TAPS2 * p.nchunk; ++i) mbar_wait(b_full + 8 * (kd * TAPS2 * p.nchunk + i), 0u);
             kd_ready |= 1u << kd;
@@ -263,16 +270,17 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
     for (int tile = cta; tile < p.tiles_per_group; tile += ncta, ++it) {
       int r = tile;
       const int qt = r % p.QT; r /= p.QT;
-      const int d = r % p.D;
-      const int n = r / p.D;
+      int d = p.stack ? 0 : r % p.D;
+      const int n = p.stack ? r : r / p.D;
       const int as = (p.nbuf == 2) ? (it & 1) : 0;
       const uint32_t acc_ph = (uint32_t)((p.nbuf == 2) ? (it >> 1) : it) & 1u;
       mbar_wait(acc_full + 8 * as, acc_ph);
       tc_fence_after();
       for (int mt = 0; mt < p.mt; ++mt) {
-      const int q = (qt * p.mt + mt) * UC_TILE_M + row;
+      int q = (qt * p.mt + mt) * UC_TILE_M + row;
+      if (p.stack) { d = q / p.Pp; q -= d * p.Pp; }
       const int h = q / p.Wp, w = q - h * p.Wp;
-      const bool valid = (h < p.H) && (w < p.W);
+      const bool valid = (d < p.D) && (h < p.H) && (w < p.W);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * NISS * p.mt + mt) * p.cout);
       __nv_bfloat16* yrow = yg + ((((int64_t)n * p.D + d) * p.H + h) * p.W + w) * p.cout;
       for (int c0 = 0; c0 < p.cout; c0 += 32) {
@@ -374,6 +382,7 @@ static int umma_issuers() {
 struct UmmaPlan {
   bool ok;
   int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident, niss, mt, nbuf;
+  int stack, Pp, NP;
   uint32_t layout, a_stage_bytes, b_stage_bytes, a_tx, b_tx, tmem_cols, smem_bytes;
   CUtensorMapSwizzle swz;
 };
@@ -467,6 +476,42 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
           if (cost < best * 0.999) { best = cost; bp = c; found = true; }
         }
     }
+    // Plane-stack candidates (see UmmaConvParams): tiles of 128 consecutive positions of the whole sample, one box of NP
+    // padded planes per (kd, chunk); same cost model per tile, rounds = ceil(B * tiles per sample / CTAs per tower).
+    const int want_stack = umma_env_int("TMF_UMMA_STACK", -1);       // bring-up switch: 0 = never, 1 = whenever possible
+    if (ks == 3 && want_stack != 0 && force_mt == 0) {
+      for (int niss = 1; niss <= (max_iss >= 2 ? 2 : 1); ++niss)
+        for (int nbuf = 2; nbuf >= 1; --nbuf) {
+          if (nbuf * niss * cout > 512) continue;
+          UmmaPlan c = pl;
+          c.stack = 1; c.mt = 1; c.niss = niss; c.nbuf = nbuf;
+          c.NH = H + 2 * hw;
+          c.Pp = c.NH * c.Wp;
+          c.NP = ((c.Pp - 1) + (UC_TILE_M - 1) + (ks - 1) * c.Wp + (ks - 1) + 1 + c.Pp - 1) / c.Pp;
+          if (c.NH > 256 || c.NP > 16) continue;
+          c.QT = ((D - 1) * c.Pp + H * c.Wp + UC_TILE_M - 1) / UC_TILE_M;
+          c.a_tx = (uint32_t)c.NP * c.Pp * c.row_bytes;
+          c.a_stage_bytes = (c.a_tx + 1023u) & ~1023u;
+          c.SA = 3;
+          if (3 * c.a_stage_bytes + 4 * c.b_stage_bytes > budget) c.SA = 2;
+          const int min_sb = (niss == 2) ? 4 : 2;
+          if ((uint32_t)c.SA * c.a_stage_bytes + (uint32_t)min_sb * c.b_stage_bytes > budget) continue;
+          c.SB = (int)((budget - (uint32_t)c.SA * c.a_stage_bytes) / c.b_stage_bytes);
+          if (c.SB > 8) c.SB = 8;
+          if (niss == 2) c.SB &= ~1;
+          const double rows128 = c.row_bytes / 128.0;
+          const double tma = (double)ks * c.nchunk *
+                             ((500.0 + 1.5 * c.NP * c.Pp * rows128) + ks * ks * (500.0 + 1.5 * cout * rows128));
+          const double per_mma = (0.75 * cout > 100.0 / niss) ? 0.75 * cout : 100.0 / niss;
+          const double mma = (double)(taps * c.nchunk * (c.chunk / 16)) * per_mma;
+          const int ncta = (148 / (ng > 0 ? ng : 1)) > 0 ? 148 / (ng > 0 ? ng : 1) : 1;
+          const int64_t ntiles = (int64_t)B * c.QT;
+          const double rounds = (double)((ntiles + ncta - 1) / ncta);
+          // x 0.9: measured on B200 (conv4.0 dgrad, B = 8: 83.7 us stacked vs 91.6 us per plane) the model overestimates these tiles
+          const double cost = 0.9 * rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0);
+          if (cost < best * 0.999 || (want_stack == 1 && !bp.stack)) { best = cost; bp = c; found = true; }
+        }
+    }
     if (!found) return pl;
     pl = bp;
   }
@@ -507,7 +552,7 @@ extern "C" int tmf_conv3d_umma_plan_info(int ng, int B, int D, int H, int W, int
   const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize, B, ng);
   if (out8 != nullptr) {
     out8[0] = pl.ok ? 1 : 0; out8[1] = pl.mt; out8[2] = pl.niss; out8[3] = pl.nbuf;
-    out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident;
+    out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident | (pl.stack << 1);   // bit 1: plane-stack mode
   }
   return pl.ok ? 0 : 1;
 }
@@ -531,7 +576,8 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   UmmaConvParams p{};
   p.ng = ng; p.B = B; p.D = D; p.H = H; p.W = W; p.cin = cin; p.cout = cout; p.ks = ksize; p.hw = ksize / 2;
   p.Wp = pl.Wp; p.NH = pl.NH; p.QT = pl.QT;
-  p.tiles_per_group = B * D * pl.QT;
+  p.stack = pl.stack; p.Pp = pl.Pp; p.NP = pl.stack ? pl.NP : 1;
+  p.tiles_per_group = pl.stack ? B * pl.QT : B * D * pl.QT;
   p.nchunk = pl.nchunk; p.chunk = pl.chunk; p.row_bytes = pl.row_bytes; p.layout = pl.layout;
   p.SA = pl.SA; p.SB = pl.SB; p.b_resident = pl.b_resident;
   p.a_stage_bytes = pl.a_stage_bytes; p.b_stage_bytes = pl.b_stage_bytes; p.a_tx_bytes = pl.a_tx; p.b_tx_bytes = pl.b_tx;
@@ -554,7 +600,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
       cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
       cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2,
                                (cuuint64_t)D * H * W * cin * 2};
-      cuuint32_t box[5] = {(cuuint32_t)pl.chunk, (cuuint32_t)pl.Wp, (cuuint32_t)pl.NH, 1, 1};
+      cuuint32_t box[5] = {(cuuint32_t)pl.chunk, (cuuint32_t)pl.Wp, (cuuint32_t)pl.NH, (cuuint32_t)(pl.stack ? pl.NP : 1), 1};
       cuuint32_t estr[5] = {1, 1, 1, 1, 1};
       CUresult r = encode(&p.tmA[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a[g]), dims, strides, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
