@@ -60,11 +60,12 @@ def test_streamed_weight_conv_plans_for_the_bench_layers(built_lib):
         keys = ("ok", "mt", "issuers", "acc_sets", "a_stages", "b_stages", "tiles_per_plane", "resident")
         return dict(zip(keys, list(out)))
 
+    # "resident" is a bit field: 1 = weights resident, 2 = plane-stack tiling, 4 = kw-fused weight boxes
     p = plan(22, 27, 22, 128, 64, 3)
     assert (p["mt"], p["issuers"], p["acc_sets"], p["resident"]) == (3, 2, 1, 0) and p["b_stages"] % 2 == 0
     # conv4.0 (planes of 13 x 13 padded rows = 1.3 tiles): plane-stack tiling, 17 tiles per sample instead of 22
     p = plan(11, 13, 11, 256, 128, 3)
-    assert (p["mt"], p["acc_sets"], p["resident"], p["tiles_per_plane"]) == (1, 2, 2, 17)      # resident bit 1 = plane-stack mode
+    assert (p["mt"], p["acc_sets"], p["resident"], p["tiles_per_plane"]) == (1, 2, 6, 17)
     p = plan(11, 13, 11, 128, 256, 3)
     assert (p["mt"], p["issuers"], p["resident"], p["tiles_per_plane"]) == (1, 1, 2, 17)
     p = plan(11, 13, 11, 256, 128, 1)

@@ -435,7 +435,8 @@ def test_loss_reader_returns_each_steps_scalars_one_call_late():
                                             ((2, 11, 13, 11), 256, 128), ((1, 19, 23, 19), 128, 64)])
 @pytest.mark.parametrize("max_ctas", ["0", "3"])
 @pytest.mark.parametrize("stack", ["0", "1"])
-def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_ctas, stack, monkeypatch):
+@pytest.mark.parametrize("kwf", ["0", "1"])
+def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_ctas, stack, kwf, monkeypatch):
     """The generic tcgen05 kernel with streamed weights (conv3.3 dgrad, conv4.0 fwd/dgrad): several 128-row tiles per
     weight pass, one or two issuer warps, single- or double-buffered accumulators -- also with only 3 CTAs per tower,
     so that every CTA walks many super-tiles (barrier phases wrap) -- and the plane-stack tiling of the same layers.
@@ -444,9 +445,12 @@ def test_conv3d_streamed_weight_plans_match_direct_kernel(shape, cin, cout, max_
     lib = L.load()
     info = (C.c_int * 8)()
     monkeypatch.setenv("TMF_UMMA_STACK", stack)      # 1: plane-stack tiles (128 consecutive positions of the whole sample)
+    monkeypatch.setenv("TMF_UMMA_KWF", kwf)          # 1: one TMA box / ring stage per (kd, kh) = three kw taps (where it fits)
     assert lib.tmf_conv3d_umma_plan_info(2, B, D, H, W, cin, cout, 3, info) == 0 and (info[7] & 1) == 0   # streamed weights
+    if cout <= 128:
+        assert ((info[7] >> 2) & 1) == int(kwf)
     if D == 11:
-        assert (info[7] >> 1) == int(stack)      # the bigger planes do not fit two padded planes per ring stage
+        assert ((info[7] >> 1) & 1) == int(stack)      # the bigger planes do not fit two padded planes per ring stage
     monkeypatch.setenv("TMF_UMMA_MAX_CTAS", max_ctas)
     ng = 2
     a = [to_ndhwc_bf16(bf16r(g_randn(B, cin, D, H, W, seed=11 + t))) for t in range(ng)]

@@ -55,6 +55,10 @@ struct alignas(64) UmmaConvParams {
   // planes starting at plane q0/Pp + kd - hw (out-of-bounds planes / rows / columns zero-filled = the padding); tap shifts
   // stay row offsets because every plane carries its own halo rows.  QT = tiles per sample, mt = 1.
   int stack, Pp, NP;
+  // kw-fused weight boxes (streamed weights): the three kw taps of a (kd, kh) are neighbouring [Cout][chunk] blocks of
+  // wf[tap][Cout][Cin], so ONE TMA box {chunk, Cout, 3} brings them and a ring stage holds three taps: a third of the weight
+  // boxes (the kernel is bound by their number, ~500 cycles each).
+  int kwf;
 };
 
 __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int mode) {
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
             ++jw;
             if (++sa == p.SA) { sa = 0; pa ^= 1u; }
             if (!p.b_resident) {
-              for (int t = 0; t < taps2; ++t, ++jw) {
+              const int tstep = p.kwf ? p.ks : 1;
+              for (int t = 0; t < taps2; t += tstep, ++jw) {
                 const int tap = kd * taps2 + t;
                 mbar_wait(b_empty + 8 * sb, pb ^ 1u);
                 if ((jw % nl) == lane) {
@@ -213,16 +218,20 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
             const uint32_t a_slab = a0_lo + (uint32_t)sa * a_units + qoff_units;
             uint32_t b_res = b0_lo + (uint32_t)((kd * TAPS2) * p.nchunk + c) * b_units;   // resident: stage of tap 0
             const uint32_t b_res_step = (uint32_t)p.nchunk * b_units;
+            const bool kwf = !RES && p.kwf != 0;
+            const uint32_t tap_units = (uint32_t)(p.cout * KSTEPS * 32) >> 4;     // one tap inside a kw-fused ring stage
 #pragma unroll
             for (int kh = 0; kh < KS; ++kh) {
+              bool skip_row = false;                               // kw-fused: this (kd, kh) stage is the other issuer's
 #pragma unroll
               for (int kw = 0; kw < KS; ++kw) {
                 const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units + (uint32_t)kw * ROW_UNITS;
+                const bool last_of_stage = !kwf || kw == KS - 1;   // the ring stage is released after its last tap
                 uint32_t b_lo;
                 if (RES) {
                   b_lo = b_res;
                   b_res += b_res_step;
-                } else {
+                } else if (!kwf) {
                   if (NISS > 1 && (sb & (NISS - 1)) != iss) {    // the other issuer's tap
                     if (++sb == p.SB) { sb = 0; pb ^= 1u; }
                     continue;
@@ -230,6 +239,19 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
                   mbar_wait(b_full + 8 * sb, pb);
                   tc_fence_after();
                   b_lo = b0_lo + (uint32_t)sb * b_units;
+                } else {
+                  if (kw == 0) {
+                    skip_row = NISS > 1 && (sb & (NISS - 1)) != iss;
+                    if (!skip_row) {
+                      mbar_wait(b_full + 8 * sb, pb);
+                      tc_fence_after();
+                    }
+                  }
+                  if (skip_row) {
+                    if (last_of_stage) { if (++sb == p.SB) { sb = 0; pb ^= 1u; } }
+                    continue;
+                  }
+                  b_lo = b0_lo + (uint32_t)sb * b_units + (uint32_t)kw * tap_units;
                 }
                 if (elect_one()) {
                   // the tap's weights multiply every 128-row tile of the super-tile before the ring stage is released
@@ -241,11 +263,11 @@ __global__ void __launch_bounds__(32 * (5 + NISS), 1) conv3d_umma_kernel(const _
                       mma_bf16_ss(d_mt, desc_hi | (uint64_t)(a_mt + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), p.idesc,
                                   k ? 1u : accumulate);
                   }
-                  if (!RES) mma_commit(b_empty + 8 * sb);
+                  if (!RES && last_of_stage) mma_commit(b_empty + 8 * sb);
                 }
                 accumulate = 1;
                 __syncwarp();
-                if (!RES) {
+                if (!RES && last_of_stage) {
                   if (++sb == p.SB) { sb = 0; pb ^= 1u; }
                 }
               }
@@ -382,7 +404,7 @@ static int umma_issuers() {
 struct UmmaPlan {
   bool ok;
   int Wp, NH, QT, nchunk, chunk, row_bytes, SA, SB, b_resident, niss, mt, nbuf;
-  int stack, Pp, NP;
+  int stack, Pp, NP, kwf;
   uint32_t layout, a_stage_bytes, b_stage_bytes, a_tx, b_tx, tmem_cols, smem_bytes;
   CUtensorMapSwizzle swz;
 };
@@ -442,6 +464,8 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
     //   big super-tiles lose to wave quantisation on the small layers (conv4.0 fwd: 88 super-tiles on 74 CTAs).
     pl.b_resident = 0;
     const int force_mt = umma_env_int("TMF_UMMA_MT", 0);             // bring-up switches
+    const int want_kwf = umma_env_int("TMF_UMMA_KWF", -1);           // kw-fused weight boxes: 0 = never, 1 = whenever possible
+    const int max_kwf = (ks == 3 && want_kwf != 0 && ((uint32_t)cout * pl.row_bytes) % 1024u == 0) ? 1 : 0;
     const int max_iss = (ks == 3) ? umma_issuers() : 1;
     double best = 1e30;
     UmmaPlan bp = pl;
@@ -449,6 +473,9 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
     for (int mt = 1; mt <= 4; ++mt) {
       if (force_mt > 0 && mt != force_mt) continue;
       if (ks != 3 && mt > 1) break;
+      // kw-fused boxes on per-plane tiles only on request: measured on B200 (conv3.3 dgrad, B = 8) the plan they allow
+      // (mt = 2, two issuers, 24 KB stages) runs 128.9 us against 121.3 us for mt = 3 with single-tap stages
+      for (int kwf = 0; kwf <= (want_kwf == 1 ? max_kwf : 0); ++kwf)
       for (int niss = 1; niss <= (max_iss >= 2 ? 2 : 1); ++niss)
         for (int nbuf = 2; nbuf >= 1; --nbuf) {
           if (nbuf * niss * mt * cout > 512) continue;
@@ -457,6 +484,9 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
           if (c.NH > 256) continue;
           c.niss = niss;
           c.nbuf = nbuf;
+          c.kwf = kwf;
+          c.b_tx = pl.b_tx * (kwf ? ks : 1);
+          c.b_stage_bytes = (c.b_tx + 1023u) & ~1023u;
           c.SA = 3;
           if (3 * c.a_stage_bytes + 4 * c.b_stage_bytes > budget) c.SA = 2;
           const int min_sb = (niss == 2) ? 4 : 2;
@@ -466,13 +496,14 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
           if (niss == 2) c.SB &= ~1;               // ring stage s is always issuer s % 2's
           const double rows128 = c.row_bytes / 128.0;
           const double tma = (double)c.QT * ks * c.nchunk *
-                             ((500.0 + 1.5 * c.NH * c.Wp * rows128) + ks * ks * (500.0 + 1.5 * cout * rows128));
+                             ((500.0 + 1.5 * c.NH * c.Wp * rows128) +
+                              (ks * ks / (kwf ? ks : 1)) * (500.0 + 1.5 * cout * rows128 * (kwf ? ks : 1)));
           const double per_mma = (0.75 * cout > 100.0 / niss) ? 0.75 * cout : 100.0 / niss;
           const double mma = (double)c.QT * mt * (taps * c.nchunk * (c.chunk / 16)) * per_mma;
           const int ncta = (148 / (ng > 0 ? ng : 1)) > 0 ? 148 / (ng > 0 ? ng : 1) : 1;
           const int64_t ntiles = (int64_t)B * D * c.QT;
           const double rounds = (double)((ntiles + ncta - 1) / ncta);
-          const double cost = rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0) / c.QT;
+          const double cost = rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0) / c.QT * ((want_kwf == 1 && kwf) ? 1e-3 : 1.0);
           if (cost < best * 0.999) { best = cost; bp = c; found = true; }
         }
     }
@@ -480,11 +511,15 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
     // padded planes per (kd, chunk); same cost model per tile, rounds = ceil(B * tiles per sample / CTAs per tower).
     const int want_stack = umma_env_int("TMF_UMMA_STACK", -1);       // bring-up switch: 0 = never, 1 = whenever possible
     if (ks == 3 && want_stack != 0 && force_mt == 0) {
+      for (int kwf = 0; kwf <= max_kwf; ++kwf)
       for (int niss = 1; niss <= (max_iss >= 2 ? 2 : 1); ++niss)
         for (int nbuf = 2; nbuf >= 1; --nbuf) {
           if (nbuf * niss * cout > 512) continue;
           UmmaPlan c = pl;
           c.stack = 1; c.mt = 1; c.niss = niss; c.nbuf = nbuf;
+          c.kwf = kwf;
+          c.b_tx = pl.b_tx * (kwf ? ks : 1);
+          c.b_stage_bytes = (c.b_tx + 1023u) & ~1023u;
           c.NH = H + 2 * hw;
           c.Pp = c.NH * c.Wp;
           c.NP = ((c.Pp - 1) + (UC_TILE_M - 1) + (ks - 1) * c.Wp + (ks - 1) + 1 + c.Pp - 1) / c.Pp;
@@ -501,14 +536,15 @@ static UmmaPlan make_plan(int D, int H, int W, int cin, int cout, int ks, int B 
           if (niss == 2) c.SB &= ~1;
           const double rows128 = c.row_bytes / 128.0;
           const double tma = (double)ks * c.nchunk *
-                             ((500.0 + 1.5 * c.NP * c.Pp * rows128) + ks * ks * (500.0 + 1.5 * cout * rows128));
+                             ((500.0 + 1.5 * c.NP * c.Pp * rows128) +
+                              (ks * ks / (kwf ? ks : 1)) * (500.0 + 1.5 * cout * rows128 * (kwf ? ks : 1)));
           const double per_mma = (0.75 * cout > 100.0 / niss) ? 0.75 * cout : 100.0 / niss;
           const double mma = (double)(taps * c.nchunk * (c.chunk / 16)) * per_mma;
           const int ncta = (148 / (ng > 0 ? ng : 1)) > 0 ? 148 / (ng > 0 ? ng : 1) : 1;
           const int64_t ntiles = (int64_t)B * c.QT;
           const double rounds = (double)((ntiles + ncta - 1) / ncta);
           // x 0.9: measured on B200 (conv4.0 dgrad, B = 8: 83.7 us stacked vs 91.6 us per plane) the model overestimates these tiles
-          const double cost = 0.9 * rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0);
+          const double cost = 0.9 * rounds * (tma > mma ? tma : mma) * (nbuf == 1 ? 1.25 : 1.0) * ((want_kwf == 1 && kwf) ? 1e-3 : 1.0);
           if (cost < best * 0.999 || (want_stack == 1 && !bp.stack)) { best = cost; bp = c; found = true; }
         }
     }
@@ -552,7 +588,7 @@ extern "C" int tmf_conv3d_umma_plan_info(int ng, int B, int D, int H, int W, int
   const UmmaPlan pl = make_plan(D, H, W, cin, cout, ksize, B, ng);
   if (out8 != nullptr) {
     out8[0] = pl.ok ? 1 : 0; out8[1] = pl.mt; out8[2] = pl.niss; out8[3] = pl.nbuf;
-    out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident | (pl.stack << 1);   // bit 1: plane-stack mode
+    out8[4] = pl.SA; out8[5] = pl.SB; out8[6] = pl.QT; out8[7] = pl.b_resident | (pl.stack << 1) | (pl.kwf << 2);   // bit 1: plane-stack mode, bit 2: kw-fused weight boxes
   }
   return pl.ok ? 0 : 1;
 }
@@ -577,6 +613,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
   p.ng = ng; p.B = B; p.D = D; p.H = H; p.W = W; p.cin = cin; p.cout = cout; p.ks = ksize; p.hw = ksize / 2;
   p.Wp = pl.Wp; p.NH = pl.NH; p.QT = pl.QT;
   p.stack = pl.stack; p.Pp = pl.Pp; p.NP = pl.stack ? pl.NP : 1;
+  p.kwf = pl.kwf;
   p.tiles_per_group = pl.stack ? B * pl.QT : B * D * pl.QT;
   p.nchunk = pl.nchunk; p.chunk = pl.chunk; p.row_bytes = pl.row_bytes; p.layout = pl.layout;
   p.SA = pl.SA; p.SB = pl.SB; p.b_resident = pl.b_resident;
@@ -610,7 +647,7 @@ int tmf_conv3d_fwd_umma(int ng, const void* const* a, const void* const* wf, con
     {
       cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
       cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
-      cuuint32_t box[3] = {(cuuint32_t)pl.chunk, (cuuint32_t)cout, 1};
+      cuuint32_t box[3] = {(cuuint32_t)pl.chunk, (cuuint32_t)cout, (cuuint32_t)(pl.kwf ? ksize : 1)};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = encode(&p.tmB[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wf[g]), dims, strides, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
