@@ -216,6 +216,38 @@ def test_bn_lrelu_pool_forward_backward(pool, shape, C, training, last):
         assert rel_l2(dbias.cpu(), y_ref.grad.sum(dim=(0, 2, 3, 4))) < 1e-3
 
 
+@pytest.mark.parametrize("shape,C,last", [((2, 9, 11, 7), 32, False), ((1, 8, 8, 8), 64, False), ((2, 5, 6, 13), 16, True)])
+def test_maxpool_backward_apply_packed_kernel_equals_generic_kernel(shape, C, last, monkeypatch):
+    """The bf16x2 max-pool backward kernel (packed arg-max, FFMA2 output) writes the same values as the generic fp32
+    kernel: odd extents, negative and zero BatchNorm scales, ties from bf16 storage."""
+    B, D, H, W = shape
+    y = bf16r(g_randn(B, C, D, H, W, seed=1, scale=0.5).round(decimals=1) + 0.5)      # coarse values: many ties
+    y_d = to_ndhwc_bf16(y)
+    gamma = 1 + 0.2 * g_randn(C, seed=2)
+    gamma[::3] *= -1.0
+    gamma[1] = 0.0
+    mean, invstd = 0.5 + 0.1 * g_randn(C, seed=3), 1.5 + 0.1 * g_randn(C, seed=4)
+    scale = gamma * invstd
+    coef = torch.cat([scale, 0.1 * g_randn(C, seed=5) - mean * scale, mean, invstd]).to(DEV)
+    bcoef = (0.01 * g_randn(2 * C, seed=6)).to(DEV)
+    Do, Ho, Wo = D // 2, H // 2, W // 2
+    dout = g_randn(B, Do, Ho, Wo, C, seed=7).to(DEV)
+    if not last:
+        dout = dout.to(torch.bfloat16)
+    res = []
+    for generic in (True, False):
+        if generic:
+            monkeypatch.setenv("TMF_BN_GENERIC_MAXPOOL_BWD", "1")
+        else:
+            monkeypatch.delenv("TMF_BN_GENERIC_MAXPOOL_BWD")
+        dy = torch.full((B, D, H, W, C), 7.0, dtype=torch.bfloat16, device=DEV)
+        L.call("tmf_bn_act_pool_bwd_apply", 1, L.ptrs([dout]), int(last), L.ptrs([y_d]), L.ptrs([coef]), L.ptrs([bcoef]),
+               L.ptrs([dy]), B, D, H, W, C, L.POOL_MAX, 0.01)
+        torch.cuda.synchronize()
+        res.append(dy.float().cpu())
+    assert torch.equal(res[0], res[1]), float((res[0] - res[1]).abs().max())
+
+
 def test_maxpool_backward_routes_ties_to_first_maximum():
     """bf16 storage makes ties common; torch sends the gradient to the first maximum in (d,h,w) scan order."""
     B, D, H, W, C = 1, 2, 2, 2, 8

@@ -4,6 +4,8 @@
 // Reference semantics: models/networks.py:23-25, 29-34, 38-43, 47-52 (nn.BatchNorm3d eps 1e-5 momentum 0.1, biased
 // variance for normalisation / unbiased into running_var; nn.LeakyReLU() slope 0.01; floor-mode pools; max-pool
 // gradient to the first maximum in (d,h,w) scan order).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tmf {
@@ -384,6 +386,10 @@ __global__ void __launch_bounds__(256, (POOL == TMF_POOL_NONE) ? 3 : 2) bn_act_p
 
 // Max-pool backward reduction from ymax (see bn_act_pool_fwd_kernel<true>): sum dz, sum dz*xhat over the pooled
 // positions;  dz = dout * LeakyReLU'(scale*ymax + shift),  xhat = (ymax - mean) * invstd.
+// The loads of RK_U positions are issued before any of them is used (the compiler does not batch them across the loop's
+// exit tests by itself: one position = 32 bytes in flight per thread left the kernel at 3.0 TB/s, ncu r2p).
+constexpr int RK_U = 4;
+template <bool FP32>
 __global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_reduce_kept_kernel(ActPoolArgs p, int npos) {
   pdl_entry();
   const int g = blockIdx.z;
@@ -402,23 +408,155 @@ __global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_reduce_kept_kernel(ActP
     s1[j] = 0.f; s2[j] = 0.f;
   }
   const __nv_bfloat16* ym = p.ymax.p[g];
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   if (active) {
-#pragma unroll 4
-    for (int pos = blockIdx.x * pstep + threadIdx.x / CQ; pos < npos; pos += gridDim.x * pstep) {
-      const int64_t off = (int64_t)pos * p.C + c0;
-      float f[8], go[8];
-      unpack8(*reinterpret_cast<const uint4*>(ym + off), f);
-      load8f(p.dout.p[g], off, p.fp32io, go);
+    const int stride = gridDim.x * pstep;
+    for (int pos0 = blockIdx.x * pstep + threadIdx.x / CQ; pos0 < npos; pos0 += RK_U * stride) {
+      uint4 ry[RK_U], rg[RK_U], rg2[RK_U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(f[j], sc[j], sh[j]);
-        const float dz = z > 0.f ? go[j] : go[j] * p.slope;
-        s1[j] += dz;
-        s2[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s2[j]);
+      for (int u = 0; u < RK_U; ++u) {
+        const int pos = pos0 + u * stride;
+        const bool ok = pos < npos;
+        const int64_t off = (int64_t)(ok ? pos : pos0) * p.C + c0;
+        ry[u] = ok ? *reinterpret_cast<const uint4*>(ym + off) : zero4;
+        if (FP32) {
+          const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dout.p[g]) + off);
+          rg[u] = ok ? gp[0] : zero4;
+          rg2[u] = ok ? gp[1] : zero4;
+        } else {
+          rg[u] = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dout.p[g]) + off) : zero4;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RK_U; ++u) {
+        float f[8], go[8];
+        unpack8(ry[u], f);
+        if (FP32) {
+          go[0] = __uint_as_float(rg[u].x); go[1] = __uint_as_float(rg[u].y); go[2] = __uint_as_float(rg[u].z); go[3] = __uint_as_float(rg[u].w);
+          go[4] = __uint_as_float(rg2[u].x); go[5] = __uint_as_float(rg2[u].y); go[6] = __uint_as_float(rg2[u].z); go[7] = __uint_as_float(rg2[u].w);
+        } else {
+          unpack8(rg[u], go);          // a position beyond npos contributes dz = 0 (go = 0)
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], sc[j], sh[j]);
+          const float dz = z > 0.f ? go[j] : go[j] * p.slope;
+          s1[j] += dz;
+          s2[j] = fmaf(dz, (f[j] - mu[j]) * is[j], s2[j]);
+        }
       }
     }
   }
   block_channel_sums(red, p.sums.p[g], p.C, CQ, active, s1, s2);
+}
+
+// Max-pool backward APPLY on packed bf16 pairs.  The generic kernel above spends ~23 instructions per element on the
+// arg-max (compare + three selects per element in fp32) and the per-element output select: 84 M warp instructions for
+// conv2.3 (ncu r2p), i.e. instruction-issue bound at 2.8 TB/s.  Here the arg-max runs on bf16x2 registers: keys
+// y ^ signflip (the sign of the BatchNorm scale turns the maximum activation into a minimum of y), window maximum with
+// HMNMX2, first position equal to it with HSET2 (1.0 / 0.0 per half) and two logic ops; the output is
+//   dy = fma(sel, scale*dz, fma(Bc, y, A))      on packed fp32 pairs (FFMA2),  sel in {0, 1}
+// -- the same values as the generic kernel (it stays the reference in the op tests).
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_eq(uint32_t a, uint32_t b) {       // 0x3F80 (1.0) per half where equal, else 0
+  __nv_bfloat162 r = __heq2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t u4_get(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <bool FP32>
+__global__ void __launch_bounds__(256, 2) bn_maxpool_bwd_apply_kernel(ActPoolArgs p) {
+  pdl_entry();
+  const int g = blockIdx.z;
+  const int CQ = p.C >> 3;
+  const __nv_bfloat16* yg = p.y.p[g];
+  const int cq = threadIdx.x % CQ, pstep = 256 / CQ;
+  if ((int)threadIdx.x >= pstep * CQ) return;
+  const int c0 = cq * 8;
+  // per channel pair: packed coefficients (a zero scale needs no special case: its scale*dz is zero wherever the maximum is)
+  uint64_t cA2[4], cB2[4], sc2[4], sh2[4];
+#pragma unroll
+  for (int j2 = 0; j2 < 4; ++j2) {
+    float a[2], b[2], s_[2], h_[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = c0 + 2 * j2 + e;
+      const float sc = p.coef.p[g][c], sh = p.coef.p[g][p.C + c], mu = p.coef.p[g][2 * p.C + c], is = p.coef.p[g][3 * p.C + c];
+      const float m1 = p.bcoef.p[g][c], m2 = p.bcoef.p[g][p.C + c];
+      b[e] = -sc * m2 * is;
+      a[e] = -sc * m1 - b[e] * mu;
+      s_[e] = sc; h_[e] = sh;
+    }
+    cA2[j2] = pair_f32(a[0], a[1]); cB2[j2] = pair_f32(b[0], b[1]);
+    sc2[j2] = pair_f32(s_[0], s_[1]); sh2[j2] = pair_f32(h_[0], h_[1]);
+  }
+  const int64_t sW = p.C, sH = (int64_t)p.W * p.C, sD = (int64_t)p.H * p.W * p.C;
+  const int nunits = p.B * p.Dc * p.nch_c;
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int hc = unit % p.nch_c;
+    const int rr = unit / p.nch_c;
+    const int dw = rr % p.Dc, n = rr / p.Dc;
+    const int hb = hc * p.hcr_c, he = min(hb + p.hcr_c, p.Hc);
+    const int items = (he - hb) * p.Wc;
+    for (int pos = threadIdx.x / CQ; pos < items; pos += pstep) {
+      const int hh = pos / p.Wc;
+      const int ww = pos - hh * p.Wc, hw = hb + hh;
+      const bool win_ok = dw < p.Do && hw < p.Ho && ww < p.Wo;
+      uint4 raw[8];                                       // y of the window, overwritten pair by pair with dy
+      const int64_t off0 = ((((int64_t)n * p.D + 2 * dw) * p.H + 2 * hw) * p.W + 2 * ww) * p.C + c0;
+      const bool exd = 2 * dw + 1 < p.D, exh = 2 * hw + 1 < p.H, exw = 2 * ww + 1 < p.W;   // (position 0 always exists)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool ex = ((q & 4) ? exd : true) && ((q & 2) ? exh : true) && ((q & 1) ? exw : true);
+        const int64_t off = off0 + ((q & 4) ? sD : 0) + ((q & 2) ? sH : 0) + ((q & 1) ? sW : 0);
+        raw[q] = ex ? *reinterpret_cast<const uint4*>(yg + off) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float go[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) go[j] = 0.f;
+      if (win_ok) load8f(p.dout.p[g], ((((int64_t)n * p.Do + dw) * p.Ho + hw) * p.Wo + ww) * p.C + c0, FP32 ? 1 : 0, go);
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        // keys, window maximum, first position that holds it
+        const uint32_t flip = ((lo_u32(sc2[j2]) >> 16) & 0x8000u) | (hi_u32(sc2[j2]) & 0x80000000u);   // sign bits of the scales
+        uint32_t key[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) key[q] = u4_get(raw[q], j2) ^ flip;
+        uint32_t m = bf2_max(bf2_max(bf2_max(key[0], key[1]), bf2_max(key[2], key[3])),
+                             bf2_max(bf2_max(key[4], key[5]), bf2_max(key[6], key[7])));
+        // scale*dz of the window (zero outside the pooled extent): y at the maximum = key with the sign flipped back
+        const uint32_t ym = m ^ flip;
+        const uint64_t y2 = pair_f32(bf16_lo(ym), bf16_hi(ym));
+        const uint64_t z2 = fma2_f32(y2, sc2[j2], sh2[j2]);
+        const float z0 = __uint_as_float(lo_u32(z2)), z1 = __uint_as_float(hi_u32(z2));
+        const float g0 = go[2 * j2], g1 = go[2 * j2 + 1];
+        const float d0 = __uint_as_float(lo_u32(sc2[j2])) * (z0 > 0.f ? g0 : g0 * p.slope);
+        const float d1 = __uint_as_float(hi_u32(sc2[j2])) * (z1 > 0.f ? g1 : g1 * p.slope);
+        const uint64_t dz2 = pair_f32(d0, d1);
+        uint32_t found = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t eq = bf2_eq(key[q], m);
+          const uint32_t sel = eq & ~found;                       // 1.0 (0x3F80) in the half whose FIRST maximum is here
+          found |= eq;
+          const uint32_t yv = u4_get(raw[q], j2);
+          const uint64_t base = fma2_f32(cB2[j2], pair_f32(bf16_lo(yv), bf16_hi(yv)), cA2[j2]);
+          const uint64_t o2 = fma2_f32(pair_f32(bf16_lo(sel), bf16_hi(sel)), dz2, base);
+          const uint32_t pk = pack_bf16(__uint_as_float(lo_u32(o2)), __uint_as_float(hi_u32(o2)));
+          if (j2 == 0) raw[q].x = pk; else if (j2 == 1) raw[q].y = pk; else if (j2 == 2) raw[q].z = pk; else raw[q].w = pk;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool ex = ((q & 4) ? exd : true) && ((q & 2) ? exh : true) && ((q & 1) ? exw : true);
+        const int64_t off = off0 + ((q & 4) ? sD : 0) + ((q & 2) ? sH : 0) + ((q & 1) ? sW : 0);
+        if (ex) *reinterpret_cast<uint4*>(p.dy.p[g] + off) = raw[q];
+      }
+    }
+  }
 }
 
 template <bool APPLY>
@@ -542,7 +680,8 @@ int tmf_bn_maxpool_bwd_reduce_kept(int ng, const void* const* dout, int dout_fp3
   if (blocks > 148) blocks = 148;                                  // one statistics row per block (<= TMF_STAT_ROWS); with two
                                                                    // towers that is 2 blocks of <= 128 registers per SM
   if (blocks < 1) blocks = 1;
-  launch_k(bn_maxpool_bwd_reduce_kept_kernel, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
+  if (dout_fp32) launch_k(bn_maxpool_bwd_reduce_kept_kernel<true>, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
+  else launch_k(bn_maxpool_bwd_reduce_kept_kernel<false>, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
   TMF_LAUNCH_CHECK();
   return 0;
 }
@@ -557,6 +696,21 @@ int tmf_bn_act_pool_bwd_reduce(int ng, const void* const* dout, int dout_fp32, c
       !load_group(p.dout, (const void* const*)dout, ng, true, "dout") || !load_group(p.sums, sums, ng, true, "sums"))
     return 1;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pool == TMF_POOL_NONE) {
+    // no pooling: dout and y have the same flat layout -- the batched-load reduction over positions (the kept-maximum
+    // kernel with y in the place of ymax; same per-element arithmetic)
+    const int64_t npos = (int64_t)B * D * H * W;
+    p.ymax.p[0] = nullptr;
+    for (int g = 0; g < ng; ++g) p.ymax.p[g] = const_cast<__nv_bfloat16*>(p.y.p[g]);
+    const int pstep = 256 / (C / 8);
+    int blocks = ceil_div(npos, (int64_t)pstep * RK_U);
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    if (dout_fp32) launch_k(bn_maxpool_bwd_reduce_kept_kernel<true>, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
+    else launch_k(bn_maxpool_bwd_reduce_kept_kernel<false>, dim3(blocks, 1, ng), 256, 16 * 256 * sizeof(float), st, p, (int)npos);
+    TMF_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(plan_units(B, p.Do, p.Ho, TMF_STAT_ROWS, &p.nch, &p.hcr), 1, ng);   // one statistics row per block
   launch_bwd<false>(p, grid, 16 * 256 * sizeof(float), st);
   TMF_LAUNCH_CHECK();
@@ -593,7 +747,13 @@ int tmf_bn_act_pool_bwd_apply(int ng, const void* const* dout, int dout_fp32, co
       !load_group(p.dy, (__nv_bfloat16* const*)dy, ng, true, "dy"))
     return 1;
   dim3 grid(plan_units(B, p.Dc, p.Hc, 148 * 6, &p.nch_c, &p.hcr_c), 1, ng);
-  launch_bwd<true>(p, grid, 0, (cudaStream_t)stream);
+  const bool generic_max = getenv("TMF_BN_GENERIC_MAXPOOL_BWD") != nullptr;            // op-test switch: the fp32 kernel
+  if (pool == TMF_POOL_MAX && !generic_max) {
+    if (dout_fp32) launch_k(bn_maxpool_bwd_apply_kernel<true>, grid, 256, 0, (cudaStream_t)stream, p);
+    else launch_k(bn_maxpool_bwd_apply_kernel<false>, grid, 256, 0, (cudaStream_t)stream, p);
+  } else {
+    launch_bwd<true>(p, grid, 0, (cudaStream_t)stream);
+  }
   TMF_LAUNCH_CHECK();
   return 0;
 }
