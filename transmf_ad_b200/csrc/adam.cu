@@ -22,8 +22,10 @@ struct AdamChunk {
   int32_t n;
   int32_t off;             // element offset of this chunk inside its tensor (pack index arithmetic)
   int32_t cout, cin, taps;
-  int32_t pad;
+  int32_t tile;            // 1: the chunk is an ADAM_TCO x ADAM_TCI block of (co, ci) pairs with all taps (p/g/m/v = tensor base,
+                           // off = co0 * cin + ci0): the pack stores leave through shared memory as whole 32 / 64-byte segments
 };
+constexpr int ADAM_TCO = 16, ADAM_TCI = 32, ADAM_MAX_TAPS = 27;
 static_assert(sizeof(AdamChunk) == 72, "host code packs 72-byte chunk records");
 
 __device__ __forceinline__ void emit_pack(const AdamChunk& c, int i, float val) {
@@ -46,7 +48,40 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  const bool vec = ((((uintptr_t)c.p | (uintptr_t)c.g | (uintptr_t)c.m | (uintptr_t)c.v) & 15) == 0);
+  if (c.tile) {
+    // Conv weight with operand packs.  The element-wise version scattered two 2-byte stores per element (wf is [tap][co][ci],
+    // wd [tap'][ci][co], the parameter [co][ci][tap]): 16x write amplification made this kernel 95 us for 117 MB (ncu r2p).
+    __shared__ __nv_bfloat16 tl[ADAM_TCO * ADAM_TCI * ADAM_MAX_TAPS];     // [co][ci][tap]
+    const int taps = c.taps, seg = ADAM_TCI * taps;
+    const int co0 = c.off / c.cin, ci0 = c.off - co0 * c.cin;
+    for (int e = threadIdx.x; e < ADAM_TCO * seg; e += 256) {
+      const int row = e / seg, col = e - row * seg;
+      const size_t gi = ((size_t)(co0 + row) * c.cin + ci0) * taps + col;
+      const float g = fmaf(wd, c.p[gi], c.g[gi]);
+      const float m = fmaf(b1, c.m[gi], (1.f - b1) * g);
+      const float v = fmaf(b2, c.v[gi], (1.f - b2) * g * g);
+      c.m[gi] = m;
+      c.v[gi] = v;
+      const float pn = c.p[gi] - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+      c.p[gi] = pn;
+      tl[e] = __float2bfloat16_rn(pn);
+    }
+    __syncthreads();
+    constexpr int NR = ADAM_TCO * ADAM_TCI;
+    for (int o = threadIdx.x; o < NR * taps; o += 256) {
+      const int t = o / NR, r = o - t * NR;
+      const int co = r / ADAM_TCI, ci = r - co * ADAM_TCI;                // ci fastest: 64-byte runs of wf
+      c.wf[((size_t)t * c.cout + co0 + co) * c.cin + ci0 + ci] = tl[(co * ADAM_TCI + ci) * taps + t];
+    }
+    if (c.wd != nullptr) {
+      for (int o = threadIdx.x; o < NR * taps; o += 256) {
+        const int t = o / NR, r = o - t * NR;
+        const int ci = r / ADAM_TCO, co = r - ci * ADAM_TCO;              // co fastest: 32-byte runs of wd
+        c.wd[((size_t)(taps - 1 - t) * c.cin + ci0 + ci) * c.cout + co0 + co] = tl[(co * ADAM_TCI + ci) * taps + t];
+      }
+    }
+  }
+  const bool vec = !c.tile && ((((uintptr_t)c.p | (uintptr_t)c.g | (uintptr_t)c.m | (uintptr_t)c.v) & 15) == 0);
   const int n4 = vec ? (c.n >> 2) : 0;
   for (int i = threadIdx.x; i < n4; i += 256) {
     float4 p4 = reinterpret_cast<float4*>(c.p)[i];
@@ -66,7 +101,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
     reinterpret_cast<float4*>(c.m)[i] = m4;
     reinterpret_cast<float4*>(c.v)[i] = v4;
   }
-  for (int i = n4 * 4 + threadIdx.x; i < c.n; i += 256) {
+  for (int i = n4 * 4 + threadIdx.x; i < (c.tile ? 0 : c.n); i += 256) {
     const float g = fmaf(wd, c.p[i], c.g[i]);
     const float m = fmaf(b1, c.m[i], (1.f - b1) * g);
     const float v = fmaf(b2, c.v[i], (1.f - b2) * g * g);

@@ -14,6 +14,7 @@ import torch
 from . import _lib as L
 
 CHUNK = 16384          # elements per block
+TILE_CO, TILE_CI = 16, 32      # (co, ci) tile of a packed conv weight per block (csrc/adam.cu: ADAM_TCO, ADAM_TCI)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -75,12 +76,19 @@ class FusedAdam(torch.optim.Optimizer):
             rec = int(L.load().tmf_adam_chunk_bytes())
             rows = []
             for pp, gp, mp, vp, n, wf, wd, cout, cin, taps in key:
+                if wf and cout % TILE_CO == 0 and cin % TILE_CI == 0 and taps <= 27:
+                    # conv weight with operand packs: one block per (16 co x 32 ci) tile with all its taps -- the kernel
+                    # transposes the tile in shared memory so that the bf16 pack stores are whole 32 / 64-byte runs
+                    for co0 in range(0, cout, TILE_CO):
+                        for ci0 in range(0, cin, TILE_CI):
+                            rows.append((pp, gp, mp, vp, wf, wd, TILE_CO * TILE_CI * taps, co0 * cin + ci0, cout, cin, taps, 1))
+                    continue
                 for off in range(0, n, CHUNK):
                     rows.append((pp + 4 * off, gp + 4 * off, mp + 4 * off, vp + 4 * off, wf, wd, min(CHUNK, n - off), off,
                                  cout, cin, taps, 0))
             arr = np.array(rows, dtype=np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("wf", "<u8"),
                                                  ("wd", "<u8"), ("n", "<i4"), ("off", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
-                                                 ("taps", "<i4"), ("pad", "<i4")]))
+                                                 ("taps", "<i4"), ("tile", "<i4")]))
             assert arr.dtype.itemsize == rec
             # pinned staging buffer + async copy: legal inside CUDA-graph capture (the captured backward hands out
             # new, then static, gradient buffers, so the table is rebuilt once while capturing)
