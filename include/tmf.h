@@ -55,6 +55,9 @@ int64_t tmf_launch_count(void);
 /* programmatic dependent launch of the train-step kernels (default off; TMF_PDL=1 in the environment turns it on): each
  * kernel waits for its stream predecessors before its first global access, so results are identical either way */
 int tmf_set_pdl(int on);
+/* which attention kernels tmf_attn_fwd / tmf_attn_bwd try first (TMF_ATTN_IMPL, read once): 2 = tensor-core (attention_mma.cu,
+ * default), 1 = register-tiled fp32 (attention.cu), 0 = row-per-warp fp32 (fusion_ops.cu) */
+int tmf_attn_impl_default(void);
 int tmf_get_pdl(void);
 /* TMF_STAT_ROWS, for callers that size statistics buffers without the header */
 int tmf_stat_rows(void);
