@@ -98,6 +98,14 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
                         const float* const* bcoef, const float* const* x, float* const* dw, int B, int D, int H,
                         int W, int cout, float slope, void* ws, size_t ws_bytes, void* stream);
 int64_t tmf_conv1_bwd_fused_workspace_bytes(int ng, int B, int D, int H, int W, int cout);
+/* The same pass in two calls: the bf16 hi/lo split of the input image depends on x alone, so a caller that knows x early
+ * (the forward pass) runs tmf_conv1_bwd_split_x() ahead of time, possibly on another stream, and later calls
+ * tmf_conv1_bwd_fused_presplit() with the SAME workspace (stream-ordered after the split). */
+int tmf_conv1_bwd_split_x(int ng, const float* const* x, int B, int D, int H, int W, int cout, void* ws, size_t ws_bytes,
+                          void* stream);
+int tmf_conv1_bwd_fused_presplit(int ng, const void* const* dout, const void* const* y, const float* const* coef,
+                                 const float* const* bcoef, float* const* dw, int B, int D, int H, int W, int cout,
+                                 float slope, void* ws, size_t ws_bytes, void* stream);
 
 /* 3x3x3 (pad 1) or 1x1x1 convolution, bf16 NDHWC input a[B,D,H,W,Cin], packed bf16 weights wf[tap][Cout][Cin],
  * optional fp32 bias, bf16 output y[B,D,H,W,Cout], optional stats (as above; NULL array = none).

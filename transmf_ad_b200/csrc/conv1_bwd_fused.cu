@@ -390,6 +390,10 @@ static C1BPlan c1b_plan(int ng, int B, int D, int H, int W, int cout) {
 
 using namespace tmf;
 
+static int conv1_bwd_fused_impl(int ng, const void* const* dout, const void* const* y, const float* const* coef,
+                               const float* const* bcoef, const float* const* x, float* const* dw, int B, int D, int H, int W,
+                               int cout, float slope, void* ws, size_t ws_bytes, void* stream, int mode);
+
 extern "C" {
 
 int64_t tmf_conv1_bwd_fused_workspace_bytes(int ng, int B, int D, int H, int W, int cout) {
@@ -400,6 +404,29 @@ int64_t tmf_conv1_bwd_fused_workspace_bytes(int ng, int B, int D, int H, int W, 
 int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, const float* const* coef,
                         const float* const* bcoef, const float* const* x, float* const* dw, int B, int D, int H, int W,
                         int cout, float slope, void* ws, size_t ws_bytes, void* stream) {
+  return conv1_bwd_fused_impl(ng, dout, y, coef, bcoef, x, dw, B, D, H, W, cout, slope, ws, ws_bytes, stream, 0);
+}
+
+// The bf16 hi/lo split of the input image (145 MB written per step at B = 8, 42 us) depends on x alone: callers that know x
+// early (the forward pass) run it ahead of time on another stream with tmf_conv1_bwd_split_x() and then call
+// tmf_conv1_bwd_fused_presplit() with the SAME workspace, which skips the split.
+int tmf_conv1_bwd_split_x(int ng, const float* const* x, int B, int D, int H, int W, int cout, void* ws, size_t ws_bytes,
+                          void* stream) {
+  return conv1_bwd_fused_impl(ng, nullptr, nullptr, nullptr, nullptr, x, nullptr, B, D, H, W, cout, 0.f, ws, ws_bytes, stream, 1);
+}
+
+int tmf_conv1_bwd_fused_presplit(int ng, const void* const* dout, const void* const* y, const float* const* coef,
+                                 const float* const* bcoef, float* const* dw, int B, int D, int H, int W, int cout,
+                                 float slope, void* ws, size_t ws_bytes, void* stream) {
+  return conv1_bwd_fused_impl(ng, dout, y, coef, bcoef, nullptr, dw, B, D, H, W, cout, slope, ws, ws_bytes, stream, 2);
+}
+
+}  // extern "C"
+
+// mode 0: split + fused pass, 1: split only, 2: fused pass on an already split image
+static int conv1_bwd_fused_impl(int ng, const void* const* dout, const void* const* y, const float* const* coef,
+                               const float* const* bcoef, const float* const* x, float* const* dw, int B, int D, int H, int W,
+                               int cout, float slope, void* ws, size_t ws_bytes, void* stream, int mode) {
   TMF_CHECK_NG(ng);
   const C1BPlan pl = c1b_plan(ng, B, D, H, W, cout);
   TMF_REQUIRE(pl.ok, "conv1_bwd_fused: unsupported problem (Cout=%d, %dx%dx%d); use bn_act_pool_bwd_apply + conv1_wgrad",
@@ -425,13 +452,15 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
   GroupPtr<__nv_bfloat16> gx6;
   GroupPtr<const float> gpart;
   GroupPtr<float> gdw;
-  if (!load_group(gx, x, ng, true, "x") || !load_group(gdw, dw, ng, true, "dw")) return 1;
+  if (!load_group(gx, x, ng, mode != 2, "x") || !load_group(gdw, dw, ng, mode != 1, "dw")) return 1;
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  for (int g = 0; g < TMF_MAX_GROUPS; ++g) gx6.p[g] = nullptr;
   for (int g = 0; g < ng; ++g) {
-    TMF_REQUIRE(dout[g] && y[g] && coef[g] && bcoef[g], "conv1_bwd_fused: NULL device pointer");
-    TMF_REQUIRE(((uintptr_t)dout[g] & 15) == 0 && ((uintptr_t)y[g] & 15) == 0, "conv1_bwd_fused: tensors must be 16-byte aligned");
     uint8_t* base = (uint8_t*)ws + (size_t)g * (xbytes + pbytes);
     gx6.p[g] = (__nv_bfloat16*)base;
+    if (mode == 1) continue;
+    TMF_REQUIRE(dout[g] && y[g] && coef[g] && bcoef[g], "conv1_bwd_fused: NULL device pointer");
+    TMF_REQUIRE(((uintptr_t)dout[g] & 15) == 0 && ((uintptr_t)y[g] & 15) == 0, "conv1_bwd_fused: tensors must be 16-byte aligned");
     p.part[g] = (float*)(base + xbytes);
     gpart.p[g] = p.part[g];
     p.coef[g] = coef[g];
@@ -466,13 +495,16 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
       TMF_REQUIRE(r == CUDA_SUCCESS, "conv1_bwd_fused: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     }
   }
-  {
+  if (mode != 2) {
     const int rows = B * D * H;
     const long long total = (long long)rows * (pl.P / 8);
-    dim3 grid((unsigned)min((long long)148 * 8, (total + 255) / 256), 1, ng);
+    // at most ~4 blocks (1024 threads) per SM in all: run ahead of time on a side stream (mode 1) the kernel must leave thread
+    // slots to the kernels of the main stream
+    dim3 grid((unsigned)min((long long)(148 * 4 / ng), (total + 255) / 256), 1, ng);
     launch_k(conv1_split_x_kernel, grid, 256, 0, st, gx, gx6, rows, W, pl.P);
     TMF_LAUNCH_CHECK();
   }
+  if (mode == 1) return 0;
   static bool attr_done = false;
   if (!attr_done) {
     TMF_CUDA(cudaFuncSetAttribute(conv1_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -484,5 +516,3 @@ int tmf_conv1_bwd_fused(int ng, const void* const* dout, const void* const* y, c
   TMF_LAUNCH_CHECK();
   return 0;
 }
-
-}  // extern "C"

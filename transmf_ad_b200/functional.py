@@ -245,6 +245,29 @@ class SNetFunction(torch.autograd.Function):
                 saved.append((act, y, coef, wd, dims, ymax))
             act = out
             dims = (Do, Ho, Wo)
+        # The fused block-1 backward (conv1_bwd_fused.cu) reads the input image as six bf16 hi/lo planes.  That split depends
+        # on x alone: it is launched HERE, behind the last forward launch of the towers, on a side stream (a parallel branch of a
+        # captured graph), so that it runs beside the fusion transformer / heads / the small deep layers of the backward pass,
+        # which leave most of the GPU idle -- instead of in front of the backward kernel (145 MB written, 42 us at B = 8).
+        # (Launched at the START of the forward pass it ran beside conv1.0 forward and cost that kernel what it saved.)
+        ctx.c1split = None
+        cout0, pool0 = spec.layers[0][1], spec.layers[0][3]
+        if (need_grad and pool0 == L.POOL_MAX and impl != L.CONV_DIRECT and len(spec.layers) > 1
+                and os.environ.get("TMF_C1B_PRESPLIT", "1") != "0"):
+            nws0 = int(L.load().tmf_conv1_bwd_fused_workspace_bytes(ng, B, D, H, W, cout0))
+            if nws0 > 0:
+                ws0 = torch.empty(nws0, dtype=torch.uint8, device=dev)
+                cur = torch.cuda.current_stream(dev)
+                side = _side_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    L.call("tmf_conv1_bwd_split_x", ng, L.ptrs(xs), B, D, H, W, cout0, L.ptr(ws0), nws0)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                ws0.record_stream(side)
+                for x in xs:
+                    x.record_stream(side)
+                ctx.c1split = (ws0, nws0, ev)
         ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
         ctx.hyper = run.hyper
         ctx.params = params if need_grad else None          # references only (gradient slots of the flat DP buffer)
@@ -339,9 +362,16 @@ class SNetFunction(torch.autograd.Function):
                 fused_ws = int(L.load().tmf_conv1_bwd_fused_workspace_bytes(ng, B, Dl, Hl, Wl, cout))
             if fused_ws > 0:
                 # block 1: BN/LeakyReLU/MaxPool backward "apply" + conv1.0 weight gradient in one pass; dy stays on chip
-                ws = torch.empty(fused_ws, dtype=torch.uint8, device=dev)
-                L.call("tmf_conv1_bwd_fused", ng, L.ptrs(dout), L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef), L.ptrs(act),
-                       L.ptrs(dw), B, Dl, Hl, Wl, cout, slope, L.ptr(ws), fused_ws)
+                if ctx.c1split is not None and ctx.c1split[1] == fused_ws:
+                    ws, _, ev = ctx.c1split
+                    torch.cuda.current_stream(dev).wait_event(ev)        # the image split launched by the forward pass
+                    L.call("tmf_conv1_bwd_fused_presplit", ng, L.ptrs(dout), L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef),
+                           L.ptrs(dw), B, Dl, Hl, Wl, cout, slope, L.ptr(ws), fused_ws, tag="tmf_conv1_bwd_fused")
+                    ctx.c1split = None
+                else:
+                    ws = torch.empty(fused_ws, dtype=torch.uint8, device=dev)
+                    L.call("tmf_conv1_bwd_fused", ng, L.ptrs(dout), L.ptrs(y), L.ptrs(coef), L.ptrs(bcoef), L.ptrs(act),
+                           L.ptrs(dw), B, Dl, Hl, Wl, cout, slope, L.ptr(ws), fused_ws)
                 SNetFunction._layer_grads(ctx, pgrads, l, dw, dbias, dgamma, dbeta)
                 saved[l] = None
                 continue
