@@ -250,10 +250,12 @@ class SNetFunction(torch.autograd.Function):
         # captured graph), so that it runs beside the fusion transformer / heads / the small deep layers of the backward pass,
         # which leave most of the GPU idle -- instead of in front of the backward kernel (145 MB written, 42 us at B = 8).
         # (Launched at the START of the forward pass it ran beside conv1.0 forward and cost that kernel what it saved.)
+        # OFF by default (TMF_C1B_PRESPLIT=1): measured on B200 over 60 graph replays the step is 4.304 ms with the early split
+        # and 4.295 ms without -- the parallel branch costs the kernels it overlaps what it saves the backward pass.
         ctx.c1split = None
         cout0, pool0 = spec.layers[0][1], spec.layers[0][3]
         if (need_grad and pool0 == L.POOL_MAX and impl != L.CONV_DIRECT and len(spec.layers) > 1
-                and os.environ.get("TMF_C1B_PRESPLIT", "1") != "0"):
+                and os.environ.get("TMF_C1B_PRESPLIT", "0") != "0"):
             nws0 = int(L.load().tmf_conv1_bwd_fused_workspace_bytes(ng, B, D, H, W, cout0))
             if nws0 > 0:
                 ws0 = torch.empty(nws0, dtype=torch.uint8, device=dev)
