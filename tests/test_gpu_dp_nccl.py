@@ -25,9 +25,12 @@ def test_two_rank_nccl_gradients_and_graph_path(kind):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     env = dict(os.environ, DP_MODEL=kind, PYTHONDONTWRITEBYTECODE="1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_nccl_worker.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for attempt in range(4):                        # a "free" port can be taken again before torchrun binds it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_nccl_worker.py")]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0 and "DP_NCCL_OK" in r.stdout

@@ -191,3 +191,31 @@ def test_full_size_step_is_bitwise_reproducible():
         assert torch.isfinite(g1[k]).all(), k
         assert torch.equal(g1[k], g2[k]), k
     assert model.mri_cnn(mri).shape == (2, 128, 5, 6, 5)
+
+
+@pytest.mark.parametrize("kind,kwargs", [("model_CNN_ad", dict(dim=128)),
+                                         ("model_ad", dict(dim=128, depth=1, heads=4, dim_head=32, mlp_dim=512, dropout=0.))])
+def test_flat_gradient_slots_leave_every_gradient_unchanged(kind, kwargs):
+    """With a FlatGradReducer installed (what bench.py and the data-parallel path run, world size 1 included) the backward
+    kernels write weight gradients straight into the slots of the flat buffer.  Every gradient must equal, BITWISE, the one
+    computed without slots -- in particular those of the discriminator ``D``, which runs twice per forward pass (reference
+    mymodel.py:210-211): its second backward call must not write into the slot that still holds the first contribution."""
+    from transmf_ad_b200.dp import FlatGradReducer
+    (mri, pet, label), = _batches(4, (33, 36, 34), 1)
+    plain = _model(kind, kwargs, seed=7)
+    _loss(plain(mri, pet), label)[0].backward()
+    slotted = _model(kind, kwargs, seed=7)
+    red = FlatGradReducer(model=slotted).install()
+    try:
+        for _ in range(2):                                  # twice: the hand-out bookkeeping must reset between backward passes
+            slotted.zero_grad(set_to_none=True)
+            _loss(slotted(mri, pet), label)[0].backward()
+            red.finish()
+            torch.cuda.synchronize()
+            for (k, p), q in zip(slotted.named_parameters(), plain.parameters()):
+                assert torch.equal(p.grad, q.grad), f"{k}: max |diff| {float((p.grad - q.grad).abs().max())}"
+        slot_of = {id(p): s for p, s in zip(red.params, red.slots)}
+        born = sum(1 for p in slotted.parameters() if p.grad.data_ptr() == slot_of[id(p)].data_ptr())
+        assert born >= 0.8 * len(red.params), (born, len(red.params))       # the slots are actually used
+    finally:
+        red.remove()

@@ -24,17 +24,31 @@ _GRAD_SLOTS = None
 def set_grad_slots(table):
     global _GRAD_SLOTS
     _GRAD_SLOTS = table
+    _SLOT_HANDED.clear()
+
+
+_SLOT_HANDED = {}        # parameter address -> id of the backward pass (autograd graph task) that last received its slot
 
 
 def grad_out(param, shape=None, dtype=torch.float32):
     """Output tensor for the gradient of ``param``: its slot of the flat buffer when one is registered (and the parameter
-    is not accumulating into an existing ``.grad``), else a fresh tensor."""
+    is not accumulating into an existing ``.grad``), else a fresh tensor.
+
+    A module that runs TWICE in one forward pass (the discriminator ``D`` of model_ad / model_CNN_ad, reference
+    mymodel.py:210-211) asks twice during one backward pass: only the first request gets the slot -- a second kernel
+    writing into the same memory would overwrite the contribution autograd still holds for the sum (found by the 2-rank
+    NCCL parity test: D.0.weight was twice the PET contribution).  Autograd then adds slot + fresh tensor out of place and
+    ``FlatGradReducer.finish()`` copies the sum into the slot."""
     if _GRAD_SLOTS is not None and param is not None:
         hit = _GRAD_SLOTS.get(param.data_ptr())
         if hit is not None:
             slot, owner = hit
             if owner.grad is None and (shape is None or tuple(slot.shape) == tuple(shape)) and slot.dtype == dtype:
-                return slot.detach()        # a fresh alias: autograd adopts it as .grad only if nobody else holds it
+                task = torch._C._current_graph_task_id()
+                key = param.data_ptr()
+                if task < 0 or _SLOT_HANDED.get(key) != task:
+                    _SLOT_HANDED[key] = task
+                    return slot.detach()    # a fresh alias: autograd adopts it as .grad only if nobody else holds it
     return torch.empty(tuple(param.shape) if shape is None else tuple(shape), dtype=dtype, device=param.device)
 
 
