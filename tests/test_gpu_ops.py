@@ -70,7 +70,9 @@ def test_conv1_fwd_and_stats(impl, shape, cout):
     ((2, 5, 6, 5), 256, 128, 1), ((1, 22, 27, 22), 64, 64, 3), ((1, 8, 8, 8), 16, 16, 3),
     # block-2 sized planes: several columns per plane, CTA ranges that roll along d and cross column boundaries
     ((1, 45, 54, 45), 32, 32, 3), ((2, 21, 54, 45), 32, 64, 3), ((1, 3, 40, 128), 64, 64, 3), ((3, 1, 9, 7), 32, 32, 3),
-    ((2, 22, 27, 22), 64, 128, 3), ((1, 5, 9, 200), 32, 96, 3)])
+    ((2, 22, 27, 22), 64, 128, 3), ((1, 5, 9, 200), 32, 96, 3),
+    # Cin = 32, Cout a multiple of 64: the non-stacked column kernel (64 channels per CTA), one and two channel blocks
+    ((2, 7, 12, 30), 32, 128, 3), ((1, 4, 33, 70), 32, 64, 3)])
 def test_conv3d_fwd_dgrad_wgrad(impl, shape, cin, cout, ks):
     B, D, H, W = shape
     lib = L.load()

@@ -43,12 +43,13 @@ constexpr int CC_TILE_OUT = 126;                // outputs per 128-row M tile (2
 constexpr int CC_MAX_SLOTS = 10;
 constexpr int CC_CO = 32;                       // output channels per CTA (slice of Cout)
 constexpr int CC_NSTACK = 3 * CC_CO;            // MMA N
+constexpr int CC_NS_CO = 64;                    // output channels per CTA of the non-stacked variant (NS, see the kernel)
 constexpr int CC_NBUF = 4;                      // accumulator buffers
 constexpr int CC_MAX_VG = 8;                    // towers x Cout slices
 constexpr uint32_t CC_SMEM_BUDGET = 227 * 1024;
 constexpr uint32_t CC_XCHG_BYTES = 2 * 2 * 4 * 3 * 32 * 4;   // [parity][group][quarter][D1_0, D2_0, D2_1][32 ch] floats
 constexpr uint32_t CC_FIXED_SMEM = 1024 /*align*/ + 8 * (2 * CC_MAX_SLOTS) + 8 + 8 * 2 * CC_NBUF + 24 + CC_XCHG_BYTES + 2048 /*stats: [8 warps][2][32]*/ +
-                                   128 /*bias*/ + 64;
+                                   256 /*bias*/ + 64;
 
 struct alignas(64) ColConvParams {
   CUtensorMap tmA[TMF_MAX_GROUPS];
@@ -61,6 +62,7 @@ struct alignas(64) ColConvParams {
   int qneed;                      // positions of a plane that hold outputs: (H-1)*Wp + W
   int steps_per_group;            // B * NC * D
   uint32_t layout, slot_bytes, a_tx_bytes, b_bytes, idesc;
+  int ns;                         // non-stacked variant (template NS)
   int debug;                      // bring-up switches (TMF_COL_DEBUG): 1 no shift, 2 no stores/stats, 8 no MMAs, 32 role timing
 };
 
@@ -73,14 +75,37 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
   acc += clock64() - t0;
 }
 
-// KSTEPS = Cin / 16 (2 or 4)
-template <int KSTEPS>
-__global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __grid_constant__ ColConvParams p) {
+// KSTEPS = Cin / 16 (2 or 4).
+// NS ("not stacked", Cin = 32 with Cout a multiple of 64: conv2.3 forward).  With K = 32 per tap the kw-stacked tile does
+// only 18 MMAs for an epilogue of 96 accumulator columns and a two-row shift, and is bound by that epilogue (the issuers wait
+// 25-35 % of the time for a free accumulator, 48 % tensor pipe); Cout = 64 as two 32-channel slices also reads the input
+// twice.  Here the CTA takes 64 output channels at once, every tap is its own N = 64 MMA with the A window shifted by
+// kh * Wp + kw rows (54 MMAs per tile over the three issuer threads; the same 1728 tensor-pipe cycles per 128 x 64 outputs),
+// all 128 rows of a tile are outputs, and the epilogue is a plain TMEM read: the two groups split the 64 channels of EVERY
+// output (32 columns per thread instead of 96, no shuffles, no exchange, no group barrier).
+// Role layout (the same for both variants).  Measured for NS and dropped: six issuers with two sub-accumulators per output (one
+// per k-step parity; 512 threads at 128 registers) ran 193 us against 171 us -- the epilogue then reads twice the TMEM bytes
+// (64 B per cycle and SM) and lost its registers; two sub-accumulators with three issuers changed nothing (178 us), i.e. MMAs
+// into the same accumulator do pipeline and the ~140 cycles per tcgen05.mma are the issuing thread's own (R2UR / LDCU /
+// UIADD3 chain per descriptor, cuobjdump -sass).
+template <bool NS> struct ColRoles {
+  static constexpr int MMA_WARPS = CC_MMA_WARPS;
+  static constexpr int FIRST_EPI = CC_FIRST_EPI;
+  static constexpr int THREADS = 32 * (FIRST_EPI + CC_EPI_WARPS);
+};
+template <int KSTEPS, bool NS>
+__global__ void __launch_bounds__(ColRoles<NS>::THREADS, 1) conv3d_umma_col_kernel(const __grid_constant__ ColConvParams p) {
   pdl_entry();
+  constexpr int MMA_WARPS = ColRoles<NS>::MMA_WARPS, FIRST_EPI = ColRoles<NS>::FIRST_EPI;
   constexpr uint32_t PITCH = KSTEPS * 32u;          // bytes per smem row (= Cin * 2)
   constexpr uint32_t ROW_UNITS = PITCH >> 4;
   constexpr uint32_t SBO = 8u * PITCH;
-  constexpr uint32_t TAP_UNITS = (uint32_t)CC_CO * ROW_UNITS;   // one tap of the slice's weights, in 16-byte units
+  constexpr int NCO = NS ? CC_NS_CO : CC_CO;        // output channels of this CTA
+  constexpr int NMMA = NS ? CC_NS_CO : CC_NSTACK;   // MMA N
+  constexpr int NSUB = 1;                           // sub-accumulators per output (see ColRoles)
+  constexpr int NCOLS = NMMA * NSUB;                // TMEM columns per accumulator buffer
+  constexpr int TILE_OUT = NS ? 128 : CC_TILE_OUT;  // outputs per 128-row tile
+  constexpr uint32_t TAP_UNITS = (uint32_t)NCO * ROW_UNITS;     // one tap of the slice's weights, in 16-byte units
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -105,20 +130,20 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
   const int ngv = p.ng * p.nsplit;
   const int gv = blockIdx.x % ngv;                  // virtual group = (tower, Cout slice)
   const int g = gv / p.nsplit;
-  const int co_off = (gv % p.nsplit) * CC_CO;
+  const int co_off = (gv % p.nsplit) * NCO;
   const int cta = blockIdx.x / ngv, ncta = gridDim.x / ngv;
   const int s_begin = (int)(((int64_t)cta * p.steps_per_group) / ncta);
   const int s_end = (int)(((int64_t)(cta + 1) * p.steps_per_group) / ncta);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.S; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, CC_MMA_WARPS); }
+    for (int i = 0; i < p.S; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, MMA_WARPS); }
     mbar_init(b_full, 1);
-    for (int i = 0; i < CC_NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, CC_EPI_WARPS / 2); }
+    for (int i = 0; i < CC_NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, NS ? CC_EPI_WARPS : CC_EPI_WARPS / 2); }
     fence_barrier_init();
     prefetch_tmap(&p.tmA[g]);
     prefetch_tmap(&p.tmB[g]);
   }
-  if (threadIdx.x < CC_CO) bias_ptr[threadIdx.x] = (p.bias[g] != nullptr) ? p.bias[g][co_off + threadIdx.x] : 0.f;
+  if (threadIdx.x < NCO) bias_ptr[threadIdx.x] = (p.bias[g] != nullptr) ? p.bias[g][co_off + threadIdx.x] : 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -144,7 +169,7 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
         const int c = col % p.NC, n = col / p.NC;
         const int len = min(p.D - d, s_end - s);
         const int pa = max(d - 1, 0), pb = min(d + len, p.D - 1);
-        const int h0 = (c * CC_TILE_OUT) / p.Wp;
+        const int h0 = (c * TILE_OUT) / p.Wp;
         for (int pl = pa; pl <= pb; ++pl, ++jw) {
           mbar_wait_t(a_empty + 8 * slot, ph ^ 1u, t_wait, prof);      // every lane sees every phase (see header)
           if ((jw % CC_TMA_LANES) == lane) {
@@ -158,9 +183,10 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
       if (prof && blockIdx.x == 0 && lane == 0)
         printf("col prof: producer lane 0: total %lld cyc, waiting for a free slot %lld\n", clock64() - t_start, t_wait);
     }
-  } else if (warp < CC_FIRST_EPI) {
+  } else if (warp <= MMA_WARPS) {
     // =========================================== MMA issuers ============================================
     const int issuer = warp - 1;
+    const int sub = issuer / CC_MMA_WARPS;          // NS: which k-step parity / sub-accumulator this issuer feeds (else 0)
     if (s_begin < s_end && elect_one()) {
       const uint64_t desc_hi = make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFFFFFF00000000ull;
       const uint32_t desc_lo_const = (uint32_t)(make_smem_desc(0, 16, SBO, p.layout, 0) & 0xFFFF0000ull);
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
         const int len = min(p.D - d0, s_end - s);
         const int da = d0, db = d0 + len - 1;
         const int pa = max(da - 1, 0), pb = min(db + 1, p.D - 1);
-        const uint32_t qoff_units = (uint32_t)((c * CC_TILE_OUT) % p.Wp) * ROW_UNITS;
+        const uint32_t qoff_units = (uint32_t)((c * TILE_OUT) % p.Wp) * ROW_UNITS;
         for (int pl = pa; pl <= pb; ++pl) {
           mbar_wait_t(a_full + 8 * slot, ph, t_full, prof);
           tc_fence_after();
@@ -199,17 +225,32 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
               mbar_wait_t(acc_empty + 8 * as, ((uint32_t)(io / CC_NBUF) & 1u) ^ 1u, t_acc, prof);
               tc_fence_after();
             }
-            if ((io % CC_MMA_WARPS) != issuer) continue;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * CC_NSTACK);
+            if ((io % CC_MMA_WARPS) != (issuer % CC_MMA_WARPS)) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * NCOLS);
             if (!no_mma) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
-                const uint32_t b_lo = b0_lo + (uint32_t)((kd * 3 + kh) * 3) * TAP_UNITS;
-                const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units;
+                if (NS) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
-                              (!first || kh != 0 || k != 0) ? 1u : 0u);
+                  for (int kw = 0; kw < 3; ++kw) {
+                    const uint32_t b_lo = b0_lo + (uint32_t)((kd * 3 + kh) * 3 + kw) * TAP_UNITS;
+                    const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units + (uint32_t)kw * ROW_UNITS;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      if ((k % NSUB) != sub) continue;                 // the other issuer of this output
+                      mma_bf16_ss(d_tmem + (uint32_t)(sub * NMMA), desc_hi | (uint64_t)(a_lo + 2u * k),
+                                  desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                                  (!first || kh != 0 || kw != 0 || k >= NSUB) ? 1u : 0u);
+                    }
+                  }
+                } else {
+                  const uint32_t b_lo = b0_lo + (uint32_t)((kd * 3 + kh) * 3) * TAP_UNITS;
+                  const uint32_t a_lo = a_slab + (uint32_t)kh * wp_units;
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    mma_bf16_ss(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                                (!first || kh != 0 || k != 0) ? 1u : 0u);
+                }
               }
             }
             if (pl == min(o + 1, p.D - 1)) mma_commit(acc_full + 8 * as);   // last contribution: output o is complete
@@ -224,11 +265,11 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
         printf("col prof: issuer %d: total %lld cyc, waiting for input planes %lld, for a free accumulator %lld (%d outputs)\n",
                issuer, clock64() - t_start, t_full, t_acc, s_end - s_begin);
     }
-  } else {
+  } else if (warp >= FIRST_EPI) {
     // =========================================== epilogue ================================================
     // Two groups of 4 warps (one per TMEM lane quarter); outputs alternate between the groups, so two accumulators are
     // drained concurrently.  A thread owns one output row and all 32 channels of the slice, processed 16 at a time.
-    const int ew = warp - CC_FIRST_EPI;
+    const int ew = warp - FIRST_EPI;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int eg = ew >> 2;                       // epilogue group
     const int row = quarter * 32 + lane;
@@ -247,13 +288,64 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
     long long t_epi = 0;
     const long long t_epi0 = clock64();
     uint32_t xb = 0;                              // exchange buffer parity
-    int it = eg;
-    int s = s_begin + eg;
+    int it = NS ? 0 : eg;
+    int s = s_begin + (NS ? 0 : eg);
     int d = s % p.D, col = s / p.D;
     bool new_col = true, valid = false;
     const int64_t dstride = (int64_t)p.H * p.W * p.cout;
     __nv_bfloat16* ycol = yg;
-    for (; s < s_end; s += 2, it += 2) {
+    if (NS) {
+      // every output, this group's 32 of the CTA's 64 channels: TMEM columns [32 eg, 32 eg + 32) of the accumulator buffer
+      const int ch0 = 32 * eg;
+      for (; s < s_end; ++s, ++it) {
+        if (new_col) {
+          const int c = col % p.NC, n = col / p.NC;
+          const int q = c * TILE_OUT + row;
+          const int h = q / p.Wp, w = q - h * p.Wp;
+          valid = (h < p.H) && (w < p.W) && !no_store;
+          ycol = yg + (((int64_t)n * p.D * p.H + h) * p.W + w) * p.cout + co_off + ch0;
+          new_col = false;
+        }
+        __nv_bfloat16* yrow = ycol + d * dstride;
+        if (++d >= p.D) { d = 0; ++col; new_col = true; }
+        const int as = it & (CC_NBUF - 1);
+        mbar_wait_t(acc_full + 8 * as, (uint32_t)(it / CC_NBUF) & 1u, t_epi, prof);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NCOLS + ch0);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[16];
+          tmem_ld16(taddr + hf * 16, r);
+          tmem_ld_wait();
+          if (hf == 1) {                                                // last TMEM read of this accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+          }
+          if (valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t a2 = pair_u32(r[2 * j], r[2 * j + 1]);
+              const uint64_t o = has_bias ? add2_f32(a2, bias2[(ch0 >> 1) + hf * 8 + j]) : a2;
+              pk[j] = pack_bf16(__uint_as_float(lo_u32(o)), __uint_as_float(hi_u32(o)));
+            }
+            if (want_stats) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint64_t f = pair_u32(pk[j] << 16, pk[j] & 0xffff0000u);        // the stored (rounded) values
+                acc_s[hf * 8 + j] = add2_f32(acc_s[hf * 8 + j], f);
+                acc_q[hf * 8 + j] = fma2_f32(f, f, acc_q[hf * 8 + j]);
+              }
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + hf * 16), "r"(pk[0]), "r"(pk[1]),
+                         "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                         : "memory");
+          }
+        }
+      }
+    }
+    for (; !NS && s < s_end; s += 2, it += 2) {
       if (new_col) {                              // (every D / 2 outputs: the divisions stay out of the per-output path)
         const int c = col % p.NC, n = col / p.NC;
         const int q = c * CC_TILE_OUT + row;
@@ -369,8 +461,16 @@ __global__ void __launch_bounds__(CC_THREADS, 1) conv3d_umma_col_kernel(const __
         }
       }
       asm volatile("bar.sync 3, %0;" ::"r"(32 * CC_EPI_WARPS) : "memory");
-      const int i = threadIdx.x - 32 * CC_FIRST_EPI;
-      if (i < 2 * CC_CO) {
+      const int i = threadIdx.x - 32 * FIRST_EPI;
+      if (NS) {
+        if (i < 2 * NCO) {                          // i = which * 64 + channel; the channel's group holds it in its four warps
+          const int which = i / NCO, ch = i - which * NCO, grp = ch >> 5, j = ch & 31;
+          double tot = 0.0;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) tot += (double)stats_ptr[(grp * 4 + w4) * 64 + which * 32 + j];
+          stat_row_store(p.stats[g], 2 * p.cout, cta, ncta, which * p.cout + co_off + ch, tot);
+        }
+      } else if (i < 2 * CC_CO) {
         double tot = 0.0;
 #pragma unroll
         for (int w8 = 0; w8 < CC_EPI_WARPS; ++w8) tot += (double)stats_ptr[w8 * 64 + i];
@@ -407,7 +507,7 @@ static EncodeTiledFn col_encode_fn() {
 
 struct ColPlan {
   bool ok;
-  int Wp, NH, NC, S, nsplit, qneed;
+  int Wp, NH, NC, S, nsplit, qneed, ns;
   uint32_t slot_bytes, a_tx, b_bytes, smem_bytes, layout;
   CUtensorMapSwizzle swz;
 };
@@ -417,7 +517,13 @@ static ColPlan make_col_plan(int ng, int D, int H, int W, int cin, int cout, int
   pl.ok = false;
   if (ks != 3) return pl;
   if (!(cin == 32 || cin == 64) || cout % CC_CO != 0 || cout < CC_CO) return pl;
-  pl.nsplit = cout / CC_CO;
+  // non-stacked variant: Cin = 32 with 64 output channels per CTA (conv2.3 forward); TMF_COL_NS=0 keeps the kw-stacked tiles
+  {
+    const char* e = getenv("TMF_COL_NS");
+    pl.ns = (cin == 32 && cout % CC_NS_CO == 0 && !(e != nullptr && atoi(e) == 0)) ? 1 : 0;
+  }
+  const int nco = pl.ns ? CC_NS_CO : CC_CO;
+  pl.nsplit = cout / nco;
   if (ng * pl.nsplit > CC_MAX_VG) return pl;
   if (D < 1 || H < 1 || W < 2) return pl;
   const uint32_t pitch = (uint32_t)cin * 2;
@@ -426,9 +532,9 @@ static ColPlan make_col_plan(int ng, int D, int H, int W, int cin, int cout, int
   pl.Wp = W + 1;
   if (pl.Wp > 256) return pl;
   pl.qneed = (H - 1) * pl.Wp + W;
-  pl.b_bytes = 27u * (uint32_t)CC_CO * pitch;
+  pl.b_bytes = 27u * (uint32_t)nco * pitch;
   const uint32_t wbytes = (pl.b_bytes + 1023u) & ~1023u;
-  const int rmax = (pl.Wp - 1) + 127 + 2 * pl.Wp;
+  const int rmax = (pl.Wp - 1) + 127 + 2 * pl.Wp + (pl.ns ? 2 : 0);      // NS: the kw shift is two more rows of the window
   pl.NH = rmax / pl.Wp + 1;
   if (pl.NH > 256) return pl;
   pl.a_tx = (uint32_t)pl.NH * pl.Wp * pitch;
@@ -441,7 +547,8 @@ static ColPlan make_col_plan(int ng, int D, int H, int W, int cin, int cout, int
     }
   }
   if (!pl.ok) return pl;
-  pl.NC = (pl.qneed + CC_TILE_OUT - 1) / CC_TILE_OUT;
+  const int tile_out = pl.ns ? 128 : CC_TILE_OUT;
+  pl.NC = (pl.qneed + tile_out - 1) / tile_out;
   return pl;
 }
 
@@ -467,7 +574,8 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
   p.Wp = pl.Wp; p.NH = pl.NH; p.NC = pl.NC; p.S = pl.S; p.qneed = pl.qneed;
   p.steps_per_group = B * pl.NC * D;
   p.layout = pl.layout; p.slot_bytes = pl.slot_bytes; p.a_tx_bytes = pl.a_tx; p.b_bytes = pl.b_bytes;
-  p.idesc = make_idesc_bf16(128, CC_NSTACK, 0, 0);
+  p.idesc = make_idesc_bf16(128, pl.ns ? CC_NS_CO : CC_NSTACK, 0, 0);
+  p.ns = pl.ns;
   p.debug = getenv("TMF_COL_DEBUG") ? atoi(getenv("TMF_COL_DEBUG")) : 0;
   cudaStream_t st = (cudaStream_t)stream;
   for (int g = 0; g < ng; ++g) {
@@ -491,7 +599,7 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
     {
       cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 27};
       cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
-      cuuint32_t box[3] = {(cuuint32_t)cin, (cuuint32_t)CC_CO, 27};
+      cuuint32_t box[3] = {(cuuint32_t)cin, (cuuint32_t)(pl.ns ? CC_NS_CO : CC_CO), 27};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = encode(&p.tmB[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wf[g]), dims, strides, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -508,18 +616,19 @@ int tmf_conv3d_fwd_col(int ng, const void* const* a, const void* const* wf, cons
   if (per_group > TMF_STAT_ROWS) per_group = TMF_STAT_ROWS;        // one statistics row per CTA of a (tower, slice)
   if (per_group < 1) per_group = 1;
   dim3 grid(per_group * ngv, 1, 1);
-#define TMF_LAUNCH_COL(KST)                                                                                              \
+#define TMF_LAUNCH_COL(KST, NSV)                                                                                         \
   do {                                                                                                                  \
     static bool attr_done = false;                                                                                      \
     if (!attr_done) {                                                                                                   \
-      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_col_kernel<KST>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+      TMF_CUDA(cudaFuncSetAttribute(conv3d_umma_col_kernel<KST, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                     (int)CC_SMEM_BUDGET));                                                              \
       attr_done = true;                                                                                                 \
     }                                                                                                                   \
-    launch_k(conv3d_umma_col_kernel<KST>, grid, CC_THREADS, pl.smem_bytes, st, p);                                            \
+    launch_k(conv3d_umma_col_kernel<KST, NSV>, grid, ColRoles<NSV>::THREADS, pl.smem_bytes, st, p);                                 \
   } while (0)
-  if (cin == 32) TMF_LAUNCH_COL(2);
-  else TMF_LAUNCH_COL(4);
+  if (cin == 32 && pl.ns) TMF_LAUNCH_COL(2, true);
+  else if (cin == 32) TMF_LAUNCH_COL(2, false);
+  else TMF_LAUNCH_COL(4, false);
 #undef TMF_LAUNCH_COL
   TMF_LAUNCH_CHECK();
   return 0;
