@@ -59,6 +59,49 @@ def main():
         return total, ce, ad
 
     batch = (mri[sl].to(dev), pet[sl].to(dev), label[sl].to(dev))
+    if os.environ.get("DP_MODE") == "syncbn":
+        # ---- optional SyncBatchNorm: torch.nn.SyncBatchNorm.convert_sync_batchnorm(model) makes the towers
+        # (our kernels) and the BatchNorm1d heads (torch) normalise over the GLOBAL batch, so `world` ranks with `per` subjects each
+        # reproduce ONE device running the global batch: logits of the shard's rows, running statistics, averaged gradients.
+        whole = fresh()
+        outs = whole(mri.to(dev), pet.to(dev))
+        loss_fn(outs, label.to(dev))[0].backward()
+        synced = torch.nn.SyncBatchNorm.convert_sync_batchnorm(fresh())
+        red = FlatGradReducer(model=synced).install()
+        outs_s = synced(*batch[:2])
+        loss_fn(outs_s, batch[2])[0].backward()
+        red.finish()
+        torch.cuda.synchronize()
+        err_logit = max(float((a - b[sl]).abs().max()) for a, b in zip(outs_s, outs))
+        sd_w, sd_s = whole.state_dict(), synced.state_dict()
+        stat = [(float(((sd_s[k] - v).abs() / (v.abs() + 1e-2)).max()), k) for k, v in sd_w.items() if "running" in k]
+        err_stat, worst_stat = max(stat)
+        g_w = torch.cat([p.grad.flatten() for p in whole.parameters()])
+        g_s = torch.cat([p.grad.flatten() for p in synced.parameters()])
+        cos = float(torch.nn.functional.cosine_similarity(g_w, g_s, dim=0))
+        # the same comparison WITHOUT SyncBatchNorm (per-rank statistics): how far plain data parallelism is from the global batch
+        plain = fresh()
+        red.remove()
+        red2 = FlatGradReducer(model=plain).install()
+        outs_p = plain(*batch[:2])
+        loss_fn(outs_p, batch[2])[0].backward()
+        red2.finish()
+        torch.cuda.synchronize()
+        err_plain = max(float((a - b[sl]).abs().max()) for a, b in zip(outs_p, outs))
+        cos_plain = float(torch.nn.functional.cosine_similarity(g_w, torch.cat([p.grad.flatten() for p in plain.parameters()]), dim=0))
+        red2.remove()
+        if rank == 0:
+            print(f"[dp] syncbn {kind} world {world}: vs one device on the global batch: logits {err_logit:.2e} (per-rank BN: "
+                  f"{err_plain:.2e}), running statistics {err_stat:.2e} rel (worst: {worst_stat}), whole-model gradient cosine "
+                  f"{cos:.4f} (per-rank BN: {cos_plain:.4f})", flush=True)
+        assert err_stat <= 2e-2, (err_stat, worst_stat)
+        assert err_logit <= 5e-2 and err_logit < err_plain, (err_logit, err_plain)
+        assert cos >= 0.97 and cos > cos_plain, (cos, cos_plain)
+        dist.barrier()
+        if rank == 0:
+            print("DP_NCCL_OK", flush=True)
+        dist.destroy_process_group()
+        return
     # ---- 1. eager: reduced gradients == mean of the ranks' own gradients, and ~ mean of per-shard Oracle-A gradients
     model = fresh()
     red = FlatGradReducer(model=model).install()

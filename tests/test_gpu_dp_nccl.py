@@ -20,11 +20,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind", ["model_CNN_ad", "model_ad"])
-def test_two_rank_nccl_gradients_and_graph_path(kind):
+@pytest.mark.parametrize("kind,mode", [("model_CNN_ad", "dp"), ("model_ad", "dp"), ("model_CNN_ad", "syncbn")])
+def test_two_rank_nccl_gradients_and_graph_path(kind, mode):
+    """mode dp: reduced gradients == mean of the ranks' gradients, graph path == eager path.  mode syncbn: with
+    torch.nn.SyncBatchNorm.convert_sync_batchnorm(model) two ranks reproduce one device on the global batch."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    env = dict(os.environ, DP_MODEL=kind, PYTHONDONTWRITEBYTECODE="1")
+    env = dict(os.environ, DP_MODEL=kind, DP_MODE=mode, PYTHONDONTWRITEBYTECODE="1")
     for attempt in range(4):                        # a "free" port can be taken again before torchrun binds it
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_nccl_worker.py")]

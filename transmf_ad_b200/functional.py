@@ -152,11 +152,33 @@ class SNetRun:
     the call site: inside ``Function.forward`` grad mode is always off), and the hyper-parameters read from the
     ``nn.BatchNorm3d`` / ``nn.LeakyReLU`` children -- per layer (eps, momentum, negative_slope)."""
 
-    def __init__(self, training, grad_enabled, hyper=None, packs=None, folds=None):
+    def __init__(self, training, grad_enabled, hyper=None, packs=None, folds=None, sync_group=False):
         self.training, self.grad_enabled = bool(training), bool(grad_enabled)
         self.hyper = hyper if hyper is not None else [(BN_EPS, BN_MOMENTUM, LRELU_SLOPE)] * 7
         self.packs = packs              # per tower: 7 ConvPack (index 0 unused: conv1.0 consumes the fp32 weight)
         self.folds = folds              # per tower: 7 EvalFold (inference path: BatchNorm folded into the conv operands)
+        # False: per-rank BatchNorm statistics (DDP semantics, the default).  None / a process group: the BatchNorm3d children
+        # are nn.SyncBatchNorm (torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)): statistics over the GLOBAL batch
+        self.sync_group = sync_group
+
+
+def _sync_world(group):
+    """World size of the SyncBatchNorm exchange (1: nothing to exchange)."""
+    import torch.distributed as dist
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
+def _allreduce_stat_rows(bufs, group):
+    """SyncBatchNorm: replace the per-CTA partial rows of every tower's statistics buffer by the sum over all ranks (row 0 =
+    the global totals, the other rows zero), so that the finalize kernels see global-batch statistics."""
+    import torch.distributed as dist
+    tot = torch.stack([b.sum(0) for b in bufs])
+    dist.all_reduce(tot, group=group)
+    for b, t in zip(bufs, tot):
+        b.zero_()
+        b[0].copy_(t)
 
 
 def wgrad_workspace(ng, impl, B, D, H, W, cin, cout, ks, dev):
@@ -206,6 +228,7 @@ class SNetFunction(torch.autograd.Function):
         saved = []
         act = xs
         dims = (D, H, W)
+        sync_world = _sync_world(run.sync_group) if training else 1
         for l, (cin, cout, ks, pool) in enumerate(spec.layers):
             Dl, Hl, Wl = dims
             count = B * Dl * Hl * Wl
@@ -236,6 +259,9 @@ class SNetFunction(torch.autograd.Function):
                     L.call("tmf_pack_conv_weights", ng, L.ptrs(w), L.ptrs(wf), L.ptrs(wd), cout, cin, ks)
                 L.call("tmf_conv3d_fwd", ng, L.ptrs(act), L.ptrs(wf), L.ptrs(b), L.ptrs(y), L.ptrs(stats),
                        B, Dl, Hl, Wl, cin, cout, ks, impl, tag=f"tmf_conv3d_fwd@L{l}")
+            if training and sync_world > 1:
+                _allreduce_stat_rows(stats, run.sync_group)           # SyncBatchNorm: global-batch mean / variance
+                count *= sync_world
             coef = list(torch.empty((ng, 4 * cout), dtype=torch.float32, device=dev).unbind(0))
             L.call("tmf_bn_finalize", ng, L.ptrs(stats), L.ptrs([P(t, l, 2) for t in range(ng)]),
                    L.ptrs([P(t, l, 3) for t in range(ng)]), L.ptrs([buffers[t][l][0] for t in range(ng)]),
@@ -286,6 +312,7 @@ class SNetFunction(torch.autograd.Function):
                 ctx.c1split = (ws0, nws0, ev)
         ctx.spec, ctx.training, ctx.ng, ctx.saved, ctx.B = spec, training, ng, saved, B
         ctx.hyper = run.hyper
+        ctx.sync_group, ctx.sync_world = run.sync_group, sync_world
         ctx.params = params if need_grad else None          # references only (gradient slots of the flat DP buffer)
         ctx.impl = impl
         outs = tuple(o.permute(0, 4, 1, 2, 3) for o in act)      # logical (B,C,d,h,w), channels-last memory
@@ -372,6 +399,13 @@ class SNetFunction(torch.autograd.Function):
             bcoef = list(torch.empty((ng, 2 * cout), dtype=torch.float32, device=dev).unbind(0))
             L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(dgamma), L.ptrs(dbeta),
                    L.ptrs(dbias), L.ptrs(bcoef), cout, count, int(training))
+            if training and ctx.sync_world > 1:
+                # SyncBatchNorm: the parameter gradients above are this rank's own (the gradient exchange averages them);
+                # the input gradient needs the GLOBAL means of dz and dz * xhat
+                _allreduce_stat_rows(sums, ctx.sync_group)
+                scratch_g = list(torch.empty((3 * ng, cout), dtype=torch.float32, device=dev).unbind(0))
+                L.call("tmf_bn_bwd_finalize", ng, L.ptrs(sums), L.ptrs(coef), L.ptrs(scratch_g[:ng]), L.ptrs(scratch_g[ng:2 * ng]),
+                       L.ptrs(scratch_g[2 * ng:]), L.ptrs(bcoef), cout, count * ctx.sync_world, int(training))
             dw = [grad_out(PG(t, 0)) for t in range(ng)]
             fused_ws = 0
             if l == 0 and pool == L.POOL_MAX and not dout_fp32 and ctx.impl != L.CONV_DIRECT:

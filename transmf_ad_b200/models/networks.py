@@ -64,7 +64,13 @@ class sNet(nn.Module):
     def _run(self, other=None):
         packs = [self._packs] if other is None else [self._packs, other._packs]
         folds = [self._folds] if other is None else [self._folds, other._folds]
-        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs, folds)
+        # torch.nn.SyncBatchNorm.convert_sync_batchnorm(model) turns the BatchNorm3d children into nn.SyncBatchNorm: the kernels
+        # then normalise with statistics over the global batch (optional row)
+        sync = [isinstance(bn, nn.SyncBatchNorm) for _, bn in self._units()]
+        if any(sync) and not all(sync):
+            raise NotImplementedError("sNet: either every BatchNorm3d is an nn.SyncBatchNorm or none")
+        group = self._units()[0][1].process_group if all(sync) else False
+        return TF.SNetRun(self.training, torch.is_grad_enabled(), self._hyper(), packs, folds, sync_group=group)
 
     def invalidate_packs(self):
         for pk in self._packs:
