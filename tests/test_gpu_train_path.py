@@ -137,6 +137,45 @@ def test_fused_adam_keeps_the_conv_weight_packs_fresh():
     assert step.launches_per_step <= 93, step.launches_per_step
 
 
+def test_fused_adam_keeps_the_encoder_weight_packs_fresh():
+    """The bf16 hi / lo operand packs of the fused transformer encoders (functional.EncPack) are rewritten by FusedAdam's kernel:
+    after graph replays they equal an explicit tmf_encoder_pack_weights of the updated weights, bitwise, and the captured
+    model_ad step contains no pack launch."""
+    from transmf_ad_b200 import _lib as L
+    from transmf_ad_b200.models.networks import Transformer
+    kind, kwargs = "model_ad", dict(dim=128, depth=2, heads=4, dim_head=32, mlp_dim=512, dropout=0.)
+    batches = _batches(4, (33, 36, 34), 2)
+    model = _model(kind, kwargs, seed=3)
+    before = {k: v.clone() for k, v in model.state_dict().items() if "fuse_transformer" in k and k.endswith("weight")}
+    opt = FusedAdam(model.parameters(), lr=LR, weight_decay=0.0)
+    step = GraphedTrainStep(model, opt, _loss, batches[0][:2], batches[0][2], warmup=3)
+    for mri, pet, label in batches:
+        step((mri, pet), label)
+    torch.cuda.synchronize()
+    after = model.state_dict()
+    assert all(not torch.equal(v, after[k]) for k, v in before.items())       # (every encoder weight was updated)
+    encs = [m for m in model.modules() if isinstance(m, Transformer)]
+    assert len(encs) == 4
+    for e in encs:
+        ws = e._enc_weights()
+        pk = e._enc_pack
+        assert pk.pack is not None and not pk.stale(ws, ws[3].shape[0])
+        want = torch.empty_like(pk.pack)
+        L.call("tmf_encoder_pack_weights", *[L.ptr(w.detach()) for w in ws], int(ws[3].shape[0]), L.ptr(want))
+        torch.cuda.synchronize()
+        assert torch.equal(want.view(torch.int16), pk.pack.view(torch.int16))
+    # an eager step with a torch optimizer moves the weights behind the cache: the next forward repacks
+    topt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    mri, pet, label = batches[0]
+    topt.zero_grad()
+    _loss(model(mri, pet), label)[0].backward()
+    topt.step()
+    assert all(e._enc_pack.stale(e._enc_weights(), 512) for e in encs)
+    with torch.no_grad():
+        model(mri, pet)
+    assert not any(e._enc_pack.stale(e._enc_weights(), 512) for e in encs)
+
+
 def test_fused_adam_state_dict_round_trip_matches_torch_adam():
     """a resumed FusedAdam must continue with the loaded step count (bias correction) and moments."""
     torch.manual_seed(0)

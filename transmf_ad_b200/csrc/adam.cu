@@ -24,6 +24,8 @@ struct AdamChunk {
   int32_t cout, cin, taps;
   int32_t tile;            // 1: the chunk is an ADAM_TCO x ADAM_TCI block of (co, ci) pairs with all taps (p/g/m/v = tensor base,
                            // off = co0 * cin + ci0): the pack stores leave through shared memory as whole 32 / 64-byte segments
+                           // 2: weight of a fused transformer encoder: wf / wd are its bf16 hi / lo arrays (enc_fused.cu's operand
+                           // pack, same element order as the parameter): hi = bf16(p), lo = bf16(p - hi) at index off + i
 };
 constexpr int ADAM_TCO = 16, ADAM_TCI = 32, ADAM_MAX_TAPS = 27;
 static_assert(sizeof(AdamChunk) == 72, "host code packs 72-byte chunk records");
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  if (c.tile) {
+  if (c.tile == 1) {
     // Conv weight with operand packs.  The element-wise version scattered two 2-byte stores per element (wf is [tap][co][ci],
     // wd [tap'][ci][co], the parameter [co][ci][tap]): 16x write amplification made this kernel 95 us for 117 MB (ncu r2p).
     __shared__ __nv_bfloat16 tl[ADAM_TCO * ADAM_TCI * ADAM_MAX_TAPS];     // [co][ci][tap]
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
       }
     }
   }
-  const bool vec = !c.tile && ((((uintptr_t)c.p | (uintptr_t)c.g | (uintptr_t)c.m | (uintptr_t)c.v) & 15) == 0);
+  const bool vec = c.tile != 1 && ((((uintptr_t)c.p | (uintptr_t)c.g | (uintptr_t)c.m | (uintptr_t)c.v) & 15) == 0);
   const int n4 = vec ? (c.n >> 2) : 0;
   for (int i = threadIdx.x; i < n4; i += 256) {
     float4 p4 = reinterpret_cast<float4*>(c.p)[i];
@@ -95,13 +97,20 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
       mp[j] = fmaf(b1, mp[j], (1.f - b1) * g);
       vp[j] = fmaf(b2, vp[j], (1.f - b2) * g * g);
       pp[j] -= step_size * (mp[j] / (sqrtf(vp[j]) * inv_sqrt_bc2 + eps));
-      if (c.wf != nullptr) emit_pack(c, 4 * i + j, pp[j]);
+      if (c.tile == 0 && c.wf != nullptr) emit_pack(c, 4 * i + j, pp[j]);
+    }
+    if (c.tile == 2) {                               // (c.off and the chunk size are multiples of 4: 8-byte stores)
+      const uint32_t h01 = pack_bf16(p4.x, p4.y), h23 = pack_bf16(p4.z, p4.w);
+      const uint32_t l01 = pack_bf16(p4.x - bf16_lo(h01), p4.y - bf16_hi(h01));
+      const uint32_t l23 = pack_bf16(p4.z - bf16_lo(h23), p4.w - bf16_hi(h23));
+      *reinterpret_cast<uint2*>(c.wf + c.off + 4 * i) = make_uint2(h01, h23);
+      *reinterpret_cast<uint2*>(c.wd + c.off + 4 * i) = make_uint2(l01, l23);
     }
     reinterpret_cast<float4*>(c.p)[i] = p4;
     reinterpret_cast<float4*>(c.m)[i] = m4;
     reinterpret_cast<float4*>(c.v)[i] = v4;
   }
-  for (int i = n4 * 4 + threadIdx.x; i < (c.tile ? 0 : c.n); i += 256) {
+  for (int i = n4 * 4 + threadIdx.x; i < (c.tile == 1 ? 0 : c.n); i += 256) {
     const float g = fmaf(wd, c.p[i], c.g[i]);
     const float m = fmaf(b1, c.m[i], (1.f - b1) * g);
     const float v = fmaf(b2, c.v[i], (1.f - b2) * g * g);
@@ -109,7 +118,11 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamChunk* __rest
     c.v[i] = v;
     const float pn = c.p[i] - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
     c.p[i] = pn;
-    if (c.wf != nullptr) emit_pack(c, i, pn);
+    if (c.tile == 2) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(pn);
+      c.wf[c.off + i] = hb;
+      c.wd[c.off + i] = __float2bfloat16_rn(pn - __bfloat162float(hb));
+    } else if (c.wf != nullptr) emit_pack(c, i, pn);
   }
   __syncthreads();
   if (threadIdx.x == 0) {

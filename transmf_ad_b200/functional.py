@@ -113,6 +113,34 @@ class ConvPack:
         self.version = w._version
 
 
+class EncPack:
+    """bf16 hi / lo copies of one encoder's five weight matrices (the operand pack of csrc/enc_fused.cu: per matrix
+    [hi | lo], in the order Wq, Wkv, Wo, W1, W2), kept across steps like ``ConvPack``: fresh while every weight's ``_version`` is
+    the one it was packed from; ``optim.FusedAdam`` rewrites the hi / lo values from its own kernel (``_tmf_encpack``), so a
+    train step on FusedAdam has no ``tmf_encoder_pack_weights`` launches (6 per ``model_ad`` step before)."""
+
+    def __init__(self):
+        self.pack, self.key, self.versions = None, None, {}
+
+    def stale(self, ws, mlp):
+        key = tuple(w.data_ptr() for w in ws) + (str(ws[0].device),)
+        if self.pack is None or key != self.key:
+            self.pack = torch.empty(int(L.load().tmf_encoder_pack_bytes(int(mlp))) // 2, dtype=torch.bfloat16, device=ws[0].device)
+            self.key, self.versions = key, {}
+        off = 0
+        for w in ws:
+            n = w.numel()
+            if getattr(w, "_tmf_pack_cache", None) is not self or getattr(w, "_tmf_encpack", (None,))[0] is None \
+                    or w._tmf_encpack[0].data_ptr() != self.pack.data_ptr() + 2 * off:
+                w._tmf_encpack = (self.pack[off:off + n], self.pack[off + n:off + 2 * n])     # optim.FusedAdam reads these
+                w._tmf_pack_cache = self
+            off += 2 * n
+        return any(self.versions.get(w.data_ptr()) != w._version for w in ws)
+
+    def mark(self, w):
+        self.versions[w.data_ptr()] = w._version
+
+
 # Bumped whenever parameters or BatchNorm running statistics change behind torch's version counters (FusedAdam's kernel,
 # train-mode forwards, CUDA-graph replays): the eval-mode BatchNorm folds below are rebuilt when it moves.
 _PARAM_EPOCH = [0]
@@ -601,7 +629,7 @@ class EncoderFunction(torch.autograd.Function):
     params = (ln1_w, ln1_b, wq, wkv, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b)."""
 
     @staticmethod
-    def forward(ctx, x, context, heads, scale, add_input, eps1, eps2, epsf, *params):
+    def forward(ctx, x, context, heads, scale, add_input, eps1, eps2, epsf, pack_cache, *params):
         ln1_w, ln1_b, wq, wkv, wo, bo, ln2_w, ln2_b, w1, b1, w2, b2, lnf_w, lnf_b = [_f32c(t) for t in params]
         x3, c3 = _f32c(x), _f32c(context)
         B, Nq, dim = x3.shape
@@ -614,8 +642,17 @@ class EncoderFunction(torch.autograd.Function):
         # them).  TMF_ENC_BF16=0: three-pass TF32 straight from the fp32 weights (pack = NULL).
         pack = None
         if os.environ.get("TMF_ENC_BF16", "1") != "0":
-            pack = torch.empty(int(L.load().tmf_encoder_pack_bytes(int(mlp))) // 2, dtype=torch.bfloat16, device=dev)
-            L.call("tmf_encoder_pack_weights", L.ptr(wq), L.ptr(wkv), L.ptr(wo), L.ptr(w1), L.ptr(w2), mlp, L.ptr(pack))
+            ws5 = (wq, wkv, wo, w1, w2)
+            cached = pack_cache is not None and all(w is t for w, t in zip(ws5, (params[2], params[3], params[4], params[8], params[10])))
+            if cached:                                      # the module's pack, refreshed by FusedAdam between steps
+                if pack_cache.stale(ws5, mlp):
+                    L.call("tmf_encoder_pack_weights", L.ptr(wq), L.ptr(wkv), L.ptr(wo), L.ptr(w1), L.ptr(w2), mlp, L.ptr(pack_cache.pack))
+                    for w in ws5:
+                        pack_cache.mark(w)
+                pack = pack_cache.pack
+            else:
+                pack = torch.empty(int(L.load().tmf_encoder_pack_bytes(int(mlp))) // 2, dtype=torch.bfloat16, device=dev)
+                L.call("tmf_encoder_pack_weights", L.ptr(wq), L.ptr(wkv), L.ptr(wo), L.ptr(w1), L.ptr(w2), mlp, L.ptr(pack))
         L.call("tmf_encoder_proj_fwd", L.ptr(x3), L.ptr(c3), L.ptr(ln1_w), L.ptr(ln1_b), L.ptr(wq), L.ptr(wkv), L.ptr(h1),
                L.ptr(mean1), L.ptr(rstd1), L.ptr(q), L.ptr(kv), Mx, Mc, float(eps1), L.ptr(pack))
         o, lse = E(B, Nq, dim), E(B, heads, Nq)
@@ -676,7 +713,7 @@ class EncoderFunction(torch.autograd.Function):
             _SIDE_PENDING.append(ev)
         else:
             L.call("tmf_encoder_wgrad", table, L.ptr(f), L.ptr(d_w2), L.ptr(d_b2), Mx, Mc, mlp, L.ptr(ws), nws)
-        return (dx.reshape(x3.shape), dctx.reshape(c3.shape), None, None, None, None, None, None,
+        return (dx.reshape(x3.shape), dctx.reshape(c3.shape), None, None, None, None, None, None, None,
                 d_ln1_w, d_ln1_b, d_wq, d_wkv, d_wo, d_bo, d_ln2_w, d_ln2_b, d_w1, d_b1, d_w2, d_b2, d_lnf_w, d_lnf_b)
 
 
@@ -689,8 +726,8 @@ def encoder_supported(dim, inner, mlp):
     return os.environ.get("TMF_ENC_FUSED", "1") != "0" and bool(L.load().tmf_encoder_supported(int(dim), int(inner), int(mlp)))
 
 
-def encoder(x, context, heads, scale, add_input, eps1, eps2, epsf, params):
-    return EncoderFunction.apply(x, context, heads, scale, add_input, eps1, eps2, epsf, *params)
+def encoder(x, context, heads, scale, add_input, eps1, eps2, epsf, params, pack_cache=None):
+    return EncoderFunction.apply(x, context, heads, scale, add_input, eps1, eps2, epsf, pack_cache, *params)
 
 
 class TokenPoolFunction(torch.autograd.Function):

@@ -195,10 +195,31 @@ class Transformer(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([])
         self.norm = nn.LayerNorm(dim)
+        self._enc_pack = TF.EncPack()          # cached bf16 hi / lo operand pack of the fused encoder (depth 1)
         for _ in range(depth):
             self.layers.append(nn.ModuleList([
                 PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout)),
                 PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout))]))
+
+    def _enc_weights(self):
+        attn, ff = self.layers[0]
+        return (attn.fn.to_q.weight, attn.fn.to_kv.weight, attn.fn.to_out[0].weight, ff.fn.net[0].weight, ff.fn.net[3].weight)
+
+    def invalidate_packs(self):
+        self._enc_pack.versions = {}
+
+    def pack_now(self):
+        """(Re-)pack the five weight matrices now (see ``sNet.pack_now``): a CUDA-graph capture that follows then contains no
+        ``tmf_encoder_pack_weights`` launch; ``optim.FusedAdam`` keeps the pack fresh from its own kernel."""
+        from transmf_ad_b200 import _lib as L
+        ws = self._enc_weights()
+        if len(self.layers) != 1 or not ws[0].is_cuda or not TF.encoder_supported(ws[0].shape[1], ws[0].shape[0], ws[3].shape[0]):
+            return
+        pk = self._enc_pack
+        pk.stale(ws, ws[3].shape[0])
+        L.call("tmf_encoder_pack_weights", *[L.ptr(w.detach()) for w in ws], int(ws[3].shape[0]), L.ptr(pk.pack))
+        for w in ws:
+            pk.mark(w)
 
     def _fused_params(self):
         attn, ff = self.layers[0]
@@ -223,7 +244,7 @@ class Transformer(nn.Module):
         if self._can_fuse(x, context):
             attn, ff = self.layers[0]          # the whole encoder in 3 launches (csrc/enc_fused.cu)
             return TF.encoder(x, context, attn.fn.heads, attn.fn.scale, add_input, attn.norm.eps, ff.norm.eps,
-                              self.norm.eps, self._fused_params())
+                              self.norm.eps, self._fused_params(), pack_cache=self._enc_pack)
         x_in = x
         for attn, ff in self.layers:
             x = attn(x, context=context, residual=x)

@@ -64,6 +64,9 @@ class FusedAdam(torch.optim.Optimizer):
                 s["step"] = st["step"]                      # one device counter shared by the group (same value for all)
         def pack_of(p):
             # conv weights whose bf16 operand packs are cached by the module (functional.ConvPack): the kernel refreshes them
+            ep = getattr(p, "_tmf_encpack", None)
+            if ep is not None and ep[0] is not None and ep[0].device == p.device:
+                return (ep[0].data_ptr(), ep[1].data_ptr(), 0, 0, -1)       # taps = -1: encoder hi / lo pack (functional.EncPack)
             pk = getattr(p, "_tmf_pack", None)
             if pk is None or pk[0] is None or pk[0].device != p.device:
                 return (0, 0, 0, 0, 0)
@@ -76,16 +79,17 @@ class FusedAdam(torch.optim.Optimizer):
             rec = int(L.load().tmf_adam_chunk_bytes())
             rows = []
             for pp, gp, mp, vp, n, wf, wd, cout, cin, taps in key:
-                if wf and cout % TILE_CO == 0 and cin % TILE_CI == 0 and taps <= 27:
+                if wf and taps > 0 and cout > 0 and cin > 0 and cout % TILE_CO == 0 and cin % TILE_CI == 0 and taps <= 27:
                     # conv weight with operand packs: one block per (16 co x 32 ci) tile with all its taps -- the kernel
                     # transposes the tile in shared memory so that the bf16 pack stores are whole 32 / 64-byte runs
                     for co0 in range(0, cout, TILE_CO):
                         for ci0 in range(0, cin, TILE_CI):
                             rows.append((pp, gp, mp, vp, wf, wd, TILE_CO * TILE_CI * taps, co0 * cin + ci0, cout, cin, taps, 1))
                     continue
+                enc = taps == -1                    # wf / wd = the hi / lo arrays of an encoder weight (same element order)
                 for off in range(0, n, CHUNK):
                     rows.append((pp + 4 * off, gp + 4 * off, mp + 4 * off, vp + 4 * off, wf, wd, min(CHUNK, n - off), off,
-                                 cout, cin, taps, 0))
+                                 cout, cin, 0 if enc else taps, 2 if enc else 0))
             arr = np.array(rows, dtype=np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("wf", "<u8"),
                                                  ("wd", "<u8"), ("n", "<i4"), ("off", "<i4"), ("cout", "<i4"), ("cin", "<i4"),
                                                  ("taps", "<i4"), ("tile", "<i4")]))
