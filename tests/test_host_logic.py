@@ -112,3 +112,32 @@ def test_fused_adam_host_logic():
         opt.step()                               # CPU parameter: must fail loudly
     with pytest.raises(ValueError):
         FusedAdam([p], amsgrad=True)
+
+
+def test_encoder_pack_cache_follows_the_weight_versions():
+    """functional.EncPack (host logic, no kernels): the cached bf16 hi / lo operand pack of a fused encoder is fresh exactly while
+    every one of the five weight matrices still has the version it was packed from; the slices handed to FusedAdam
+    (``_tmf_encpack``) tile the pack in the order Wq, Wkv, Wo, W1, W2, each as [hi | lo]."""
+    import torch
+    from transmf_ad_b200.models.networks import Transformer
+    enc = Transformer(128, 1, 4, 32, 512)
+    ws = enc._enc_weights()
+    pk = enc._enc_pack
+    assert pk.stale(ws, 512)                                   # never packed
+    assert pk.pack.numel() == 2 * sum(w.numel() for w in ws) and pk.pack.dtype == torch.bfloat16
+    off = 0
+    for w in ws:
+        hi, lo = w._tmf_encpack
+        assert hi.data_ptr() == pk.pack.data_ptr() + 2 * off and lo.data_ptr() == hi.data_ptr() + 2 * w.numel()
+        assert hi.numel() == lo.numel() == w.numel() and w._tmf_pack_cache is pk
+        off += 2 * w.numel()
+    for w in ws:
+        pk.mark(w)
+    assert not pk.stale(ws, 512)
+    with torch.no_grad():
+        ws[3].mul_(1.5)                                        # a torch optimizer / load_state_dict moves W1 in place
+    assert pk.stale(ws, 512)
+    pk.mark(ws[3])
+    assert not pk.stale(ws, 512)
+    enc.invalidate_packs()
+    assert pk.stale(ws, 512)
