@@ -131,6 +131,10 @@ int tmf_conv3d_supported(int op, int impl, int D, int H, int W, int cin, int cou
  * (conv_umma.cu) for this problem (ng towers of batch B: the plan weighs wave quantisation).  out8 = {ok, 128-row tiles per weight pass, issuer warps, accumulator sets,
  * input stages, weight stages, super-tiles per plane, weights resident}.  Returns 0 if the kernel takes the problem. */
 int tmf_conv3d_umma_plan_info(int ng, int B, int D, int H, int W, int cin, int cout, int ksize, int* out8);
+/* host-only: launch plan of the column kernel (conv_umma_col.cu: Cin 32 / 64 layers) for one problem; out6 = {ok, non-stacked
+ * variant (Cin = 32, Cout a multiple of 64), Cout blocks per tower, 128-row tiles per plane, input ring slots, slab rows}.
+ * Returns 0 iff the kernel takes the problem. */
+int tmf_conv3d_col_plan_info(int ng, int D, int H, int W, int cin, int cout, int ksize, int* out6);
 
 /* BatchNorm statistics -> coefficients.  coef[4*C] = {scale = gamma*invstd, shift = beta - mean*scale, mean,
  * invstd}.  training != 0: batch statistics from stats (biased variance), running_mean/var updated with

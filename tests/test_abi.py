@@ -79,3 +79,28 @@ def test_streamed_weight_conv_plans_for_the_bench_layers(built_lib):
             assert p["ok"] == 1 and p["acc_sets"] * p["issuers"] * p["mt"] * cout <= 512
     # unsupported channel counts are refused, not mis-planned
     assert built_lib.tmf_conv3d_umma_plan_info(2, 8, 22, 27, 22, 24, 64, 3, out) != 0
+
+
+def test_column_conv_plans_for_the_bench_layers(built_lib, monkeypatch):
+    """Host-only: the column kernel (Cin 32 / 64) takes conv2.0 .. conv3.3 forward and the matching dgrads at the bench shape;
+    conv2.3 forward (32 -> 64) runs the non-stacked 64-channel variant, everything else the
+    kw-stacked 32-channel slices; TMF_COL_NS=0 switches the variant off."""
+    import ctypes as C
+    out = (C.c_int * 6)()
+
+    def plan(D, H, W, cin, cout, ng=2):
+        rc = built_lib.tmf_conv3d_col_plan_info(ng, D, H, W, cin, cout, 3, out)
+        return rc, dict(zip(("ok", "ns", "blocks", "tiles_per_plane", "slots", "slab_rows"), list(out)))
+
+    rc, p = plan(45, 54, 45, 32, 64)                      # conv2.3 forward
+    assert rc == 0 and (p["ns"], p["blocks"], p["tiles_per_plane"]) == (1, 1, 20) and p["slots"] >= 4
+    rc, p = plan(45, 54, 45, 32, 32)                      # conv2.0 forward / dgrad
+    assert rc == 0 and (p["ns"], p["blocks"], p["tiles_per_plane"]) == (0, 1, 20)
+    rc, p = plan(45, 54, 45, 64, 32)                      # conv2.3 dgrad
+    assert rc == 0 and (p["ns"], p["blocks"]) == (0, 1)
+    rc, p = plan(22, 27, 22, 64, 128)                     # conv3.3 forward: four 32-channel slices per tower
+    assert rc == 0 and (p["ns"], p["blocks"]) == (0, 4)
+    assert plan(22, 27, 22, 128, 64)[0] != 0              # Cin = 128: the streamed-weight kernel's layer
+    monkeypatch.setenv("TMF_COL_NS", "0")
+    rc, p = plan(45, 54, 45, 32, 64)
+    assert rc == 0 and (p["ns"], p["blocks"]) == (0, 2)

@@ -75,6 +75,7 @@ PLAIN = {"tmf_last_error": (C.c_char_p, []), "tmf_version": (_i, []), "tmf_check
          "tmf_launch_count": (_i64, []), "tmf_set_pdl": (_i, [_i]), "tmf_attn_impl_default": (_i, []), "tmf_get_pdl": (_i, []), "tmf_conv3d_supported": (_i, [_i] * 8),
          "tmf_conv3d_wgrad_workspace_bytes": (_i64, [_i] * 9),
          "tmf_conv3d_umma_plan_info": (_i, [_i] * 8 + [C.POINTER(C.c_int)]),
+         "tmf_conv3d_col_plan_info": (_i, [_i] * 7 + [C.POINTER(C.c_int)]),
          "tmf_conv1_bwd_fused_workspace_bytes": (_i64, [_i] * 6), "tmf_conv1_wgrad_workspace_bytes": (_i64, [_i] * 4), "tmf_line_conv_wgrad_workspace_bytes": (_i64, [_i, _i]), "tmf_adam_chunk_bytes": (_i, [])}
 
 _lib = None

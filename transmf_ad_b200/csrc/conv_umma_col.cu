@@ -556,6 +556,16 @@ static ColPlan make_col_plan(int ng, int D, int H, int W, int cin, int cout, int
 
 using namespace tmf;
 
+// host-only introspection of the column kernel's launch plan (tests / DESIGN.md): out6 = {ok, non-stacked variant, Cout blocks per
+// tower, tiles per plane, ring slots, slab rows}
+extern "C" int tmf_conv3d_col_plan_info(int ng, int D, int H, int W, int cin, int cout, int ksize, int* out6) {
+  const ColPlan pl = make_col_plan(ng, D, H, W, cin, cout, ksize);
+  if (out6 != nullptr) {
+    out6[0] = pl.ok ? 1 : 0; out6[1] = pl.ns; out6[2] = pl.nsplit; out6[3] = pl.NC; out6[4] = pl.S; out6[5] = pl.NH;
+  }
+  return pl.ok ? 0 : 1;
+}
+
 bool tmf_conv3d_fwd_col_supported(int ng, int D, int H, int W, int cin, int cout, int ksize) {
   if (getenv("TMF_DISABLE_UMMA") != nullptr || getenv("TMF_DISABLE_COL") != nullptr) return false;
   return make_col_plan(ng, D, H, W, cin, cout, ksize).ok;
